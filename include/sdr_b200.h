@@ -1,0 +1,175 @@
+/*
+ * sdr_b200.h -- C ABI of the B200-native FM receiver DSP path.
+ *
+ * This is the drop-in boundary.  The reference (mnigm2001/Software-Defined-Radio)
+ * has no FFI layer; its "operator API" for this path is the set of C++ free
+ * functions in include/filter.h:18-43 plus the process contract of
+ * src/project.cpp:385-500 (raw interleaved uint8 I/Q on stdin, native-endian
+ * int16 PCM on stdout, mode 0-3, 1|2 audio channels).  Every entry point below
+ * names the reference interface it replaces.  include/dropin/filter.h re-declares
+ * the reference's C++ prototypes on top of this ABI.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross the boundary;
+ *   - every function returns an int status: 0 (SDR_OK) or a negative SDR_ERR_*;
+ *     sdr_last_error() returns a thread-local message for the last failure;
+ *   - the caller owns every host buffer; the library owns device state;
+ *   - one sdr_pipeline handle must be driven by one thread at a time; distinct
+ *     handles are independent;
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     SDR_ERR_NO_DEVICE when no sm_100 CUDA device is usable.
+ *
+ * All arithmetic that the reference performs in float is performed on the device
+ * in the same order with the same roundings (separate multiply and add, IEEE
+ * division, glibc-identical atan2f/sincosf/cosf), so results are bit-identical
+ * to the reference built with g++ -O3 on x86-64/glibc 2.39.
+ */
+#ifndef SDR_B200_H
+#define SDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDR_OK 0
+#define SDR_ERR_INVALID -1   /* bad argument */
+#define SDR_ERR_NO_DEVICE -2 /* no usable sm_100 device / CUDA driver */
+#define SDR_ERR_CUDA -3      /* a CUDA call failed; see sdr_last_error() */
+#define SDR_ERR_NOMEM -4     /* host or device allocation failed */
+#define SDR_ERR_CAPACITY -5  /* request exceeds the capacity fixed at create time */
+
+/* Arithmetic variants of the batched pipeline. */
+#define SDR_VARIANT_EXACT 0 /* CUDA-core path, bit-identical to the reference */
+
+/* Intermediate signals that sdr_pipeline_tap can return (same numbering as the
+ * oracle, oracle/fm_oracle.h).  Names follow src/project.cpp's variables. */
+#define SDR_TAP_I_FILT 0        /* project.cpp:111  */
+#define SDR_TAP_Q_FILT 1        /* project.cpp:121  */
+#define SDR_TAP_DEMOD 2         /* project.cpp:128  fm_demod */
+#define SDR_TAP_ALLPASS 3       /* project.cpp:194  audio_allpass */
+#define SDR_TAP_STEREO_FILT 4   /* project.cpp:202  stereo_filt */
+#define SDR_TAP_CARRIER_FILT 5  /* project.cpp:207  carrier_filt */
+#define SDR_TAP_NCO 6           /* project.cpp:237  PLL[0..N) as seen by the mixer */
+#define SDR_TAP_MIXER 7         /* project.cpp:246-248 */
+#define SDR_TAP_AUDIO_FILT 8    /* project.cpp:219/227/346/353 audio_filt */
+#define SDR_TAP_STEREO_FINAL 9  /* project.cpp:257/264 stereo_final */
+#define SDR_TAP_COUNT 10
+
+const char *sdr_version(void);
+const char *sdr_last_error(void);
+/* Number of usable sm_100 devices (0 when there is none; never fails). */
+int sdr_device_count(void);
+
+/* ------------------------------------------------------------------------ */
+/* Filter design (host; double precision internally, like the reference).   */
+/* ------------------------------------------------------------------------ */
+/* Replaces impulseResponseLPF(Fs, Fc, num_taps, h)   include/filter.h:24, src/filter.cpp:103-114 */
+int sdr_lpf_design(float Fs, float Fc, unsigned short ntaps, float *h);
+/* Replaces bandPass(Fs, Fb, Fe, N_taps, coeff)        include/filter.h:20, src/filter.cpp:83-99  */
+int sdr_bpf_design(float Fs, float Fb, float Fe, unsigned short ntaps, float *h);
+
+/* ------------------------------------------------------------------------ */
+/* Single stateful operators on HOST buffers (upload -> kernel -> download). */
+/* They exist so that the reference's filter.h functions can be re-pointed   */
+/* one by one; the batched pipeline below is the throughput path.            */
+/* `device` is a CUDA ordinal.  State buffers are updated in place with the  */
+/* reference's layouts so callers may mix these with the reference freely.   */
+/* ------------------------------------------------------------------------ */
+/* convolveFIR(y, x, h)                                filter.h:26, filter.cpp:118-130; y has nx+nh-1 */
+int sdr_convolve(int device, float *y, const float *x, size_t nx, const float *h, size_t nh);
+/* convolveBlockFIR(y, x, h, state)                    filter.h:28, filter.cpp:133-154; state nh-1, y nx */
+int sdr_fir_block(int device, float *y, const float *x, size_t nx, const float *h, size_t nh,
+                  float *state);
+/* convolveBlockFastFIR(y, x, h, state, decim, _)      filter.h:31, filter.cpp:158-188; y nx/decim.
+ * The reference's one-past-the-end iteration (filter.cpp:166) is not performed. */
+int sdr_fir_decim(int device, float *y, const float *x, size_t nx, const float *h, size_t nh,
+                  float *state, unsigned decim);
+/* convolveBlockResampleFIR(y, x, h, state, D, U, _)   filter.h:34, filter.cpp:191-223;
+ * state is the reference's zero-stuffed nh-1 vector; y has nx*U/D; gain is (1+U). */
+int sdr_fir_resample(int device, float *y, const float *x, size_t nx, const float *h, size_t nh,
+                     float *state, unsigned decim, unsigned upsamp);
+/* fmDemod(out, I, Q, prev_i, prev_q)                  filter.h:41, filter.cpp:248-266 */
+int sdr_fm_demod(int device, float *out, const float *I, const float *Q, size_t n, float *prev_i,
+                 float *prev_q);
+/* fmPLL(in, ncoOut, state, freq, Fs, ncoScale, phaseAdjust, normBandwidth)
+ *                                                     filter.h:22, filter.cpp:32-80; out n+1, state 6 */
+int sdr_pll(int device, const float *in, size_t n, float *out, float *state, float freq, float Fs,
+            float ncoScale, float phaseAdjust, float normBandwidth);
+/* allPass(in, state, out)                             filter.h:18, filter.cpp:14-29; state ns <= n */
+int sdr_allpass(int device, const float *in, size_t n, float *state, size_t ns, float *out);
+/* upsample(x, xu, U)                                  filter.h:37, filter.cpp:227-234; xu has nx*U */
+int sdr_upsample(int device, const float *x, size_t nx, float *xu, int up_rate);
+/* downsample(out, in, D)                              filter.h:39, filter.cpp:237-245; out ceil(n/D) */
+int sdr_downsample(int device, float *out, const float *in, size_t n, unsigned short ds);
+
+/* ------------------------------------------------------------------------ */
+/* Batched receiver pipeline: project.cpp's RF_FrontEnd + RF_MONO/RF_STEREO  */
+/* for `batch` independent captures, all state carried on the device.        */
+/* ------------------------------------------------------------------------ */
+typedef struct sdr_pipeline sdr_pipeline;
+
+typedef struct {
+  int mode;        /* 0..3: project.cpp:424-427 mode table */
+  int channels;    /* 1 mono (RF_MONO), 2 stereo (RF_STEREO) */
+  int rf_taps;     /* project.cpp:46 (13 as shipped) / threadMonoOnly.cpp:66 (151) */
+  int audio_taps;  /* per-phase count; x audio_upsamp in modes 2/3 (project.cpp:425-426) */
+  int stereo_taps; /* project.cpp:429 */
+  int batch;       /* independent captures processed per call (>= 1) */
+  int device;      /* CUDA ordinal */
+  int variant;     /* SDR_VARIANT_* */
+  uint64_t max_bytes_per_channel; /* capacity of one process call, per capture */
+} sdr_config;
+
+typedef struct {
+  int rf_Fs, if_Fs, audio_Fs;
+  int rf_decim, audio_decim, audio_upsamp; /* audio_upsamp is 1 in modes 0/1 */
+  int block_bytes;   /* the reference's block size (project.cpp:55-57) */
+  int granule_bytes; /* process() accepts any multiple of this per capture */
+  int pcm_per_granule; /* int16 values produced per granule (x2 when stereo) */
+} sdr_mode_info;
+
+int sdr_mode_lookup(int mode, int channels, sdr_mode_info *out);
+
+int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out);
+int sdr_pipeline_destroy(sdr_pipeline *p);
+/* Back to the reference's initial state (project.cpp:61-65,446-458). */
+int sdr_pipeline_reset(sdr_pipeline *p);
+/* Copies every carried state of capture `src` over capture `dst` (used to
+ * restart / fork a capture; no reference equivalent). */
+int sdr_pipeline_copy_state(sdr_pipeline *p, int dst, int src);
+
+/* Number of int16 values produced per capture for nbytes_per_channel input. */
+int sdr_pipeline_pcm_count(const sdr_pipeline *p, size_t nbytes_per_channel, size_t *n_pcm);
+
+/* Device-resident form.  d_iq is [batch][iq_stride_bytes] uint8 interleaved I,Q
+ * in device memory (only the first nbytes_per_channel of each row are read);
+ * d_pcm is [batch][pcm_stride] int16 (mono) or L,R interleaved (stereo).
+ * `stream` is a cudaStream_t (NULL = default stream); the call only enqueues. */
+int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq, size_t iq_stride_bytes,
+                                size_t nbytes_per_channel, int16_t *d_pcm, size_t pcm_stride,
+                                void *stream);
+
+/* Host form (the call a user of the reference's `project` would make for a
+ * batch): uploads in slices over pinned double buffers on two streams, runs the
+ * pipeline, downloads PCM, and returns when pcm is complete. */
+int sdr_pipeline_process_host(sdr_pipeline *p, const uint8_t *iq, size_t iq_stride_bytes,
+                              size_t nbytes_per_channel, int16_t *pcm, size_t pcm_stride);
+
+/* Keep (1) or drop (0, default) the float intermediates of the NEXT process
+ * calls so that sdr_pipeline_tap can return them (costs extra HBM traffic). */
+int sdr_pipeline_keep_taps(sdr_pipeline *p, int keep);
+/* Copies intermediate `stage` of capture `channel` from the last process call
+ * to host memory; *n receives the element count (dst may be NULL to query). */
+int sdr_pipeline_tap(sdr_pipeline *p, int stage, int channel, float *dst, size_t cap, size_t *n);
+
+/* Number of kernels this handle has launched since creation / last reset of the
+ * counter (bench.py reports it as gpu_launches). */
+int sdr_pipeline_launch_count(sdr_pipeline *p, uint64_t *count, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDR_B200_H */

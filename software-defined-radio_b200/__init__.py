@@ -1,0 +1,279 @@
+"""Python binding of the B200-native FM receiver DSP path (ctypes over the C ABI).
+
+The product is the shared library ``libsdr_b200.so`` (CUDA kernels for sm_100a behind
+``include/sdr_b200.h``); this module only marshals numpy arrays / raw device pointers into it
+for the tests and the benchmark.  There is no CPU fallback: if the library is missing, or no
+sm_100 device is present, the calls raise.
+
+The function names mirror the reference's ``include/filter.h`` (file:line cited per function in
+``include/sdr_b200.h``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsdr_b200.so")
+
+TAP_NAMES = ["i_filt", "q_filt", "demod", "allpass", "stereo_filt", "carrier_filt", "nco",
+             "mixer", "audio_filt", "stereo_final"]
+
+VARIANT_EXACT = 0
+
+
+class SdrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sdr_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("mode", C.c_int), ("channels", C.c_int), ("rf_taps", C.c_int),
+                ("audio_taps", C.c_int), ("stereo_taps", C.c_int), ("batch", C.c_int),
+                ("device", C.c_int), ("variant", C.c_int), ("max_bytes_per_channel", C.c_uint64)]
+
+
+class ModeInfo(C.Structure):
+    _fields_ = [("rf_Fs", C.c_int), ("if_Fs", C.c_int), ("audio_Fs", C.c_int),
+                ("rf_decim", C.c_int), ("audio_decim", C.c_int), ("audio_upsamp", C.c_int),
+                ("block_bytes", C.c_int), ("granule_bytes", C.c_int), ("pcm_per_granule", C.c_int)]
+
+
+_f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+
+# name -> (restype, argtypes): every symbol include/sdr_b200.h declares
+ABI = {
+    "sdr_version": (C.c_char_p, []),
+    "sdr_last_error": (C.c_char_p, []),
+    "sdr_device_count": (C.c_int, []),
+    "sdr_lpf_design": (C.c_int, [C.c_float, C.c_float, C.c_ushort, _f32]),
+    "sdr_bpf_design": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_ushort, _f32]),
+    "sdr_convolve": (C.c_int, [C.c_int, _f32, _f32, C.c_size_t, _f32, C.c_size_t]),
+    "sdr_fir_block": (C.c_int, [C.c_int, _f32, _f32, C.c_size_t, _f32, C.c_size_t, _f32]),
+    "sdr_fir_decim": (C.c_int, [C.c_int, _f32, _f32, C.c_size_t, _f32, C.c_size_t, _f32, C.c_uint]),
+    "sdr_fir_resample": (C.c_int, [C.c_int, _f32, _f32, C.c_size_t, _f32, C.c_size_t, _f32,
+                                   C.c_uint, C.c_uint]),
+    "sdr_fm_demod": (C.c_int, [C.c_int, _f32, _f32, _f32, C.c_size_t, C.POINTER(C.c_float),
+                               C.POINTER(C.c_float)]),
+    "sdr_pll": (C.c_int, [C.c_int, _f32, C.c_size_t, _f32, _f32, C.c_float, C.c_float, C.c_float,
+                          C.c_float, C.c_float]),
+    "sdr_allpass": (C.c_int, [C.c_int, _f32, C.c_size_t, _f32, C.c_size_t, _f32]),
+    "sdr_upsample": (C.c_int, [C.c_int, _f32, C.c_size_t, _f32, C.c_int]),
+    "sdr_downsample": (C.c_int, [C.c_int, _f32, _f32, C.c_size_t, C.c_ushort]),
+    "sdr_mode_lookup": (C.c_int, [C.c_int, C.c_int, C.POINTER(ModeInfo)]),
+    "sdr_pipeline_create": (C.c_int, [C.POINTER(Config), C.POINTER(_vp)]),
+    "sdr_pipeline_destroy": (C.c_int, [_vp]),
+    "sdr_pipeline_reset": (C.c_int, [_vp]),
+    "sdr_pipeline_copy_state": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "sdr_pipeline_pcm_count": (C.c_int, [_vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sdr_pipeline_process_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_size_t, _vp]),
+    "sdr_pipeline_process_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_size_t]),
+    "sdr_pipeline_keep_taps": (C.c_int, [_vp, C.c_int]),
+    "sdr_pipeline_tap": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sdr_pipeline_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libsdr_b200.so (built by build.py / __graft_entry__.build()); fail loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SdrError(-2, f"{LIB_PATH} is missing: run `python __graft_entry__.py build` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise SdrError(rc, lib().sdr_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    return int(lib().sdr_device_count())
+
+
+def mode_info(mode: int, channels: int = 1) -> ModeInfo:
+    mi = ModeInfo()
+    _check(lib().sdr_mode_lookup(mode, channels, C.byref(mi)))
+    return mi
+
+
+# ---- filter.h-shaped single operators (numpy in / numpy out) -------------------------------
+def impulseResponseLPF(Fs: float, Fc: float, num_taps: int) -> np.ndarray:
+    h = np.zeros(num_taps, np.float32)
+    _check(lib().sdr_lpf_design(Fs, Fc, num_taps, h))
+    return h
+
+
+def bandPass(Fs: float, Fb: float, Fe: float, num_taps: int) -> np.ndarray:
+    h = np.zeros(num_taps, np.float32)
+    _check(lib().sdr_bpf_design(Fs, Fb, Fe, num_taps, h))
+    return h
+
+
+def _f(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def convolveFIR(x, h, device: int = 0) -> np.ndarray:
+    x, h = _f(x), _f(h)
+    y = np.zeros(x.size + h.size - 1, np.float32)
+    _check(lib().sdr_convolve(device, y, x, x.size, h, h.size))
+    return y
+
+
+def convolveBlockFIR(x, h, state: np.ndarray, device: int = 0) -> np.ndarray:
+    """state (float32, len(h)-1) is updated in place, as in the reference."""
+    x, h = _f(x), _f(h)
+    y = np.zeros(x.size, np.float32)
+    _check(lib().sdr_fir_block(device, y, x, x.size, h, h.size, state))
+    return y
+
+
+def convolveBlockFastFIR(x, h, state: np.ndarray, decim: int, device: int = 0) -> np.ndarray:
+    x, h = _f(x), _f(h)
+    y = np.zeros(x.size // decim, np.float32)
+    _check(lib().sdr_fir_decim(device, y, x, x.size, h, h.size, state, decim))
+    return y
+
+
+def convolveBlockResampleFIR(x, h, state: np.ndarray, decim: int, upsamp: int,
+                             device: int = 0) -> np.ndarray:
+    x, h = _f(x), _f(h)
+    y = np.zeros(x.size * upsamp // decim, np.float32)
+    _check(lib().sdr_fir_resample(device, y, x, x.size, h, h.size, state, decim, upsamp))
+    return y
+
+
+def fmDemod(I, Q, prev_i: float, prev_q: float, device: int = 0):
+    I, Q = _f(I), _f(Q)
+    out = np.zeros(I.size, np.float32)
+    pi, pq = C.c_float(prev_i), C.c_float(prev_q)
+    _check(lib().sdr_fm_demod(device, out, I, Q, I.size, C.byref(pi), C.byref(pq)))
+    return out, pi.value, pq.value
+
+
+def fmPLL(pll_in, state: np.ndarray, freq, Fs, ncoScale=1.0, phaseAdjust=0.0,
+          normBandwidth=0.01, device: int = 0) -> np.ndarray:
+    """state (float32[6]) is updated in place; returns ncoOut with len(pll_in)+1 entries."""
+    x = _f(pll_in)
+    out = np.zeros(x.size + 1, np.float32)
+    _check(lib().sdr_pll(device, x, x.size, out, state, freq, Fs, ncoScale, phaseAdjust,
+                         normBandwidth))
+    return out
+
+
+def allPass(x, state: np.ndarray, device: int = 0) -> np.ndarray:
+    x = _f(x)
+    out = np.zeros(x.size, np.float32)
+    _check(lib().sdr_allpass(device, x, x.size, state, state.size, out))
+    return out
+
+
+def upsample(x, up_rate: int, device: int = 0) -> np.ndarray:
+    x = _f(x)
+    out = np.zeros(x.size * up_rate, np.float32)
+    _check(lib().sdr_upsample(device, x, x.size, out, up_rate))
+    return out
+
+
+def downsample(x, ds: int, device: int = 0) -> np.ndarray:
+    x = _f(x)
+    out = np.zeros((x.size + ds - 1) // ds, np.float32)
+    _check(lib().sdr_downsample(device, out, x, x.size, ds))
+    return out
+
+
+# ---- batched pipeline ------------------------------------------------------------------------
+class Pipeline:
+    """project.cpp's receiver for ``batch`` independent captures on one GPU."""
+
+    def __init__(self, mode=0, channels=1, rf_taps=151, audio_taps=101, stereo_taps=151, batch=1,
+                 device=0, variant=VARIANT_EXACT, max_bytes_per_channel=0):
+        self.cfg = Config(mode, channels, rf_taps, audio_taps, stereo_taps, batch, device, variant,
+                          max_bytes_per_channel)
+        self.info = mode_info(mode, channels)
+        self._h = _vp()
+        _check(lib().sdr_pipeline_create(C.byref(self.cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sdr_pipeline_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def batch(self) -> int:
+        return self.cfg.batch
+
+    def reset(self):
+        _check(lib().sdr_pipeline_reset(self._h))
+
+    def keep_taps(self, keep=True):
+        _check(lib().sdr_pipeline_keep_taps(self._h, 1 if keep else 0))
+
+    def pcm_count(self, nbytes: int) -> int:
+        n = C.c_size_t(0)
+        _check(lib().sdr_pipeline_pcm_count(self._h, nbytes, C.byref(n)))
+        return n.value
+
+    def launch_count(self, reset=False) -> int:
+        n = C.c_uint64(0)
+        _check(lib().sdr_pipeline_launch_count(self._h, C.byref(n), 1 if reset else 0))
+        return n.value
+
+    def process_host(self, iq: np.ndarray, pcm: np.ndarray | None = None) -> np.ndarray:
+        """iq: uint8 [batch, nbytes] (host).  Returns int16 [batch, n_pcm]."""
+        iq = np.ascontiguousarray(iq, np.uint8)
+        if iq.ndim == 1:
+            iq = iq[None, :]
+        assert iq.shape[0] == self.batch, "first dimension must equal the batch"
+        nbytes = iq.shape[1]
+        n_pcm = self.pcm_count(nbytes)
+        if pcm is None:
+            pcm = np.zeros((self.batch, n_pcm), np.int16)
+        _check(lib().sdr_pipeline_process_host(self._h, iq.ctypes.data, iq.strides[0], nbytes,
+                                               pcm.ctypes.data, pcm.strides[0] // 2))
+        return pcm
+
+    def process_host_ptr(self, iq_ptr: int, iq_stride: int, nbytes: int, pcm_ptr: int,
+                         pcm_stride: int):
+        _check(lib().sdr_pipeline_process_host(self._h, iq_ptr, iq_stride, nbytes, pcm_ptr,
+                                               pcm_stride))
+
+    def process_device(self, d_iq_ptr: int, iq_stride: int, nbytes: int, d_pcm_ptr: int,
+                       pcm_stride: int, stream: int = 0):
+        """Raw device pointers (e.g. torch ``tensor.data_ptr()``); only enqueues on ``stream``."""
+        _check(lib().sdr_pipeline_process_device(self._h, d_iq_ptr, iq_stride, nbytes, d_pcm_ptr,
+                                                 pcm_stride, stream))
+
+    def tap(self, name: str, channel: int = 0) -> np.ndarray:
+        stage = TAP_NAMES.index(name)
+        n = C.c_size_t(0)
+        _check(lib().sdr_pipeline_tap(self._h, stage, channel, None, 0, C.byref(n)))
+        out = np.zeros(n.value, np.float32)
+        _check(lib().sdr_pipeline_tap(self._h, stage, channel, out.ctypes.data, out.size, C.byref(n)))
+        return out

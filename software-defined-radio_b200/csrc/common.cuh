@@ -1,0 +1,67 @@
+// common.cuh -- shared device/host helpers for the B200 FM receiver kernels.
+//
+// Arithmetic contract: the reference (src/filter.cpp) is built for baseline
+// x86-64, so every float multiply and add rounds separately (mulss/addss, no
+// FMA), division is IEEE and denormals are kept.  The helpers below spell that
+// out with round-to-nearest intrinsics so that no compiler flag can contract
+// them; the library is additionally compiled with -fmad=false.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+namespace sdr {
+
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+// acc + h*x with two roundings: one step of the reference's FIR inner loops
+// (filter.cpp:142-144,169-174,202-207).
+__device__ __forceinline__ float xmac(float acc, float h, float x) {
+  return __fadd_rn(acc, __fmul_rn(h, x));
+}
+
+// (u8 - 128) as an exact float without an integer->float conversion: the byte is
+// placed in the low mantissa bits of 2^23 and the bias is subtracted.
+__device__ __forceinline__ float u8_centered(uint32_t byte) {
+  return __fsub_rn(__uint_as_float(0x4B000000u | byte), 8388736.0f);
+}
+// iofunc.cpp:128-135: float((u8-128)/128.0); exact, so the power-of-two scaling
+// may be applied to the byte or (as the fused kernels do) to the filtered sum.
+__device__ __forceinline__ float u8_to_unit(uint32_t byte) {
+  return __fmul_rn(u8_centered(byte), 0.0078125f);
+}
+
+// threadMonoOnly.cpp:185-190: NaN -> 0, else static_cast<short>(v*16384).  On
+// x86-64 the cast is cvttss2si (32-bit, "integer indefinite" 0x80000000 when out
+// of range) followed by a 16-bit truncation; reproduce exactly that.
+__device__ __forceinline__ int16_t pcm16(float v) {
+  if (v != v) return 0;
+  float t = __fmul_rn(v, 16384.0f);
+  int32_t i = (t >= -2147483648.0f && t < 2147483648.0f) ? __float2int_rz(t) : INT32_MIN;
+  return (int16_t)(uint16_t)((uint32_t)i & 0xffffu);
+}
+
+// fmDemod, filter.cpp:254-260, one sample.
+__device__ __forceinline__ float fm_demod_one(float i, float q, float pi, float pq) {
+  float den = xadd(xmul(i, i), xmul(q, q));
+  if (den == 0.0f) return 0.0f;
+  float num = xsub(xmul(i, xsub(q, pq)), xmul(q, xsub(i, pi)));
+  return xdiv(num, den);
+}
+
+// ---- host-side error plumbing -------------------------------------------
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+}  // namespace sdr
+
+#define SDR_CUDA(call)                                                  \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return sdr::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)

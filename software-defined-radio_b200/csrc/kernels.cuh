@@ -1,0 +1,665 @@
+// kernels.cuh -- sm_100a kernels of the FM receiver DSP path (exact variant).
+//
+// Layout in HBM (all channel-major, one row per capture):
+//   iq      [B][iq_stride]            uint8, interleaved I,Q (caller's buffer)
+//   rf_hist [B][2*HR]                 uint8, last HR I/Q pairs of the previous call
+//   demod   [B][HD + n_if (+pad)]     float, HD-sample history prefix then this call's samples
+//   stf     [B][HA + n_if (+pad)]     float, stereo band-pass output, history-prefixed
+//   car     [B][n_if]                 float, pilot band-pass output
+//   nco     [B][HA + n_if + 1 (+pad)] float, PLL output delayed by one sample (what the
+//                                     reference's mixer indexes, project.cpp:246-248)
+//   pcm     [B][pcm_stride]           int16 (mono) or L,R interleaved (stereo)
+// A history prefix plays the role of the reference's per-filter `state` vectors
+// (project.cpp:29-36,61-65): the last samples of the previous call are kept in
+// front of the current ones, so every FIR reads one contiguous window and no
+// kernel branches on "previous block or this block" (filter.cpp:141-145).
+//
+// Every FIR accumulates exactly like the reference: float accumulator from +0,
+// taps in ascending order, separately rounded multiply and add.
+#pragma once
+
+#include "common.cuh"
+#include "libm_exact.cuh"
+
+namespace sdr {
+
+constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Taps travel as a kernel parameter: with the tap index a compile-time constant
+// after unrolling, every tap is a constant-bank operand of its FMUL and costs no
+// load instruction and no register.
+template <int T>
+struct TapArray {
+  float h[round_up(T, 4)];
+};
+
+// ---------------------------------------------------------------------------
+// Register-tiled FIR core.  One thread produces R consecutive outputs of a
+// decimate-by-D, T-tap FIR from a window in shared memory.  `w` points at the
+// sample with index (first_output*D - HALO) and must be 16-byte aligned; the
+// window is walked from the newest sample to the oldest so that each accumulator
+// sees its taps in ascending order (n = r*D - e grows as e falls).
+// ---------------------------------------------------------------------------
+template <int T, int D, int R, int HALO>
+__device__ __forceinline__ void fir_window(const float *__restrict__ w, const TapArray<T> &taps,
+                                           float (&acc)[R]) {
+  static_assert(HALO % 4 == 0 && HALO >= T - 1, "halo must cover the filter and be float4-aligned");
+  constexpr int NEWEST = (R - 1) * D;              // newest sample used, relative to first output
+  constexpr int C_HI = (HALO + NEWEST) / 4;        // chunk holding the newest sample
+  constexpr int C_LO = (HALO - (T - 1)) / 4;       // chunk holding the oldest sample
+#pragma unroll
+  for (int c = C_HI; c >= C_LO; --c) {
+    const float4 v = *reinterpret_cast<const float4 *>(w + 4 * c);
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      const int e = 4 * c + j - HALO;
+      const float xv = (j == 0) ? v.x : (j == 1) ? v.y : (j == 2) ? v.z : v.w;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int n = r * D - e;
+        if (n >= 0 && n < T) acc[r] = xmac(acc[r], taps.h[n], xv);
+      }
+    }
+  }
+}
+
+// Same sum for ONE output with a run-time loop (used once per segment for the
+// sample that precedes the segment; not performance relevant).
+template <int T>
+__device__ __forceinline__ float fir_single(const float *__restrict__ newest,
+                                            const TapArray<T> &taps) {
+  float acc = 0.0f;
+#pragma unroll 1
+  for (int n = 0; n < T; ++n) acc = xmac(acc, taps.h[n], newest[-n]);
+  return acc;
+}
+
+// ---------------------------------------------------------------------------
+// K1: RF front end.  uint8 I/Q -> (u8-128)/128 -> low-pass + decimate (I and Q)
+// -> FM discriminator.  Replaces readStdinBlockData (iofunc.cpp:128-135), the
+// de-interleave (project.cpp:101-105), two convolveBlockFastFIR calls (:111,:121)
+// and fmDemod (:128).
+// Grid: (segments, B).  Each CTA walks its segment tile by tile; a tile is
+// NT*R outputs = NT*R*D input pairs staged in shared memory as floats.
+// ---------------------------------------------------------------------------
+struct RfArgs {
+  const uint8_t *iq;       // [B][iq_stride]
+  size_t iq_stride;        // bytes
+  const uint8_t *hist;     // [B][2*HR]   (HR = rf_hist_len)
+  int rf_hist_len;         // HR
+  const float *prev_in;    // [B][2]  I,Q of the last output of the previous call
+  float *prev_out;         // [B][2]
+  float *demod;            // [B][demod_stride], sample 0 at demod_off
+  size_t demod_stride;
+  int demod_off;
+  float *i_filt, *q_filt;  // optional [B][tap_stride]
+  size_t tap_stride;
+  long long n_rf;          // input pairs per capture in this call
+  int n_if;                // outputs per capture in this call
+  int outs_per_seg;        // multiple of the tile size
+};
+
+template <int T, int D>
+__device__ __forceinline__ void rf_fetch_pair(const RfArgs &a, const uint8_t *row,
+                                              const uint8_t *hrow, long long i, float &fi,
+                                              float &fq) {
+  uint32_t bi = 128, bq = 128;
+  if (i < 0) {
+    long long k = a.rf_hist_len + i;
+    if (k >= 0) {
+      bi = hrow[2 * k];
+      bq = hrow[2 * k + 1];
+    }
+  } else if (i < a.n_rf) {
+    bi = row[2 * i];
+    bq = row[2 * i + 1];
+  }
+  fi = u8_centered(bi);
+  fq = u8_centered(bq);
+}
+
+template <int T, int D, int R, int NT>
+struct RfCfg {
+  static constexpr int HALO = round_up(T - 1 + D, 8);
+  static constexpr int TILE_OUT = NT * R;
+  static constexpr int TILE_IN = TILE_OUT * D;
+  static constexpr int ROW = HALO + TILE_IN + 8;  // floats per component in smem
+  static constexpr size_t SMEM = (size_t)ROW * 2 * sizeof(float);
+};
+
+template <int T, int D, int R, int NT>
+__global__ void __launch_bounds__(NT)
+k_rf_demod(const RfArgs a, const __grid_constant__ TapArray<T> taps) {
+  using Cfg = RfCfg<T, D, R, NT>;
+  constexpr int HALO = Cfg::HALO;
+  extern __shared__ __align__(16) float smem[];
+  float *xi = smem;
+  float *xq = smem + Cfg::ROW;
+  __shared__ float edge_i[NT + 1], edge_q[NT + 1];
+
+  const int t = threadIdx.x;
+  const int b = blockIdx.y;
+  const int o_begin = blockIdx.x * a.outs_per_seg;
+  const int o_end = min(o_begin + a.outs_per_seg, a.n_if);
+  if (o_begin >= o_end) return;
+  const uint8_t *row = a.iq + (size_t)b * a.iq_stride;
+  const uint8_t *hrow = a.hist + (size_t)b * 2 * a.rf_hist_len;
+  const bool row_aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+
+  for (int o0 = o_begin; o0 < o_end; o0 += Cfg::TILE_OUT) {
+    __syncthreads();  // everyone is done with the previous tile's smem and edges
+    if (t == 0 && o0 != o_begin) {
+      edge_i[0] = edge_i[NT];
+      edge_q[0] = edge_q[NT];
+    }
+    // ---- stage [o0*D - HALO, o0*D + TILE_IN) as centred floats ----
+    const long long s0 = (long long)o0 * D - HALO;
+    constexpr int NCHUNK = (HALO + Cfg::TILE_IN) / 8;
+    for (int q = t; q < NCHUNK; q += NT) {
+      const long long i = s0 + 8ll * q;
+      float fi[8], fq[8];
+      if (row_aligned && i >= 0 && i + 8 <= a.n_rf) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + 2 * i));
+        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          fi[2 * k] = u8_centered(wds[k] & 0xffu);
+          fq[2 * k] = u8_centered((wds[k] >> 8) & 0xffu);
+          fi[2 * k + 1] = u8_centered((wds[k] >> 16) & 0xffu);
+          fq[2 * k + 1] = u8_centered(wds[k] >> 24);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rf_fetch_pair<T, D>(a, row, hrow, i + k, fi[k], fq[k]);
+      }
+      float4 *di = reinterpret_cast<float4 *>(xi + 8 * q);
+      float4 *dq = reinterpret_cast<float4 *>(xq + 8 * q);
+      di[0] = make_float4(fi[0], fi[1], fi[2], fi[3]);
+      di[1] = make_float4(fi[4], fi[5], fi[6], fi[7]);
+      dq[0] = make_float4(fq[0], fq[1], fq[2], fq[3]);
+      dq[1] = make_float4(fq[4], fq[5], fq[6], fq[7]);
+    }
+    __syncthreads();
+    // ---- I,Q of the output that precedes this segment (fmDemod's prev_i/prev_q) ----
+    if (o0 == o_begin && t < 2) {
+      float v;
+      if (o_begin == 0) {
+        v = a.prev_in[2 * b + t];
+      } else {
+        const float *src = (t == 0 ? xi : xq) + HALO - D;  // sample (o0-1)*D
+        v = xmul(fir_single<T>(src, taps), 0.0078125f);
+      }
+      (t == 0 ? edge_i : edge_q)[0] = v;
+    }
+    // ---- R outputs per thread for I and Q ----
+    float ai[R], aq[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) ai[r] = aq[r] = 0.0f;
+    fir_window<T, D, R, HALO>(xi + t * (R * D), taps, ai);
+    fir_window<T, D, R, HALO>(xq + t * (R * D), taps, aq);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // exact power-of-two scaling: (u8-128)/128
+      ai[r] = xmul(ai[r], 0.0078125f);
+      aq[r] = xmul(aq[r], 0.0078125f);
+    }
+    edge_i[t + 1] = ai[R - 1];
+    edge_q[t + 1] = aq[R - 1];
+    __syncthreads();
+    float pi = edge_i[t], pq = edge_q[t];
+    const int o = o0 + t * R;
+    float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (o + r < o_end) {
+        drow[o + r] = fm_demod_one(ai[r], aq[r], pi, pq);
+        if (a.i_filt) {
+          a.i_filt[(size_t)b * a.tap_stride + o + r] = ai[r];
+          a.q_filt[(size_t)b * a.tap_stride + o + r] = aq[r];
+        }
+        if (o + r == a.n_if - 1) {
+          a.prev_out[2 * b] = ai[r];
+          a.prev_out[2 * b + 1] = aq[r];
+        }
+      }
+      pi = ai[r];
+      pq = aq[r];
+    }
+  }
+}
+
+// Generic-taps fallback of K1, part 1: one thread per output, taps in shared
+// memory, run-time loops.  Writes I_filt/Q_filt (slot 0 of each row is prev).
+struct RfGenericArgs {
+  RfArgs a;
+  const float *h;  // [T]
+  int T, D;
+  float *iq_filt;  // [B][2][1 + n_if]: I row then Q row, slot 0 = previous output
+};
+
+static __global__ void k_rf_generic(const RfGenericArgs g) {
+  extern __shared__ float sh[];
+  for (int n = threadIdx.x; n < g.T; n += blockDim.x) sh[n] = g.h[n];
+  __syncthreads();
+  const RfArgs &a = g.a;
+  const int b = blockIdx.y;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= a.n_if) return;
+  const uint8_t *row = a.iq + (size_t)b * a.iq_stride;
+  const uint8_t *hrow = a.hist + (size_t)b * 2 * a.rf_hist_len;
+  float ai = 0.0f, aq = 0.0f;
+  const long long m = (long long)o * g.D;
+  for (int n = 0; n < g.T; ++n) {
+    float fi, fq;
+    rf_fetch_pair<0, 0>(a, row, hrow, m - n, fi, fq);
+    // the generic path applies /128 per sample, exactly as iofunc.cpp:133 does
+    ai = xmac(ai, sh[n], xmul(fi, 0.0078125f));
+    aq = xmac(aq, sh[n], xmul(fq, 0.0078125f));
+  }
+  float *irow = g.iq_filt + ((size_t)b * 2) * (a.n_if + 1);
+  float *qrow = irow + (a.n_if + 1);
+  irow[1 + o] = ai;
+  qrow[1 + o] = aq;
+  if (o == 0) {
+    irow[0] = a.prev_in[2 * b];
+    qrow[0] = a.prev_in[2 * b + 1];
+  }
+  if (o == a.n_if - 1) {
+    a.prev_out[2 * b] = ai;
+    a.prev_out[2 * b + 1] = aq;
+  }
+  if (a.i_filt) {
+    a.i_filt[(size_t)b * a.tap_stride + o] = ai;
+    a.q_filt[(size_t)b * a.tap_stride + o] = aq;
+  }
+}
+
+// Part 2 (also the stand-alone fmDemod operator, filter.cpp:248-266): element-wise
+// discriminator.  The one-sample state comes from the neighbouring lane by warp
+// shuffle; only lane 0 of each warp re-reads its predecessor from memory.
+static __global__ void k_fm_demod(const float *__restrict__ iq_filt, int n, float *__restrict__ out,
+                           size_t out_stride, int out_off) {
+  const int b = blockIdx.y;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const float *irow = iq_filt + ((size_t)b * 2) * (n + 1);
+  const float *qrow = irow + (n + 1);
+  const bool live = o < n;
+  float i = live ? irow[1 + o] : 0.0f, q = live ? qrow[1 + o] : 0.0f;
+  float pi = __shfl_up_sync(0xffffffffu, i, 1), pq = __shfl_up_sync(0xffffffffu, q, 1);
+  if ((threadIdx.x & 31) == 0 && live) {
+    pi = irow[o];
+    pq = qrow[o];
+  }
+  if (live) out[(size_t)b * out_stride + out_off + o] = fm_demod_one(i, q, pi, pq);
+}
+
+// ---------------------------------------------------------------------------
+// K3/K6 (modes 0/1): audio low-pass + decimate + PCM.  Mono: one input (demod).
+// Stereo: the mono path reads demod delayed by `delay` samples (allPass,
+// filter.cpp:14-29, is a pure delay), the stereo path reads the mixer
+// stereo_filt*nco*2 formed on the fly (project.cpp:246-248); outputs L = s+m,
+// R = m-s (project.cpp:277-280) as interleaved int16 (project.cpp:294-301).
+// ---------------------------------------------------------------------------
+struct AudioArgs {
+  const float *demod;  // [B][demod_stride], sample 0 at demod_off
+  size_t demod_stride;
+  int demod_off;
+  int delay;           // 0 mono; (stereo_taps-1)/2 stereo
+  const float *stf;    // stereo only: [B][stf_stride], sample 0 at hist_off
+  const float *nco;    // stereo only: same geometry as stf
+  size_t stf_stride, nco_stride;
+  int hist_off;
+  int16_t *pcm;        // [B][pcm_stride]
+  size_t pcm_stride;
+  float *audio_filt, *stereo_final;  // optional [B][tap_stride]
+  size_t tap_stride;
+  int n_out;           // audio samples per capture in this call
+  int outs_per_seg;
+};
+
+template <int T, int D, int R, int NT>
+struct AudioCfg {
+  static constexpr int HALO = round_up(T - 1, 4);
+  static constexpr int TILE_OUT = NT * R;
+  static constexpr int TILE_IN = TILE_OUT * D;
+  static constexpr int ROW = HALO + TILE_IN + 4;
+};
+
+template <int T, int D, int R, int NT, bool STEREO>
+__global__ void __launch_bounds__(NT)
+k_audio_fir(const AudioArgs a, const __grid_constant__ TapArray<T> taps) {
+  using Cfg = AudioCfg<T, D, R, NT>;
+  constexpr int HALO = Cfg::HALO;
+  extern __shared__ __align__(16) float smem[];
+  float *xm = smem;             // mono-path input
+  float *xs = smem + Cfg::ROW;  // stereo-path input (mixer)
+  const int t = threadIdx.x;
+  const int b = blockIdx.y;
+  const int o_begin = blockIdx.x * a.outs_per_seg;
+  const int o_end = min(o_begin + a.outs_per_seg, a.n_out);
+  const float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off - a.delay;
+  const float *srow = STEREO ? a.stf + (size_t)b * a.stf_stride + a.hist_off : nullptr;
+  const float *nrow = STEREO ? a.nco + (size_t)b * a.nco_stride + a.hist_off : nullptr;
+  const long long n_in = (long long)a.n_out * D;
+
+  for (int o0 = o_begin; o0 < o_end; o0 += Cfg::TILE_OUT) {
+    __syncthreads();
+    const long long s0 = (long long)o0 * D - HALO;
+    for (int q = t; q < HALO + Cfg::TILE_IN; q += NT) {
+      const long long i = s0 + q;
+      const bool ok = i < n_in;  // history prefix makes negative indices valid
+      xm[q] = ok ? drow[i] : 0.0f;
+      if (STEREO) xs[q] = ok ? xmul(xmul(srow[i], nrow[i]), 2.0f) : 0.0f;
+    }
+    __syncthreads();
+    float am[R], as[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) am[r] = as[r] = 0.0f;
+    fir_window<T, D, R, HALO>(xm + t * (R * D), taps, am);
+    if (STEREO) fir_window<T, D, R, HALO>(xs + t * (R * D), taps, as);
+    const int o = o0 + t * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (o + r < o_end) {
+        if (STEREO) {
+          const float L = xadd(as[r], am[r]), Rr = xsub(am[r], as[r]);
+          int16_t *p = a.pcm + (size_t)b * a.pcm_stride + 2 * (size_t)(o + r);
+          p[0] = pcm16(L);
+          p[1] = pcm16(Rr);
+          if (a.stereo_final) a.stereo_final[(size_t)b * a.tap_stride + o + r] = as[r];
+        } else {
+          a.pcm[(size_t)b * a.pcm_stride + o + r] = pcm16(am[r]);
+        }
+        if (a.audio_filt) a.audio_filt[(size_t)b * a.tap_stride + o + r] = am[r];
+      }
+    }
+  }
+}
+
+// Generic-taps form (modes 0/1 with unusual tap counts; also convolveBlockFIR /
+// convolveBlockFastFIR as stand-alone operators): one thread per output.
+struct FirGenericArgs {
+  const float *x;  // [B][x_stride], sample 0 at x_off (history prefix before it)
+  size_t x_stride;
+  int x_off;
+  const float *h;
+  int T, D;
+  float *y;  // [B][y_stride], output 0 at y_off
+  size_t y_stride;
+  int y_off;
+  int n_out;
+};
+
+static __global__ void k_fir_generic(const FirGenericArgs g) {
+  extern __shared__ float sh[];
+  for (int n = threadIdx.x; n < g.T; n += blockDim.x) sh[n] = g.h[n];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= g.n_out) return;
+  const float *x = g.x + (size_t)b * g.x_stride + g.x_off + (long long)o * g.D;
+  float acc = 0.0f;
+  for (int n = 0; n < g.T; ++n) acc = xmac(acc, sh[n], x[-n]);
+  g.y[(size_t)b * g.y_stride + g.y_off + o] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// K6r (modes 2/3): polyphase up/down resampler (convolveBlockResampleFIR,
+// filter.cpp:191-223).  Output j sits at upsampled position m = j*D: phase
+// p = m % U, newest input i0 = m / U, y = sum_k hp[p][k] * x[i0-k], then
+// y += y*U (the reference's (1+U) gain, filter.cpp:213).  hp is the phase-major
+// rearrangement hp[p][k] = h[p + k*U]; the zero-stuffed state of the reference
+// collapses to the TA-1 sample history prefix.
+// ---------------------------------------------------------------------------
+struct ResampleArgs {
+  AudioArgs a;
+  const float *hp;  // [U][TA]
+  int U, D, TA;
+};
+
+template <bool STEREO>
+static __global__ void k_audio_resample(const ResampleArgs g) {
+  const AudioArgs &a = g.a;
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n_out) return;
+  const long long m = (long long)j * g.D;
+  const int p = (int)(m % g.U);
+  const long long i0 = m / g.U;
+  const float *hp = g.hp + (size_t)p * g.TA;
+  const float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off - a.delay + i0;
+  float am = 0.0f, as = 0.0f;
+  if (STEREO) {
+    const float *srow = a.stf + (size_t)b * a.stf_stride + a.hist_off + i0;
+    const float *nrow = a.nco + (size_t)b * a.nco_stride + a.hist_off + i0;
+    for (int k = 0; k < g.TA; ++k) {
+      const float h = __ldg(hp + k);
+      am = xmac(am, h, drow[-k]);
+      as = xmac(as, h, xmul(xmul(srow[-k], nrow[-k]), 2.0f));
+    }
+    const float fu = (float)g.U;
+    am = xadd(am, xmul(am, fu));
+    as = xadd(as, xmul(as, fu));
+    const float L = xadd(as, am), R = xsub(am, as);
+    int16_t *q = a.pcm + (size_t)b * a.pcm_stride + 2 * (size_t)j;
+    q[0] = pcm16(L);
+    q[1] = pcm16(R);
+    if (a.stereo_final) a.stereo_final[(size_t)b * a.tap_stride + j] = as;
+  } else {
+    for (int k = 0; k < g.TA; ++k) am = xmac(am, __ldg(hp + k), drow[-k]);
+    am = xadd(am, xmul(am, (float)g.U));
+    a.pcm[(size_t)b * a.pcm_stride + j] = pcm16(am);
+  }
+  if (a.audio_filt) a.audio_filt[(size_t)b * a.tap_stride + j] = am;
+}
+
+// Stand-alone resampler on float in/out (no PCM), for sdr_fir_resample.
+struct ResampleOpArgs {
+  const float *x;  // sample 0 at x_off, TA-1 history before it
+  int x_off;
+  const float *hp;
+  int U, D, TA;
+  float *y;
+  int n_out;
+};
+static __global__ void k_resample_op(const ResampleOpArgs g) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.n_out) return;
+  const long long m = (long long)j * g.D;
+  const int p = (int)(m % g.U);
+  const float *x = g.x + g.x_off + m / g.U;
+  const float *hp = g.hp + (size_t)p * g.TA;
+  float acc = 0.0f;
+  for (int k = 0; k < g.TA; ++k) acc = xmac(acc, hp[k], x[-k]);
+  g.y[j] = xadd(acc, xmul(acc, (float)g.U));
+}
+
+// Mono/stereo PCM epilogue for the generic-taps path (float audio -> int16).
+static __global__ void k_pcm_pack(const float *mono, const float *stereo, size_t in_stride, int n,
+                           int16_t *pcm, size_t pcm_stride) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const float m = mono[(size_t)b * in_stride + j];
+  if (stereo) {
+    const float s = stereo[(size_t)b * in_stride + j];
+    pcm[(size_t)b * pcm_stride + 2 * (size_t)j] = pcm16(xadd(s, m));
+    pcm[(size_t)b * pcm_stride + 2 * (size_t)j + 1] = pcm16(xsub(m, s));
+  } else {
+    pcm[(size_t)b * pcm_stride + j] = pcm16(m);
+  }
+}
+
+// mixer = stereo_filt * nco * 2 into a history-prefixed row (generic path / taps).
+static __global__ void k_mixer(const float *stf, size_t stf_stride, const float *nco, size_t nco_stride,
+                        int off, int n_total, float *out, size_t out_stride) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  out[(size_t)b * out_stride + i] =
+      xmul(xmul(stf[(size_t)b * stf_stride + off + i], nco[(size_t)b * nco_stride + off + i]), 2.0f);
+}
+
+// Row-wise copy used to keep intermediates that the carry would overwrite.
+static __global__ void k_copy_rows(const float *src, size_t src_stride, int src_off, float *dst,
+                            size_t dst_stride, int n) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[(size_t)b * dst_stride + i] = src[(size_t)b * src_stride + src_off + i];
+}
+
+// ---------------------------------------------------------------------------
+// K4: the two stereo band-pass filters on one staged input tile
+// (convolveBlockFIR x2, project.cpp:202,207; filter.cpp:133-154).
+// ---------------------------------------------------------------------------
+struct BpfArgs {
+  const float *demod;
+  size_t demod_stride;
+  int demod_off;
+  float *stf;  // [B][stf_stride], output 0 at hist_off
+  size_t stf_stride;
+  int hist_off;
+  float *car;  // [B][car_stride]
+  size_t car_stride;
+  int n_if;
+  int outs_per_seg;
+};
+
+template <int T, int R, int NT>
+__global__ void __launch_bounds__(NT)
+k_bpf_dual(const BpfArgs a, const __grid_constant__ TapArray<T> h_stereo,
+           const __grid_constant__ TapArray<T> h_pilot) {
+  constexpr int HALO = round_up(T - 1, 4);
+  constexpr int TILE = NT * R;
+  __shared__ __align__(16) float xs[HALO + TILE + 4];
+  const int t = threadIdx.x;
+  const int b = blockIdx.y;
+  const int o_begin = blockIdx.x * a.outs_per_seg;
+  const int o_end = min(o_begin + a.outs_per_seg, a.n_if);
+  const float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
+  for (int o0 = o_begin; o0 < o_end; o0 += TILE) {
+    __syncthreads();
+    for (int q = t; q < HALO + TILE; q += NT) {
+      const int i = o0 - HALO + q;
+      xs[q] = (i < a.n_if) ? drow[i] : 0.0f;
+    }
+    __syncthreads();
+    float as[R], ap[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) as[r] = ap[r] = 0.0f;
+    fir_window<T, 1, R, HALO>(xs + t * R, h_stereo, as);
+    fir_window<T, 1, R, HALO>(xs + t * R, h_pilot, ap);
+    const int o = o0 + t * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (o + r < o_end) {
+        a.stf[(size_t)b * a.stf_stride + a.hist_off + o + r] = as[r];
+        a.car[(size_t)b * a.car_stride + o + r] = ap[r];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5: PLL + NCO (fmPLL, filter.cpp:32-80).  The recurrence is inherently
+// sequential, so one lane owns one capture and walks its samples in order.
+// The NCO output is written one slot late (slot k+1 at step k) which is exactly
+// the reference's ncoOut vector: ncoOut[0] is the last value of the previous
+// block (state[4]) and the mixer reads ncoOut[0..N) (project.cpp:246-248).
+// ---------------------------------------------------------------------------
+struct PllArgs {
+  const float *in;  // [B][in_stride]
+  size_t in_stride;
+  float *out;  // [B][out_stride]; step k writes out[out_off + k + 1]
+  size_t out_stride;
+  int out_off;
+  float *state;  // [B][8]: integrator, phaseEst, feedbackI, feedbackQ, lastOut, trigOffset
+  int n;
+  int batch;
+  float freq, Fs, ncoScale, phaseAdjust, normBandwidth;
+};
+
+static __global__ void k_pll(const PllArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.batch) return;
+  // filter.cpp:35-39
+  const float Kp = xmul(a.normBandwidth, 2.666f);
+  const float Ki = xmul(xmul(a.normBandwidth, a.normBandwidth), 3.555f);
+  float *st = a.state + (size_t)b * 8;
+  float integrator = st[0], phaseEst = st[1], fbI = st[2], fbQ = st[3], trigOffset = st[5];
+  const float *in = a.in + (size_t)b * a.in_stride;
+  float *out = a.out + (size_t)b * a.out_stride + a.out_off;
+  // filter.cpp:68: 2*PI*(freq/Fs) evaluated in double from the float quotient
+  const double w = __dmul_rn(6.283185307179586476925286766559, (double)xdiv(a.freq, a.Fs));
+  float last = st[4];
+  for (int k = 0; k < a.n; ++k) {
+    const float x = in[k];
+    const float eI = xmul(x, fbI);
+    const float eQ = xmul(x, -fbQ);
+    const float eD = atan2f_glibc(eQ, eI);
+    integrator = xadd(integrator, xmul(Ki, eD));
+    phaseEst = xadd(xadd(phaseEst, xmul(Kp, eD)), integrator);
+    trigOffset = xadd(trigOffset, 1.0f);
+    const float trigArg =
+        __double2float_rn(__dadd_rn(__dmul_rn(w, (double)trigOffset), (double)phaseEst));
+    sincosf_glibc(trigArg, fbQ, fbI);
+    last = cosf_glibc(xadd(xmul(trigArg, a.ncoScale), a.phaseAdjust));
+    out[k + 1] = last;
+  }
+  st[0] = integrator;
+  st[1] = phaseEst;
+  st[2] = fbI;
+  st[3] = fbQ;
+  st[4] = last;
+  st[5] = trigOffset;
+}
+
+// ---------------------------------------------------------------------------
+// Carry: after a call, move the tails that the next call needs into the history
+// prefixes (the reference's "prepare next state" loops, filter.cpp:148-153,
+// 183-187, 217-222) and rebuild the raw I/Q history.
+// ---------------------------------------------------------------------------
+struct CarryArgs {
+  // float rows: copy row[off_src .. off_src+len) -> row[0 .. len)
+  float *rows[3];
+  size_t strides[3];
+  int src_off[3];
+  int len[3];
+  // raw I/Q history
+  const uint8_t *iq;
+  size_t iq_stride;
+  uint8_t *hist;
+  int rf_hist_len;
+  long long n_rf;
+  float *prev_dst;
+  const float *prev_src;
+};
+
+static __global__ void k_carry(const CarryArgs c) {
+  extern __shared__ unsigned char stage[];
+  const int b = blockIdx.x;
+  const int t = threadIdx.x;
+  // 1. float tails.  Source and destination ranges may overlap when the call was
+  //    shorter than the history, so go through shared memory.
+  float *fstage = reinterpret_cast<float *>(stage);
+  for (int r = 0; r < 3; ++r) {
+    if (!c.rows[r]) continue;
+    float *row = c.rows[r] + (size_t)b * c.strides[r];
+    for (int i = t; i < c.len[r]; i += blockDim.x) fstage[i] = row[c.src_off[r] + i];
+    __syncthreads();
+    for (int i = t; i < c.len[r]; i += blockDim.x) row[i] = fstage[i];
+    __syncthreads();
+  }
+  // 2. raw history: the last HR pairs of (old history ++ this call's input)
+  const int HR = c.rf_hist_len;
+  uint8_t *hrow = c.hist + (size_t)b * 2 * HR;
+  const uint8_t *row = c.iq + (size_t)b * c.iq_stride;
+  for (int k = t; k < 2 * HR; k += blockDim.x) {
+    const long long byte = 2 * c.n_rf - 2 * HR + k;  // position in this call's input
+    stage[k] = (byte >= 0) ? row[byte] : hrow[2 * HR + byte];
+  }
+  __syncthreads();
+  for (int k = t; k < 2 * HR; k += blockDim.x) hrow[k] = stage[k];
+  if (t < 2) c.prev_dst[2 * b + t] = c.prev_src[2 * b + t];
+}
+
+}  // namespace sdr

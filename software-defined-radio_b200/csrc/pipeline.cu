@@ -1,0 +1,892 @@
+// pipeline.cu -- host side of the C ABI (include/sdr_b200.h): device buffers,
+// carried state, kernel selection and launch order for the batched receiver.
+//
+// Launch order per call (the reference's per-block order, project.cpp:80-149,
+// 178-309, 327-381, over an arbitrarily long span instead of one block):
+//   mono  : K1 rf+demod -> K3 audio (FIR or resampler) -> carry
+//   stereo: K1 rf+demod -> K4 dual band-pass -> K5 PLL -> K6 audio L/R -> carry
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sdr_b200.h"
+#include "design.h"
+#include "kernels.cuh"
+
+namespace sdr {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+  g_err = buf;
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return SDR_ERR_NO_DEVICE;
+  if (e == cudaErrorMemoryAllocation) return SDR_ERR_NOMEM;
+  return SDR_ERR_CUDA;
+}
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+static bool device_is_sm100(int dev) {
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return false;
+  return p.major == 10;
+}
+
+static int use_device(int dev) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(SDR_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (dev < 0 || dev >= n) return fail(SDR_ERR_INVALID, "device ordinal out of range");
+  if (!device_is_sm100(dev))
+    return fail(SDR_ERR_NO_DEVICE, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
+  SDR_CUDA(cudaSetDevice(dev));
+  return SDR_OK;
+}
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (!count) return SDR_OK;
+    SDR_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    return SDR_OK;
+  }
+  int zero(cudaStream_t s = nullptr) {
+    if (p) SDR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    return SDR_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+struct ModeRow {
+  int rf_Fs, if_Fs, audio_Fs, rf_decim, audio_decim, audio_upsamp, block_bytes;
+};
+// project.cpp:424-427 (mode table) and :55-57 (block sizes)
+static const ModeRow kModes[4] = {
+    {2400000, 240000, 48000, 10, 5, 1, 1024 * 10 * 5 * 2},
+    {1440000, 288000, 48000, 5, 6, 1, 1024 * 5 * 6 * 2},
+    {2400000, 240000, 44100, 10, 800, 147, 7 * 800 * 10 * 2},
+    {960000, 320000, 44100, 3, 3200, 441, 7 * 3200 * 3 * 2},
+};
+
+}  // namespace sdr
+
+using namespace sdr;
+
+struct sdr_pipeline {
+  sdr_config cfg;
+  ModeRow m;
+  bool stereo, resample;
+  int TA;     // audio taps per phase
+  int HR;     // raw I/Q history pairs
+  int HD;     // demod history prefix
+  int HA;     // stf/nco history prefix
+  int delay;  // all-pass delay (stereo), project.cpp:457
+  int granule_bytes, if_per_granule, pcm_per_granule;
+  size_t cap_if, cap_audio;  // per-capture capacities of one call
+  size_t demod_stride, stf_stride, nco_stride, car_stride, tap_if_stride, tap_audio_stride;
+  bool rf_fast, audio_fast, bpf_fast;  // specialised kernels available for these tap counts
+  std::vector<float> h_rf, h_audio, h_pilot, h_stereo, h_poly;
+  DevBuf<float> d_h_rf, d_h_audio, d_h_pilot, d_h_stereo, d_h_poly;
+  DevBuf<uint8_t> rf_hist;
+  DevBuf<float> prev, prev_new, demod, stf, car, nco, pll_state;
+  // optional intermediates (keep_taps or generic-taps path)
+  DevBuf<float> iq_filt, t_ifilt, t_qfilt, mix, t_audio, t_stfinal, t_nco, t_allpass;
+  bool keep_taps = false;
+  size_t last_n_if = 0, last_n_audio = 0;
+  uint64_t launches = 0;
+  // host staging for process_host
+  uint8_t *pin_in[2] = {nullptr, nullptr};
+  int16_t *pin_out[2] = {nullptr, nullptr};
+  DevBuf<uint8_t> d_in[2];
+  DevBuf<int16_t> d_out[2];
+  size_t slice_bytes = 0, slice_pcm = 0;
+  cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr},
+              ev_out[2] = {nullptr, nullptr};
+};
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+static int check_launch(sdr_pipeline *p, const char *name) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, name, __FILE__, __LINE__);
+  if (p) p->launches++;
+  return SDR_OK;
+}
+
+static int pick_segments(int n_out, int tile_out, int batch, int *outs_per_seg) {
+  const int n_tiles = (n_out + tile_out - 1) / tile_out;
+  int want = (1776 + batch - 1) / batch;  // ~ 148 SMs x 3 CTAs x 4 waves
+  want = std::max(1, std::min(want, n_tiles));
+  const int tiles_per_seg = (n_tiles + want - 1) / want;
+  *outs_per_seg = tiles_per_seg * tile_out;
+  return (n_tiles + tiles_per_seg - 1) / tiles_per_seg;
+}
+
+template <int T>
+static TapArray<T> make_taps(const std::vector<float> &h) {
+  TapArray<T> t;
+  std::memset(&t, 0, sizeof t);
+  std::memcpy(t.h, h.data(), sizeof(float) * T);
+  return t;
+}
+
+// ---- K1 dispatch -------------------------------------------------------------
+template <int T, int D, int R>
+static int launch_rf(sdr_pipeline *p, RfArgs a, cudaStream_t s) {
+  constexpr int NT = 128;
+  using Cfg = RfCfg<T, D, R, NT>;
+  auto kern = k_rf_demod<T, D, R, NT>;
+  static std::once_flag once[16];
+  int dev = p->cfg.device;
+  std::call_once(once[dev & 15], [&] {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  });
+  int segs = pick_segments(a.n_if, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
+  dim3 grid(segs, p->cfg.batch);
+  kern<<<grid, NT, Cfg::SMEM, s>>>(a, make_taps<T>(p->h_rf));
+  return check_launch(p, "k_rf_demod");
+}
+
+static bool rf_fast_available(int T, int D) {
+  return (T == 151 || T == 13) && (D == 10 || D == 5 || D == 3);
+}
+
+static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
+  const int T = p->cfg.rf_taps, D = p->m.rf_decim;
+  if (p->rf_fast) {
+    if (T == 151 && D == 10) return launch_rf<151, 10, 6>(p, a, s);
+    if (T == 151 && D == 5) return launch_rf<151, 5, 12>(p, a, s);
+    if (T == 151 && D == 3) return launch_rf<151, 3, 12>(p, a, s);
+    if (T == 13 && D == 10) return launch_rf<13, 10, 6>(p, a, s);
+    if (T == 13 && D == 5) return launch_rf<13, 5, 12>(p, a, s);
+    if (T == 13 && D == 3) return launch_rf<13, 3, 12>(p, a, s);
+  }
+  RfGenericArgs g;
+  g.a = a;
+  g.h = p->d_h_rf.p;
+  g.T = T;
+  g.D = D;
+  g.iq_filt = p->iq_filt.p;
+  dim3 grid((a.n_if + 127) / 128, p->cfg.batch);
+  k_rf_generic<<<grid, 128, T * sizeof(float), s>>>(g);
+  int rc = check_launch(p, "k_rf_generic");
+  if (rc) return rc;
+  k_fm_demod<<<grid, 128, 0, s>>>(p->iq_filt.p, a.n_if, a.demod, a.demod_stride, a.demod_off);
+  return check_launch(p, "k_fm_demod");
+}
+
+// ---- K3/K6 dispatch (modes 0/1) ----------------------------------------------
+template <int T, int D, int R, bool STEREO>
+static int launch_audio(sdr_pipeline *p, AudioArgs a, cudaStream_t s) {
+  constexpr int NT = 128;
+  using Cfg = AudioCfg<T, D, R, NT>;
+  constexpr size_t SMEM = (size_t)Cfg::ROW * (STEREO ? 2 : 1) * sizeof(float);
+  auto kern = k_audio_fir<T, D, R, NT, STEREO>;
+  static std::once_flag once[16];
+  std::call_once(once[p->cfg.device & 15], [&] {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  });
+  int segs = pick_segments(a.n_out, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
+  dim3 grid(segs, p->cfg.batch);
+  kern<<<grid, NT, SMEM, s>>>(a, make_taps<T>(p->h_audio));
+  return check_launch(p, "k_audio_fir");
+}
+
+static bool audio_fast_available(int T, int D) { return (T == 101 || T == 13) && (D == 5 || D == 6); }
+
+template <bool STEREO>
+static int run_audio_fir_fast(sdr_pipeline *p, const AudioArgs &a, cudaStream_t s) {
+  const int T = p->TA, D = p->m.audio_decim;
+  if (T == 101 && D == 5) return launch_audio<101, 5, 12, STEREO>(p, a, s);
+  if (T == 101 && D == 6) return launch_audio<101, 6, 6, STEREO>(p, a, s);
+  if (T == 13 && D == 5) return launch_audio<13, 5, 12, STEREO>(p, a, s);
+  if (T == 13 && D == 6) return launch_audio<13, 6, 6, STEREO>(p, a, s);
+  return fail(SDR_ERR_INVALID, "no specialised audio kernel");
+}
+
+// ---- K4 dispatch ---------------------------------------------------------------
+template <int T>
+static int launch_bpf(sdr_pipeline *p, BpfArgs a, cudaStream_t s) {
+  constexpr int NT = 128, R = 12;
+  int segs = pick_segments(a.n_if, NT * R, p->cfg.batch, &a.outs_per_seg);
+  dim3 grid(segs, p->cfg.batch);
+  k_bpf_dual<T, R, NT><<<grid, NT, 0, s>>>(a, make_taps<T>(p->h_stereo), make_taps<T>(p->h_pilot));
+  return check_launch(p, "k_bpf_dual");
+}
+
+static int run_fir_generic(sdr_pipeline *p, const float *x, size_t xs, int xoff, const float *h,
+                           int T, int D, float *y, size_t ys, int yoff, int n_out, int batch,
+                           cudaStream_t s) {
+  FirGenericArgs g{x, xs, xoff, h, T, D, y, ys, yoff, n_out};
+  dim3 grid((n_out + 127) / 128, batch);
+  k_fir_generic<<<grid, 128, T * sizeof(float), s>>>(g);
+  return check_launch(p, "k_fir_generic");
+}
+
+// ---------------------------------------------------------------------------
+// C ABI: misc
+// ---------------------------------------------------------------------------
+extern "C" const char *sdr_version(void) { return "sdr_b200 0.1 (sm_100a)"; }
+extern "C" const char *sdr_last_error(void) { return g_err.c_str(); }
+
+extern "C" int sdr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) ok += device_is_sm100(d) ? 1 : 0;
+  return ok;
+}
+
+extern "C" int sdr_mode_lookup(int mode, int channels, sdr_mode_info *out) {
+  if (mode < 0 || mode > 3 || channels < 1 || channels > 2 || !out)
+    return fail(SDR_ERR_INVALID, "mode must be 0..3 and channels 1|2");
+  const ModeRow &m = kModes[mode];
+  out->rf_Fs = m.rf_Fs;
+  out->if_Fs = m.if_Fs;
+  out->audio_Fs = m.audio_Fs;
+  out->rf_decim = m.rf_decim;
+  out->audio_decim = m.audio_decim;
+  out->audio_upsamp = m.audio_upsamp;
+  out->block_bytes = m.block_bytes;
+  // Smallest span after which every stage is back in phase: the IF count must be a
+  // multiple of audio_decim / gcd(audio_decim, audio_upsamp).
+  int g = m.audio_decim, r = m.audio_upsamp;
+  while (r) { int t = g % r; g = r; r = t; }
+  int if_per = m.audio_decim / g;
+  out->granule_bytes = if_per * m.rf_decim * 2;
+  out->pcm_per_granule = (int)((long long)if_per * m.audio_upsamp / m.audio_decim) * channels;
+  return SDR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// pipeline create / destroy / reset
+// ---------------------------------------------------------------------------
+static int upload(DevBuf<float> &d, const std::vector<float> &h) {
+  int rc = d.alloc(h.size());
+  if (rc) return rc;
+  SDR_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_reset(sdr_pipeline *p) {
+  if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
+  SDR_CUDA(cudaSetDevice(p->cfg.device));
+  int rc;
+  // raw history = byte 128, i.e. the reference's zero-filled I_state/Q_state (project.cpp:64-65)
+  if (p->rf_hist.p) SDR_CUDA(cudaMemset(p->rf_hist.p, 128, p->rf_hist.n));
+  if ((rc = p->prev.zero())) return rc;
+  if ((rc = p->prev_new.zero())) return rc;
+  if ((rc = p->demod.zero())) return rc;
+  if ((rc = p->stf.zero())) return rc;
+  if ((rc = p->car.zero())) return rc;
+  if ((rc = p->nco.zero())) return rc;
+  if (p->stereo) {
+    // project.cpp:458: state_PLL{0,0,1,0,1,0}; nco slot HA is ncoOut[0] of the first block
+    std::vector<float> st((size_t)p->cfg.batch * 8, 0.0f);
+    for (int b = 0; b < p->cfg.batch; ++b) {
+      st[(size_t)b * 8 + 2] = 1.0f;
+      st[(size_t)b * 8 + 4] = 1.0f;
+    }
+    SDR_CUDA(cudaMemcpy(p->pll_state.p, st.data(), st.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const float one = 1.0f;
+    SDR_CUDA(cudaMemcpy2D(p->nco.p + p->HA, p->nco_stride * sizeof(float), &one, 0, sizeof(float),
+                          p->cfg.batch, cudaMemcpyHostToDevice));
+  }
+  p->last_n_if = p->last_n_audio = 0;
+  SDR_CUDA(cudaDeviceSynchronize());
+  return SDR_OK;
+}
+
+static int alloc_tap_buffers(sdr_pipeline *p) {
+  int rc;
+  const size_t B = (size_t)p->cfg.batch;
+  if (!p->t_ifilt.p) {
+    if ((rc = p->t_ifilt.alloc(B * p->tap_if_stride))) return rc;
+    if ((rc = p->t_qfilt.alloc(B * p->tap_if_stride))) return rc;
+    if ((rc = p->t_audio.alloc(B * p->tap_audio_stride))) return rc;
+    if (p->stereo) {
+      if ((rc = p->t_stfinal.alloc(B * p->tap_audio_stride))) return rc;
+      if ((rc = p->mix.alloc(B * p->stf_stride))) return rc;
+      if ((rc = p->t_nco.alloc(B * p->tap_if_stride))) return rc;
+      if ((rc = p->t_allpass.alloc(B * p->tap_if_stride))) return rc;
+    }
+  }
+  return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
+  if (!cfg || !out) return fail(SDR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->mode < 0 || cfg->mode > 3) return fail(SDR_ERR_INVALID, "mode must be 0..3 (project.cpp:396)");
+  if (cfg->channels < 1 || cfg->channels > 2)
+    return fail(SDR_ERR_INVALID, "channels must be 1 or 2 (project.cpp:405)");
+  if (cfg->batch < 1 || cfg->batch > 65535) return fail(SDR_ERR_INVALID, "batch must be 1..65535");
+  if (cfg->rf_taps < 2 || cfg->rf_taps > 1024 || cfg->audio_taps < 2 || cfg->audio_taps > 1024 ||
+      cfg->stereo_taps < 3 || cfg->stereo_taps > 1024)
+    return fail(SDR_ERR_INVALID, "tap counts out of range");
+  if (cfg->variant != SDR_VARIANT_EXACT) return fail(SDR_ERR_INVALID, "unknown variant");
+  const ModeRow &m = kModes[cfg->mode];
+  if ((long long)cfg->audio_taps * m.audio_upsamp > 65535)
+    return fail(SDR_ERR_INVALID, "audio_taps*audio_upsamp exceeds unsigned short (filter.h:24)");
+  int rc = use_device(cfg->device);
+  if (rc) return rc;
+
+  sdr_pipeline *p = new sdr_pipeline();
+  p->cfg = *cfg;
+  p->m = m;
+  p->stereo = cfg->channels == 2;
+  p->resample = cfg->mode >= 2;
+  p->TA = cfg->audio_taps;
+  p->delay = p->stereo ? (cfg->stereo_taps - 1) / 2 : 0;
+  p->HR = round_up(cfg->rf_taps - 1 + m.rf_decim, 8);
+  p->HA = round_up(p->TA - 1, 4);
+  p->HD = round_up(std::max(p->stereo ? cfg->stereo_taps - 1 : 0, p->TA - 1 + p->delay), 4);
+  sdr_mode_info mi;
+  sdr_mode_lookup(cfg->mode, cfg->channels, &mi);
+  p->granule_bytes = mi.granule_bytes;
+  p->if_per_granule = mi.granule_bytes / 2 / m.rf_decim;
+  p->pcm_per_granule = mi.pcm_per_granule;
+  uint64_t cap_bytes = cfg->max_bytes_per_channel ? cfg->max_bytes_per_channel : (uint64_t)m.block_bytes;
+  cap_bytes = (cap_bytes + mi.granule_bytes - 1) / mi.granule_bytes * mi.granule_bytes;
+  p->cap_if = cap_bytes / 2 / m.rf_decim;
+  p->cap_audio = p->cap_if * m.audio_upsamp / m.audio_decim;
+  if (p->cap_if > 0x7fff0000ull / std::max(1, m.audio_upsamp)) {
+    delete p;
+    return fail(SDR_ERR_INVALID, "max_bytes_per_channel too large for 32-bit sample indices");
+  }
+  p->rf_fast = rf_fast_available(cfg->rf_taps, m.rf_decim);
+  p->audio_fast = !p->resample && audio_fast_available(p->TA, m.audio_decim);
+  p->bpf_fast = cfg->stereo_taps == 151 || cfg->stereo_taps == 13;
+
+  // ---- filter design (host, same arithmetic as the reference; design.cpp) ----
+  p->h_rf.resize(cfg->rf_taps);
+  design_lpf((float)m.rf_Fs, (float)100000, (unsigned short)cfg->rf_taps, p->h_rf.data());  // project.cpp:50
+  const int n_audio_taps = p->TA * m.audio_upsamp;
+  p->h_audio.resize(n_audio_taps);
+  design_lpf((float)(m.if_Fs * m.audio_upsamp), (float)16000, (unsigned short)n_audio_taps,
+             p->h_audio.data());  // project.cpp:165-167
+  if (p->stereo) {
+    p->h_pilot.resize(cfg->stereo_taps);
+    p->h_stereo.resize(cfg->stereo_taps);
+    design_bpf((float)m.if_Fs, (float)18.5e3, (float)19.5e3, (unsigned short)cfg->stereo_taps,
+               p->h_pilot.data());  // project.cpp:172
+    design_bpf((float)m.if_Fs, (float)22e3, (float)54e3, (unsigned short)cfg->stereo_taps,
+               p->h_stereo.data());  // project.cpp:173
+  }
+  // The fused RF kernel scales by 2^-7 after the sum; that is exact only while no
+  // product is subnormal.  Designed taps are nowhere near that, but guard anyway.
+  for (float h : p->h_rf)
+    if (h != 0.0f && std::fabs(h) < 1e-30f) p->rf_fast = false;
+  if (p->resample) {
+    const int U = m.audio_upsamp;
+    p->h_poly.resize((size_t)U * p->TA);
+    for (int ph = 0; ph < U; ++ph)
+      for (int k = 0; k < p->TA; ++k) p->h_poly[(size_t)ph * p->TA + k] = p->h_audio[ph + (size_t)k * U];
+  }
+
+  const size_t B = (size_t)cfg->batch;
+  p->demod_stride = round_up((int)(p->HD + p->cap_if + 8), 4);
+  p->stf_stride = round_up((int)(p->HA + p->cap_if + 8), 4);
+  p->nco_stride = p->stf_stride;
+  p->car_stride = round_up((int)p->cap_if + 4, 4);
+  p->tap_if_stride = p->cap_if;
+  p->tap_audio_stride = p->cap_audio;
+#define TRY(x)            \
+  do {                    \
+    rc = (x);             \
+    if (rc) {             \
+      sdr_pipeline_destroy(p); \
+      return rc;          \
+    }                     \
+  } while (0)
+  TRY(upload(p->d_h_rf, p->h_rf));
+  TRY(upload(p->d_h_audio, p->h_audio));
+  if (p->resample) TRY(upload(p->d_h_poly, p->h_poly));
+  TRY(p->rf_hist.alloc(B * 2 * p->HR));
+  TRY(p->prev.alloc(B * 2));
+  TRY(p->prev_new.alloc(B * 2));
+  TRY(p->demod.alloc(B * p->demod_stride));
+  if (p->stereo) {
+    TRY(upload(p->d_h_pilot, p->h_pilot));
+    TRY(upload(p->d_h_stereo, p->h_stereo));
+    TRY(p->stf.alloc(B * p->stf_stride));
+    TRY(p->nco.alloc(B * p->nco_stride));
+    TRY(p->car.alloc(B * p->car_stride));
+    TRY(p->pll_state.alloc(B * 8));
+  }
+  if (!p->rf_fast) TRY(p->iq_filt.alloc(B * 2 * (p->cap_if + 1)));
+  if (!p->resample && !p->audio_fast) TRY(alloc_tap_buffers(p));
+  TRY(sdr_pipeline_reset(p));
+#undef TRY
+  *out = p;
+  return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_destroy(sdr_pipeline *p) {
+  if (!p) return SDR_OK;
+  cudaSetDevice(p->cfg.device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 2; ++i) {
+    if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
+    if (p->pin_out[i]) cudaFreeHost(p->pin_out[i]);
+    if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+    if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+    if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+  }
+  if (p->s_copy_in) cudaStreamDestroy(p->s_copy_in);
+  if (p->s_compute) cudaStreamDestroy(p->s_compute);
+  if (p->s_copy_out) cudaStreamDestroy(p->s_copy_out);
+  delete p;
+  return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_keep_taps(sdr_pipeline *p, int keep) {
+  if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
+  SDR_CUDA(cudaSetDevice(p->cfg.device));
+  if (keep) {
+    int rc = alloc_tap_buffers(p);
+    if (rc) return rc;
+  }
+  p->keep_taps = keep != 0;
+  return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_pcm_count(const sdr_pipeline *p, size_t nbytes, size_t *n_pcm) {
+  if (!p || !n_pcm) return fail(SDR_ERR_INVALID, "null argument");
+  if (nbytes % (size_t)p->granule_bytes) return fail(SDR_ERR_INVALID, "nbytes is not a multiple of the granule");
+  *n_pcm = nbytes / (size_t)p->granule_bytes * (size_t)p->pcm_per_granule;
+  return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_launch_count(sdr_pipeline *p, uint64_t *count, int reset) {
+  if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
+  if (count) *count = p->launches;
+  if (reset) p->launches = 0;
+  return SDR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// process (device-resident)
+// ---------------------------------------------------------------------------
+extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq, size_t iq_stride,
+                                           size_t nbytes, int16_t *d_pcm, size_t pcm_stride,
+                                           void *stream) {
+  if (!p || !d_iq || !d_pcm) return fail(SDR_ERR_INVALID, "null argument");
+  if (nbytes == 0) return SDR_OK;
+  if (nbytes % (size_t)p->granule_bytes)
+    return fail(SDR_ERR_INVALID, "nbytes_per_channel must be a multiple of the mode's granule");
+  if (iq_stride < nbytes) return fail(SDR_ERR_INVALID, "iq_stride smaller than nbytes_per_channel");
+  const long long n_rf = (long long)(nbytes / 2);
+  const size_t n_if = (size_t)(n_rf / p->m.rf_decim);
+  const size_t n_audio = n_if * p->m.audio_upsamp / p->m.audio_decim;
+  if (n_if > p->cap_if) return fail(SDR_ERR_CAPACITY, "nbytes_per_channel exceeds max_bytes_per_channel");
+  if (pcm_stride < n_audio * (size_t)p->cfg.channels)
+    return fail(SDR_ERR_INVALID, "pcm_stride too small");
+  SDR_CUDA(cudaSetDevice(p->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int B = p->cfg.batch;
+  const bool taps = p->keep_taps;
+  int rc;
+
+  // ---- K1 ----
+  RfArgs ra{};
+  ra.iq = d_iq;
+  ra.iq_stride = iq_stride;
+  ra.hist = p->rf_hist.p;
+  ra.rf_hist_len = p->HR;
+  ra.prev_in = p->prev.p;
+  ra.prev_out = p->prev_new.p;
+  ra.demod = p->demod.p;
+  ra.demod_stride = p->demod_stride;
+  ra.demod_off = p->HD;
+  ra.i_filt = taps ? p->t_ifilt.p : nullptr;
+  ra.q_filt = taps ? p->t_qfilt.p : nullptr;
+  ra.tap_stride = p->tap_if_stride;
+  ra.n_rf = n_rf;
+  ra.n_if = (int)n_if;
+  if ((rc = run_rf(p, ra, s))) return rc;
+
+  // ---- stereo: K4 + K5 ----
+  if (p->stereo) {
+    if (p->bpf_fast) {
+      BpfArgs ba{};
+      ba.demod = p->demod.p;
+      ba.demod_stride = p->demod_stride;
+      ba.demod_off = p->HD;
+      ba.stf = p->stf.p;
+      ba.stf_stride = p->stf_stride;
+      ba.hist_off = p->HA;
+      ba.car = p->car.p;
+      ba.car_stride = p->car_stride;
+      ba.n_if = (int)n_if;
+      rc = (p->cfg.stereo_taps == 151) ? launch_bpf<151>(p, ba, s) : launch_bpf<13>(p, ba, s);
+      if (rc) return rc;
+    } else {
+      const int T = p->cfg.stereo_taps;
+      if ((rc = run_fir_generic(p, p->demod.p, p->demod_stride, p->HD, p->d_h_stereo.p, T, 1,
+                                p->stf.p, p->stf_stride, p->HA, (int)n_if, B, s)))
+        return rc;
+      if ((rc = run_fir_generic(p, p->demod.p, p->demod_stride, p->HD, p->d_h_pilot.p, T, 1,
+                                p->car.p, p->car_stride, 0, (int)n_if, B, s)))
+        return rc;
+    }
+    PllArgs pa{};
+    pa.in = p->car.p;
+    pa.in_stride = p->car_stride;
+    pa.out = p->nco.p;
+    pa.out_stride = p->nco_stride;
+    pa.out_off = p->HA;
+    pa.state = p->pll_state.p;
+    pa.n = (int)n_if;
+    pa.batch = B;
+    // project.cpp:237
+    pa.freq = (float)19e3;
+    pa.Fs = (float)p->m.if_Fs;
+    pa.ncoScale = (float)2.0;
+    pa.phaseAdjust = (float)0.0;
+    pa.normBandwidth = (float)0.01;
+    k_pll<<<(B + 31) / 32, 32, 0, s>>>(pa);
+    if ((rc = check_launch(p, "k_pll"))) return rc;
+  }
+
+  // ---- K3 / K6 ----
+  AudioArgs aa{};
+  aa.demod = p->demod.p;
+  aa.demod_stride = p->demod_stride;
+  aa.demod_off = p->HD;
+  aa.delay = p->delay;
+  aa.stf = p->stf.p;
+  aa.nco = p->nco.p;
+  aa.stf_stride = p->stf_stride;
+  aa.nco_stride = p->nco_stride;
+  aa.hist_off = p->HA;
+  aa.pcm = d_pcm;
+  aa.pcm_stride = pcm_stride;
+  aa.audio_filt = taps ? p->t_audio.p : nullptr;
+  aa.stereo_final = (taps && p->stereo) ? p->t_stfinal.p : nullptr;
+  aa.tap_stride = p->tap_audio_stride;
+  aa.n_out = (int)n_audio;
+  if (p->resample) {
+    ResampleArgs g{aa, p->d_h_poly.p, p->m.audio_upsamp, p->m.audio_decim, p->TA};
+    dim3 grid(((int)n_audio + 127) / 128, B);
+    if (p->stereo) k_audio_resample<true><<<grid, 128, 0, s>>>(g);
+    else k_audio_resample<false><<<grid, 128, 0, s>>>(g);
+    if ((rc = check_launch(p, "k_audio_resample"))) return rc;
+  } else if (p->audio_fast) {
+    rc = p->stereo ? run_audio_fir_fast<true>(p, aa, s) : run_audio_fir_fast<false>(p, aa, s);
+    if (rc) return rc;
+  } else {
+    // generic tap counts: separate FIR launches + PCM pack
+    const int T = p->TA, D = p->m.audio_decim;
+    if ((rc = run_fir_generic(p, p->demod.p, p->demod_stride, p->HD - p->delay, p->d_h_audio.p, T, D,
+                              p->t_audio.p, p->tap_audio_stride, 0, (int)n_audio, B, s)))
+      return rc;
+    if (p->stereo) {
+      dim3 g2(((int)(p->HA + n_if) + 127) / 128, B);
+      k_mixer<<<g2, 128, 0, s>>>(p->stf.p, p->stf_stride, p->nco.p, p->nco_stride, 0,
+                                 (int)(p->HA + n_if), p->mix.p, p->stf_stride);
+      if ((rc = check_launch(p, "k_mixer"))) return rc;
+      if ((rc = run_fir_generic(p, p->mix.p, p->stf_stride, p->HA, p->d_h_audio.p, T, D,
+                                p->t_stfinal.p, p->tap_audio_stride, 0, (int)n_audio, B, s)))
+        return rc;
+    }
+    dim3 g3(((int)n_audio + 127) / 128, B);
+    k_pcm_pack<<<g3, 128, 0, s>>>(p->t_audio.p, p->stereo ? p->t_stfinal.p : nullptr,
+                                  p->tap_audio_stride, (int)n_audio, d_pcm, pcm_stride);
+    if ((rc = check_launch(p, "k_pcm_pack"))) return rc;
+  }
+  if (taps && p->stereo) {
+    // Intermediates that the carry below would clobber are copied out first.
+    dim3 g2(((int)(p->HA + n_if) + 127) / 128, B);
+    k_mixer<<<g2, 128, 0, s>>>(p->stf.p, p->stf_stride, p->nco.p, p->nco_stride, 0,
+                               (int)(p->HA + n_if), p->mix.p, p->stf_stride);
+    if ((rc = check_launch(p, "k_mixer"))) return rc;
+    dim3 g3(((int)n_if + 127) / 128, B);
+    k_copy_rows<<<g3, 128, 0, s>>>(p->nco.p, p->nco_stride, p->HA, p->t_nco.p, p->tap_if_stride,
+                                   (int)n_if);
+    if ((rc = check_launch(p, "k_copy_rows"))) return rc;
+    k_copy_rows<<<g3, 128, 0, s>>>(p->demod.p, p->demod_stride, p->HD - p->delay, p->t_allpass.p,
+                                   p->tap_if_stride, (int)n_if);
+    if ((rc = check_launch(p, "k_copy_rows"))) return rc;
+  }
+
+  // ---- carry ----
+  CarryArgs ca{};
+  ca.rows[0] = p->demod.p;
+  ca.strides[0] = p->demod_stride;
+  ca.src_off[0] = (int)n_if;
+  ca.len[0] = p->HD;
+  if (p->stereo) {
+    ca.rows[1] = p->stf.p;
+    ca.strides[1] = p->stf_stride;
+    ca.src_off[1] = (int)n_if;
+    ca.len[1] = p->HA;
+    ca.rows[2] = p->nco.p;
+    ca.strides[2] = p->nco_stride;
+    ca.src_off[2] = (int)n_if;
+    ca.len[2] = p->HA + 1;
+  }
+  ca.iq = d_iq;
+  ca.iq_stride = iq_stride;
+  ca.hist = p->rf_hist.p;
+  ca.rf_hist_len = p->HR;
+  ca.n_rf = n_rf;
+  ca.prev_dst = p->prev.p;
+  ca.prev_src = p->prev_new.p;
+  // When taps are kept the carry would overwrite what sdr_pipeline_tap reads
+  // (history-prefixed rows), so the tap accessor accounts for it via last_n_if.
+  size_t sh = std::max<size_t>((size_t)std::max(p->HD, p->HA + 1) * sizeof(float), (size_t)2 * p->HR);
+  k_carry<<<B, 128, sh, s>>>(ca);
+  if ((rc = check_launch(p, "k_carry"))) return rc;
+  p->last_n_if = n_if;
+  p->last_n_audio = n_audio;
+  return SDR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// taps
+// ---------------------------------------------------------------------------
+extern "C" int sdr_pipeline_tap(sdr_pipeline *p, int stage, int channel, float *dst, size_t cap,
+                                size_t *n) {
+  if (!p || !n) return fail(SDR_ERR_INVALID, "null argument");
+  if (channel < 0 || channel >= p->cfg.batch) return fail(SDR_ERR_INVALID, "channel out of range");
+  if (!p->keep_taps) return fail(SDR_ERR_INVALID, "call sdr_pipeline_keep_taps(p, 1) before process");
+  SDR_CUDA(cudaSetDevice(p->cfg.device));
+  const size_t n_if = p->last_n_if, n_audio = p->last_n_audio;
+  const float *src = nullptr;
+  size_t count = 0;
+  const size_t b = (size_t)channel;
+  // After the carry, a history-prefixed row holds sample g of the last call at
+  // position (prefix + g) for g < n_if - prefix only; the prefix itself now holds
+  // the tail.  Rows below are therefore read from the dedicated tap buffers or
+  // reassembled from (body, carried tail).
+  switch (stage) {
+    case SDR_TAP_I_FILT: src = p->t_ifilt.p + b * p->tap_if_stride; count = n_if; break;
+    case SDR_TAP_Q_FILT: src = p->t_qfilt.p + b * p->tap_if_stride; count = n_if; break;
+    case SDR_TAP_AUDIO_FILT: src = p->t_audio.p + b * p->tap_audio_stride; count = n_audio; break;
+    case SDR_TAP_STEREO_FINAL:
+      if (!p->stereo) return fail(SDR_ERR_INVALID, "stereo-only tap");
+      src = p->t_stfinal.p + b * p->tap_audio_stride; count = n_audio; break;
+    case SDR_TAP_CARRIER_FILT:
+      if (!p->stereo) return fail(SDR_ERR_INVALID, "stereo-only tap");
+      src = p->car.p + b * p->car_stride; count = n_if; break;
+    case SDR_TAP_NCO:
+      if (!p->stereo) return fail(SDR_ERR_INVALID, "stereo-only tap");
+      src = p->t_nco.p + b * p->tap_if_stride; count = n_if; break;
+    case SDR_TAP_ALLPASS:
+      if (!p->stereo) return fail(SDR_ERR_INVALID, "stereo-only tap");
+      src = p->t_allpass.p + b * p->tap_if_stride; count = n_if; break;
+    case SDR_TAP_DEMOD: case SDR_TAP_STEREO_FILT: case SDR_TAP_MIXER:
+      count = n_if;
+      break;
+    default:
+      return fail(SDR_ERR_INVALID, "unknown tap stage");
+  }
+  *n = count;
+  if (!dst) return SDR_OK;
+  if (cap < count) return fail(SDR_ERR_CAPACITY, "tap destination too small");
+  SDR_CUDA(cudaDeviceSynchronize());
+  if (src) {
+    SDR_CUDA(cudaMemcpy(dst, src, count * sizeof(float), cudaMemcpyDeviceToHost));
+    return SDR_OK;
+  }
+  // History-prefixed rows: the carry only rewrites the prefix [0, H), so
+  // row[H .. H+n_if) still holds this call's samples.
+  const float *row = nullptr;
+  size_t H = 0, stride = 0;
+  if (stage == SDR_TAP_DEMOD) {
+    row = p->demod.p; H = p->HD; stride = p->demod_stride;
+  } else if (stage == SDR_TAP_STEREO_FILT) {
+    if (!p->stereo) return fail(SDR_ERR_INVALID, "stereo-only tap");
+    row = p->stf.p; H = p->HA; stride = p->stf_stride;
+  } else {  // mixer: computed by k_mixer into p->mix before the carry
+    if (!p->stereo) return fail(SDR_ERR_INVALID, "stereo-only tap");
+    row = p->mix.p; H = p->HA; stride = p->stf_stride;
+  }
+  SDR_CUDA(cudaMemcpy(dst, row + b * stride + H, count * sizeof(float), cudaMemcpyDeviceToHost));
+  return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_copy_state(sdr_pipeline *p, int dst, int src) {
+  if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
+  if (dst < 0 || src < 0 || dst >= p->cfg.batch || src >= p->cfg.batch)
+    return fail(SDR_ERR_INVALID, "channel out of range");
+  if (dst == src) return SDR_OK;
+  SDR_CUDA(cudaSetDevice(p->cfg.device));
+  auto cp = [&](void *base, size_t row_bytes) -> int {
+    if (!base) return SDR_OK;
+    SDR_CUDA(cudaMemcpy((char *)base + (size_t)dst * row_bytes, (char *)base + (size_t)src * row_bytes,
+                        row_bytes, cudaMemcpyDeviceToDevice));
+    return SDR_OK;
+  };
+  int rc;
+  if ((rc = cp(p->rf_hist.p, 2 * (size_t)p->HR))) return rc;
+  if ((rc = cp(p->prev.p, 2 * sizeof(float)))) return rc;
+  if ((rc = cp(p->demod.p, (size_t)p->HD * sizeof(float)))) return rc;
+  // rows are strided: only the prefixes matter, but they sit at row starts
+  auto cprow = [&](float *base, size_t stride, size_t len) -> int {
+    if (!base) return SDR_OK;
+    SDR_CUDA(cudaMemcpy(base + (size_t)dst * stride, base + (size_t)src * stride, len * sizeof(float),
+                        cudaMemcpyDeviceToDevice));
+    return SDR_OK;
+  };
+  if ((rc = cprow(p->demod.p, p->demod_stride, p->HD))) return rc;
+  if ((rc = cprow(p->stf.p, p->stf_stride, p->HA))) return rc;
+  if ((rc = cprow(p->nco.p, p->nco_stride, p->HA + 1))) return rc;
+  if ((rc = cprow(p->pll_state.p, 8, 8))) return rc;
+  return SDR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// process (host buffers): pinned double buffers over three streams replace the
+// reference's producer/consumer queue (project.cpp:141-149,181-189,471-496).
+// The span is cut along time into slices; slice k+1 is uploaded while slice k
+// is computed and slice k-1's PCM is downloaded.
+// ---------------------------------------------------------------------------
+static int ensure_host_staging(sdr_pipeline *p, size_t slice_bytes) {
+  if (p->slice_bytes >= slice_bytes && p->s_compute) return SDR_OK;
+  const size_t B = (size_t)p->cfg.batch;
+  size_t n_pcm;
+  sdr_pipeline_pcm_count(p, slice_bytes, &n_pcm);
+  for (int i = 0; i < 2; ++i) {
+    if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
+    if (p->pin_out[i]) cudaFreeHost(p->pin_out[i]);
+    p->pin_in[i] = nullptr;
+    p->pin_out[i] = nullptr;
+    SDR_CUDA(cudaMallocHost(&p->pin_in[i], B * slice_bytes));
+    SDR_CUDA(cudaMallocHost(&p->pin_out[i], B * n_pcm * sizeof(int16_t)));
+    int rc;
+    if ((rc = p->d_in[i].alloc(B * slice_bytes))) return rc;
+    if ((rc = p->d_out[i].alloc(B * n_pcm))) return rc;
+    if (!p->ev_in[i]) {
+      SDR_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+      SDR_CUDA(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+      SDR_CUDA(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  if (!p->s_compute) {
+    SDR_CUDA(cudaStreamCreateWithFlags(&p->s_copy_in, cudaStreamNonBlocking));
+    SDR_CUDA(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
+    SDR_CUDA(cudaStreamCreateWithFlags(&p->s_copy_out, cudaStreamNonBlocking));
+  }
+  p->slice_bytes = slice_bytes;
+  p->slice_pcm = n_pcm;
+  return SDR_OK;
+}
+
+static bool is_pinned(const void *ptr) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int sdr_pipeline_process_host(sdr_pipeline *p, const uint8_t *iq, size_t iq_stride,
+                                         size_t nbytes, int16_t *pcm, size_t pcm_stride) {
+  if (!p || !iq || !pcm) return fail(SDR_ERR_INVALID, "null argument");
+  if (nbytes % (size_t)p->granule_bytes)
+    return fail(SDR_ERR_INVALID, "nbytes_per_channel must be a multiple of the mode's granule");
+  if (nbytes == 0) return SDR_OK;
+  SDR_CUDA(cudaSetDevice(p->cfg.device));
+  const size_t B = (size_t)p->cfg.batch;
+  const size_t gran = (size_t)p->granule_bytes;
+  // slice: <= capacity, and about 64 MiB over the whole batch
+  size_t cap_bytes = p->cap_if * p->m.rf_decim * 2;
+  size_t slice = std::max<size_t>(gran, ((64ull << 20) / B) / gran * gran);
+  slice = std::min(slice, cap_bytes / gran * gran);
+  slice = std::min(slice, nbytes);
+  int rc = ensure_host_staging(p, slice);
+  if (rc) return rc;
+  slice = std::min(p->slice_bytes, nbytes) / gran * gran;
+  const bool in_pinned = is_pinned(iq), out_pinned = is_pinned(pcm);
+  const size_t n_slices = (nbytes + slice - 1) / slice;
+  size_t pcm_done = 0;
+  size_t pcm_off[2] = {0, 0}, pcm_cnt[2] = {0, 0};
+  auto drain = [&](int buf) -> int {  // wait for buffer's D2H and hand PCM to the caller
+    SDR_CUDA(cudaEventSynchronize(p->ev_out[buf]));
+    if (!out_pinned && pcm_cnt[buf]) {
+      for (size_t b = 0; b < B; ++b)
+        std::memcpy(pcm + b * pcm_stride + pcm_off[buf], p->pin_out[buf] + b * pcm_cnt[buf],
+                    pcm_cnt[buf] * sizeof(int16_t));
+    }
+    pcm_cnt[buf] = 0;
+    return SDR_OK;
+  };
+  for (size_t k = 0; k < n_slices; ++k) {
+    const int buf = (int)(k & 1);
+    const size_t off = k * slice;
+    const size_t len = std::min(slice, nbytes - off);
+    size_t n_pcm;
+    sdr_pipeline_pcm_count(p, len, &n_pcm);
+    if (k >= 2) {
+      // this buffer pair was last used by slice k-2: its PCM must have reached the
+      // caller, its compute must be finished before the device input is overwritten
+      if ((rc = drain(buf))) return rc;
+      SDR_CUDA(cudaStreamWaitEvent(p->s_copy_in, p->ev_done[buf], 0));
+      if (!in_pinned) SDR_CUDA(cudaEventSynchronize(p->ev_in[buf]));
+    }
+    // ---- upload ----
+    if (in_pinned) {
+      SDR_CUDA(cudaMemcpy2DAsync(p->d_in[buf].p, len, iq + off, iq_stride, len, B,
+                                 cudaMemcpyHostToDevice, p->s_copy_in));
+    } else {
+      for (size_t b = 0; b < B; ++b) std::memcpy(p->pin_in[buf] + b * len, iq + b * iq_stride + off, len);
+      SDR_CUDA(cudaMemcpyAsync(p->d_in[buf].p, p->pin_in[buf], B * len, cudaMemcpyHostToDevice,
+                               p->s_copy_in));
+    }
+    SDR_CUDA(cudaEventRecord(p->ev_in[buf], p->s_copy_in));
+    // ---- compute (after its input arrived and slice k-2's PCM left d_out[buf]) ----
+    SDR_CUDA(cudaStreamWaitEvent(p->s_compute, p->ev_in[buf], 0));
+    if (k >= 2) SDR_CUDA(cudaStreamWaitEvent(p->s_compute, p->ev_out[buf], 0));
+    if ((rc = sdr_pipeline_process_device(p, p->d_in[buf].p, len, len, p->d_out[buf].p, n_pcm,
+                                          p->s_compute)))
+      return rc;
+    SDR_CUDA(cudaEventRecord(p->ev_done[buf], p->s_compute));
+    // ---- download ----
+    SDR_CUDA(cudaStreamWaitEvent(p->s_copy_out, p->ev_done[buf], 0));
+    if (out_pinned) {
+      SDR_CUDA(cudaMemcpy2DAsync(pcm + pcm_done, pcm_stride * sizeof(int16_t), p->d_out[buf].p,
+                                 n_pcm * sizeof(int16_t), n_pcm * sizeof(int16_t), B,
+                                 cudaMemcpyDeviceToHost, p->s_copy_out));
+    } else {
+      SDR_CUDA(cudaMemcpyAsync(p->pin_out[buf], p->d_out[buf].p, B * n_pcm * sizeof(int16_t),
+                               cudaMemcpyDeviceToHost, p->s_copy_out));
+    }
+    SDR_CUDA(cudaEventRecord(p->ev_out[buf], p->s_copy_out));
+    pcm_off[buf] = pcm_done;
+    pcm_cnt[buf] = n_pcm;
+    pcm_done += n_pcm;
+  }
+  for (size_t k = (n_slices >= 2 ? n_slices - 2 : 0); k < n_slices; ++k)
+    if ((rc = drain((int)(k & 1)))) return rc;
+  SDR_CUDA(cudaStreamSynchronize(p->s_compute));
+  return SDR_OK;
+}
