@@ -314,9 +314,9 @@ extern "C" int sdr_pipeline_reset(sdr_pipeline *p) {
       st[(size_t)b * 8 + 4] = 1.0f;
     }
     SDR_CUDA(cudaMemcpy(p->pll_state.p, st.data(), st.size() * sizeof(float), cudaMemcpyHostToDevice));
-    const float one = 1.0f;
-    SDR_CUDA(cudaMemcpy2D(p->nco.p + p->HA, p->nco_stride * sizeof(float), &one, 0, sizeof(float),
-                          p->cfg.batch, cudaMemcpyHostToDevice));
+    std::vector<float> ones((size_t)p->cfg.batch, 1.0f);
+    SDR_CUDA(cudaMemcpy2D(p->nco.p + p->HA, p->nco_stride * sizeof(float), ones.data(), sizeof(float),
+                          sizeof(float), p->cfg.batch, cudaMemcpyHostToDevice));
   }
   p->last_n_if = p->last_n_audio = 0;
   SDR_CUDA(cudaDeviceSynchronize());
