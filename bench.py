@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the FM receiver DSP hot path on B200.
+
+Metric (BASELINE.json): aggregate input I/Q MS/s (10^6 complex samples, one I byte + one Q byte
+each, consumed per second, summed over captures), device-timed, plus % of the HBM roofline.
+
+Workload at N=1: BASELINE.json configs[1] -- mono custom-rate mode 2 (2.4 MS/s -> 44.1 kS/s through
+the 147/800 polyphase resampler), 1024 batched captures on one B200, functional tap set
+(rf 151 / audio 101 per phase).  One "step" = one pass of the whole path over one resident batch
+([1024][blocks*112000] uint8, larger than L2).  N>1: every rank owns `--batch` captures on its own
+GPU (captures are independent: no collective on the data path, weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
+  python bench.py --impl reference [...]                       the reference's CPU path
+  torchrun ... bench.py --gpus N ...                           one rank per GPU (driver-launched)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aggregate input I/Q MS/s (device-timed)"
+UNIT = "MS/s"
+TAPS = dict(rf_taps=151, audio_taps=101, stereo_taps=151)
+
+
+def algorithmic_bytes_per_sample(mode: int, channels: int) -> float:
+    """2 B read (u8 I + u8 Q) + int16 PCM written per input complex sample."""
+    fs = {0: 2.4e6, 1: 1.44e6, 2: 2.4e6, 3: 0.96e6}[mode]
+    fa = {0: 48e3, 1: 48e3, 2: 44.1e3, 3: 44.1e3}[mode]
+    return 2.0 + 2.0 * channels * fa / fs
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref when it was compiled from
+# /root/reference, else the oracle port), all host threads, bounded sample of the same workload
+# --------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, mode, channels, seed, n_blocks, reps = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orclib
+    from sdr_b200 import siggen
+    lib = orclib.REF() if kind == "reference" else orclib.ORC()
+    iq = siggen.make_capture(seed, mode, n_blocks, "stereo")
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        lib.run_chain(iq, mode, channels, TAPS["rf_taps"], TAPS["audio_taps"], TAPS["stereo_taps"],
+                      keep_taps=False)
+    return time.perf_counter() - t0, reps * iq.size // 2
+
+
+def cpu_baseline(mode: int, channels: int, seconds: float = 12.0, cores: int | None = None):
+    """Times the CPU path on `cores` processes, one independent capture each (embarrassingly
+    parallel, like the GPU batch).  Returns (MS/s, kind, cores, sample description)."""
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orclib
+    import sdr_b200  # noqa: F401  (registers the package alias for the workers)
+    kind = "reference" if orclib.REF() is not None else "port"
+    cores = cores or os.cpu_count() or 1
+    n_blocks = 8
+    # calibrate one capture on one core, then size reps for ~`seconds` of work per core
+    t, n = _cpu_worker((kind, mode, channels, 0, n_blocks, 1))
+    reps = max(1, int(seconds / max(t, 1e-3)))
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(kind, mode, channels, c, n_blocks, reps) for c in range(cores)])
+    wall = time.perf_counter() - t0
+    total = sum(r[1] for r in res)
+    sample = (f"{cores} captures x {n_blocks} reference blocks x {reps} passes, mode {mode}, "
+              f"{'stereo' if channels == 2 else 'mono'}, taps 151/101/151, one process per core")
+    return total / wall / 1e6, kind, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    per_step = max(1.0, min(20.0, 90.0 / (steps + args.warmup)))
+    vals = []
+    for i in range(args.warmup + steps):
+        v, kind, cores, sample = cpu_baseline(args.mode, args.audio_channels, seconds=per_step)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    n_samples_step = None
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"mode {args.mode} {'stereo' if args.audio_channels == 2 else 'mono'}, "
+                        f"{args.batch} captures per GPU x {args.blocks} reference blocks "
+                        f"({args.blocks * BLOCK_BYTES[args.mode]} B each), taps rf 151 / audio 101"
+                        f"{' / stereo 151' if args.audio_channels == 2 else ''}",
+            "mode": args.mode, "audio_channels": args.audio_channels, "batch_per_gpu": args.batch,
+            "blocks_per_capture": args.blocks, "l2_policy": "input batch larger than L2 (no flush needed)",
+            "variant": "exact"}
+
+
+BLOCK_BYTES = {0: 102400, 1: 61440, 2: 112000, 3: 134400}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def make_device_batch(torch, mode, batch, blocks, kind, device):
+    """[batch, nbytes] uint8 on the device: a few distinct synthetic captures, tiled with a
+    per-capture circular shift so that every row is a different valid capture."""
+    from sdr_b200 import siggen
+    distinct = min(batch, 8)
+    base = torch.from_numpy(np.stack([siggen.make_capture(c, mode, blocks, kind) for c in range(distinct)])).to(device)
+    out = torch.empty((batch, base.shape[1]), dtype=torch.uint8, device=device)
+    for c in range(batch):
+        rot = 2 * ((c // distinct) * 977 % (base.shape[1] // 2))
+        out[c] = torch.roll(base[c % distinct], rot) if rot else base[c % distinct]
+    return out
+
+
+def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, world, profile=True):
+    """Device-resident timing of one configuration.  Returns dict with ms/step (max over ranks),
+    per-kernel times and launches."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    kind = "stereo"
+    d_iq = make_device_batch(torch, mode, args.batch, args.blocks, kind, dev)
+    nbytes = d_iq.shape[1]
+    p = sdr.Pipeline(mode=mode, channels=audio_channels, batch=args.batch, device=dev.index,
+                     max_bytes_per_channel=nbytes, **TAPS)
+    n_pcm = p.pcm_count(nbytes)
+    d_pcm = torch.zeros((args.batch, n_pcm), dtype=torch.int16, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        p.process_device(d_iq.data_ptr(), d_iq.stride(0), nbytes, d_pcm.data_ptr(), d_pcm.stride(0), stream)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    p.launch_count(reset=True)
+    p.profile(profile)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = p.launch_count()
+    ktimes = p.kernel_times(reset=True) if profile else {}
+    p.profile(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    samples_per_step = args.batch * (nbytes // 2)
+    checksum = int(d_pcm[:, :64].to(torch.int64).abs().sum().item())
+    p.close()
+    del d_iq, d_pcm
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms / steps, "samples_per_step": samples_per_step, "launches": launches,
+            "kernels": ktimes, "nbytes": nbytes, "n_pcm": n_pcm, "checksum": checksum}
+
+
+def time_e2e(torch, sdr, args, steps, dist, world):
+    """Same metric through the public host-buffer call (sdr_pipeline_process_host): pinned host
+    input -> H2D -> kernels -> D2H PCM, all inside the timed region, every step."""
+    from sdr_b200 import siggen
+    dev_index = torch.cuda.current_device()
+    blocks = min(args.blocks, args.e2e_blocks)
+    distinct = min(args.batch, 8)
+    base = np.stack([siggen.make_capture(c, args.mode, blocks, "stereo") for c in range(distinct)])
+    nbytes = base.shape[1]
+    h_iq = torch.empty((args.batch, nbytes), dtype=torch.uint8).pin_memory()
+    hv = h_iq.numpy()
+    for c in range(args.batch):
+        rot = 2 * ((c // distinct) * 977 % (nbytes // 2))
+        hv[c] = np.roll(base[c % distinct], rot) if rot else base[c % distinct]
+    p = sdr.Pipeline(mode=args.mode, channels=args.audio_channels, batch=args.batch, device=dev_index,
+                     max_bytes_per_channel=nbytes, **TAPS)
+    n_pcm = p.pcm_count(nbytes)
+    h_pcm = torch.empty((args.batch, n_pcm), dtype=torch.int16).pin_memory()
+
+    def step():
+        p.process_host_ptr(h_iq.data_ptr(), h_iq.stride(0), nbytes, h_pcm.data_ptr(), h_pcm.stride(0))
+
+    step()  # warm-up: allocates the staging buffers
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec], dtype=torch.float64, device=torch.device("cuda", dev_index))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    p.close()
+    samples = args.batch * (nbytes // 2) * steps * world
+    return {"value": samples / sec / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(args.batch * nbytes),
+            "d2h_bytes_per_step": int(args.batch * n_pcm * 2), "blocks_per_capture": blocks,
+            "ms_per_step": sec / steps * 1e3,
+            "api": "sdr_pipeline_process_host (pinned host buffers, 3 streams, double-buffered slices)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sdr_b200 as sdr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or sdr.device_count() < 1:
+        raise SystemExit("bench.py needs a B200 (sm_100) GPU: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    main = time_config(torch, sdr, args, args.mode, args.audio_channels, args.steps, args.warmup, dist, world)
+    clocks = None
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+        clocks = sampler.summary()
+
+    e2e = time_e2e(torch, sdr, args, max(2, min(args.steps, 5)), dist, world)
+
+    others = {}
+    if args.others and world == 1:
+        for name, (m, ch) in {"mono_mode0": (0, 1), "stereo_mode0": (0, 2), "stereo_mode2": (2, 2)}.items():
+            r = time_config(torch, sdr, args, m, ch, max(2, args.steps // 4), 3, dist, world, profile=True)
+            msps = r["samples_per_step"] / (r["ms_per_step"] * 1e-3) / 1e6
+            peak, _ = measured_peak()
+            others[name] = {"value": msps, "unit": UNIT, "ms_per_step": r["ms_per_step"],
+                            "hbm_frac": msps * 1e6 * algorithmic_bytes_per_sample(m, ch) / 1e9 / peak,
+                            "kernel_ms_per_step": {k: v[0] / max(1, v[1]) * (v[1] / max(2, args.steps // 4))
+                                                   for k, v in r["kernels"].items()}}
+
+    if rank == 0:
+        total_samples = main["samples_per_step"] * world
+        value = total_samples / (main["ms_per_step"] * 1e-3) / 1e6
+        peak, peak_src = measured_peak()
+        bps = algorithmic_bytes_per_sample(args.mode, args.audio_channels)
+        # dominant kernel: the one with the largest total time in the timed region
+        kt = main["kernels"]
+        dom = max(kt, key=lambda k: kt[k][0]) if kt else None
+        step_kernel_ms = sum(v[0] for v in kt.values()) / args.steps if kt else None
+        roofline = None
+        if dom:
+            dom_ms = kt[dom][0] / kt[dom][1]
+            alg_bytes = main["samples_per_step"] * bps  # per launch: one launch covers the whole batch
+            achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
+                        "kernel_share_of_step": kt[dom][0] / args.steps / step_kernel_ms,
+                        "whole_step_frac": value * 1e6 * bps / 1e9 / peak / world,
+                        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()}}
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, kind, cores, sample = cpu_baseline(args.mode, args.audio_channels, seconds=10.0)
+            cb = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args), "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
+            "gpu_launches": main["launches"], "clocks": clocks, "pcm_checksum": main["checksum"],
+        }
+        if others:
+            line["other_configs"] = others
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", type=int, default=2)
+    ap.add_argument("--audio-channels", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=1024, help="captures per GPU")
+    ap.add_argument("--blocks", type=int, default=16, help="reference blocks per capture per step")
+    ap.add_argument("--e2e-blocks", type=int, default=8)
+    ap.add_argument("--others", action="store_true", help="also time mono mode 0 / stereo configs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -169,6 +169,13 @@ int sdr_pipeline_tap(sdr_pipeline *p, int stage, int channel, float *dst, size_t
  * counter (bench.py reports it as gpu_launches). */
 int sdr_pipeline_launch_count(sdr_pipeline *p, uint64_t *count, int reset);
 
+/* Per-kernel device timing (CUDA events on the launching stream, recorded around
+ * every kernel of this handle while enabled).  sdr_pipeline_kernel_times walks the
+ * kernels by index: returns 0 and fills name/total/count, or 1 past the last one. */
+int sdr_pipeline_profile(sdr_pipeline *p, int enable);
+int sdr_pipeline_kernel_times(sdr_pipeline *p, int index, char *name, size_t name_cap,
+                              double *total_ms, uint64_t *count, int reset);
+
 #ifdef __cplusplus
 }
 #endif

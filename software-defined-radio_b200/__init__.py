@@ -75,6 +75,9 @@ ABI = {
     "sdr_pipeline_keep_taps": (C.c_int, [_vp, C.c_int]),
     "sdr_pipeline_tap": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sdr_pipeline_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
+    "sdr_pipeline_profile": (C.c_int, [_vp, C.c_int]),
+    "sdr_pipeline_kernel_times": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_size_t,
+                                            C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
 }
 
 _lib = None
@@ -269,6 +272,23 @@ class Pipeline:
         """Raw device pointers (e.g. torch ``tensor.data_ptr()``); only enqueues on ``stream``."""
         _check(lib().sdr_pipeline_process_device(self._h, d_iq_ptr, iq_stride, nbytes, d_pcm_ptr,
                                                  pcm_stride, stream))
+
+    def profile(self, enable=True):
+        _check(lib().sdr_pipeline_profile(self._h, 1 if enable else 0))
+
+    def kernel_times(self, reset=False) -> dict:
+        """{kernel name: (total_ms, launches)} from CUDA events recorded while profiling."""
+        out, i = {}, 0
+        while True:
+            name = C.create_string_buffer(64)
+            ms, cnt = C.c_double(0), C.c_uint64(0)
+            rc = lib().sdr_pipeline_kernel_times(self._h, i, name, 64, C.byref(ms), C.byref(cnt),
+                                                 1 if reset else 0)
+            if rc == 1:
+                return out
+            _check(rc)
+            out[name.value.decode()] = (ms.value, cnt.value)
+            i += 1
 
     def tap(self, name: str, channel: int = 0) -> np.ndarray:
         stage = TAP_NAMES.index(name)

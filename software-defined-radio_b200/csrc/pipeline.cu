@@ -115,6 +115,16 @@ struct sdr_pipeline {
   bool keep_taps = false;
   size_t last_n_if = 0, last_n_audio = 0;
   uint64_t launches = 0;
+  // optional per-kernel timing (CUDA events on the launching stream)
+  bool profiling = false;
+  struct Site {
+    std::string name;
+    std::vector<cudaEvent_t> ev;  // start,stop pairs
+    size_t used = 0;
+    double total_ms = 0.0;
+    uint64_t count = 0;
+  };
+  std::vector<Site> sites;
   // host staging for process_host
   uint8_t *pin_in[2] = {nullptr, nullptr};
   int16_t *pin_out[2] = {nullptr, nullptr};
@@ -129,8 +139,40 @@ struct sdr_pipeline {
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
+static sdr_pipeline::Site *g_open_site = nullptr;  // site between prof_begin and check_launch
+static cudaStream_t g_open_stream = nullptr;
+
+// Called right before a kernel launch; records the start event when profiling.
+static void prof_begin(sdr_pipeline *p, const char *name, cudaStream_t s) {
+  g_open_site = nullptr;
+  if (!p || !p->profiling) return;
+  sdr_pipeline::Site *site = nullptr;
+  for (auto &x : p->sites)
+    if (x.name == name) site = &x;
+  if (!site) {
+    p->sites.push_back({});
+    site = &p->sites.back();
+    site->name = name;
+  }
+  if (site->used + 2 > site->ev.size()) {
+    if (site->ev.size() >= 8192) return;  // bounded: stop sampling this site until drained
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    site->ev.push_back(a);
+    site->ev.push_back(b);
+  }
+  cudaEventRecord(site->ev[site->used], s);
+  g_open_site = site;
+  g_open_stream = s;
+}
+
 static int check_launch(sdr_pipeline *p, const char *name) {
   cudaError_t e = cudaGetLastError();
+  if (g_open_site) {
+    cudaEventRecord(g_open_site->ev[g_open_site->used + 1], g_open_stream);
+    g_open_site->used += 2;
+    g_open_site = nullptr;
+  }
   if (e != cudaSuccess) return cuda_fail(e, name, __FILE__, __LINE__);
   if (p) p->launches++;
   return SDR_OK;
@@ -166,6 +208,7 @@ static int launch_rf(sdr_pipeline *p, RfArgs a, cudaStream_t s) {
   });
   int segs = pick_segments(a.n_if, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
+  prof_begin(p, "k_rf_demod", s);
   kern<<<grid, NT, Cfg::SMEM, s>>>(a, make_taps<T>(p->h_rf));
   return check_launch(p, "k_rf_demod");
 }
@@ -191,9 +234,11 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
   g.D = D;
   g.iq_filt = p->iq_filt.p;
   dim3 grid((a.n_if + 127) / 128, p->cfg.batch);
+  prof_begin(p, "k_rf_generic", s);
   k_rf_generic<<<grid, 128, T * sizeof(float), s>>>(g);
   int rc = check_launch(p, "k_rf_generic");
   if (rc) return rc;
+  prof_begin(p, "k_fm_demod", s);
   k_fm_demod<<<grid, 128, 0, s>>>(p->iq_filt.p, a.n_if, a.demod, a.demod_stride, a.demod_off);
   return check_launch(p, "k_fm_demod");
 }
@@ -211,6 +256,7 @@ static int launch_audio(sdr_pipeline *p, AudioArgs a, cudaStream_t s) {
   });
   int segs = pick_segments(a.n_out, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
+  prof_begin(p, "k_audio_fir", s);
   kern<<<grid, NT, SMEM, s>>>(a, make_taps<T>(p->h_audio));
   return check_launch(p, "k_audio_fir");
 }
@@ -233,6 +279,7 @@ static int launch_bpf(sdr_pipeline *p, BpfArgs a, cudaStream_t s) {
   constexpr int NT = 128, R = 12;
   int segs = pick_segments(a.n_if, NT * R, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
+  prof_begin(p, "k_bpf_dual", s);
   k_bpf_dual<T, R, NT><<<grid, NT, 0, s>>>(a, make_taps<T>(p->h_stereo), make_taps<T>(p->h_pilot));
   return check_launch(p, "k_bpf_dual");
 }
@@ -242,6 +289,7 @@ static int run_fir_generic(sdr_pipeline *p, const float *x, size_t xs, int xoff,
                            cudaStream_t s) {
   FirGenericArgs g{x, xs, xoff, h, T, D, y, ys, yoff, n_out};
   dim3 grid((n_out + 127) / 128, batch);
+  prof_begin(p, "k_fir_generic", s);
   k_fir_generic<<<grid, 128, T * sizeof(float), s>>>(g);
   return check_launch(p, "k_fir_generic");
 }
@@ -459,6 +507,8 @@ extern "C" int sdr_pipeline_destroy(sdr_pipeline *p) {
     if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
     if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
   }
+  for (auto &st : p->sites)
+    for (auto e : st.ev) cudaEventDestroy(e);
   if (p->s_copy_in) cudaStreamDestroy(p->s_copy_in);
   if (p->s_compute) cudaStreamDestroy(p->s_compute);
   if (p->s_copy_out) cudaStreamDestroy(p->s_copy_out);
@@ -488,6 +538,39 @@ extern "C" int sdr_pipeline_launch_count(sdr_pipeline *p, uint64_t *count, int r
   if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
   if (count) *count = p->launches;
   if (reset) p->launches = 0;
+  return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_profile(sdr_pipeline *p, int enable) {
+  if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
+  p->profiling = enable != 0;
+  return SDR_OK;
+}
+
+extern "C" int sdr_pipeline_kernel_times(sdr_pipeline *p, int index, char *name, size_t name_cap,
+                                         double *total_ms, uint64_t *count, int reset) {
+  if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
+  if (index < 0 || index >= (int)p->sites.size()) return 1;  // past the end (not an error)
+  SDR_CUDA(cudaSetDevice(p->cfg.device));
+  sdr_pipeline::Site &st = p->sites[index];
+  for (size_t i = 0; i + 1 < st.used; i += 2) {
+    SDR_CUDA(cudaEventSynchronize(st.ev[i + 1]));
+    float ms = 0.0f;
+    SDR_CUDA(cudaEventElapsedTime(&ms, st.ev[i], st.ev[i + 1]));
+    st.total_ms += ms;
+    st.count++;
+  }
+  st.used = 0;
+  if (name && name_cap) {
+    std::strncpy(name, st.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (total_ms) *total_ms = st.total_ms;
+  if (count) *count = st.count;
+  if (reset) {
+    st.total_ms = 0.0;
+    st.count = 0;
+  }
   return SDR_OK;
 }
 
@@ -571,6 +654,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
     pa.ncoScale = (float)2.0;
     pa.phaseAdjust = (float)0.0;
     pa.normBandwidth = (float)0.01;
+    prof_begin(p, "k_pll", s);
     k_pll<<<(B + 31) / 32, 32, 0, s>>>(pa);
     if ((rc = check_launch(p, "k_pll"))) return rc;
   }
@@ -595,6 +679,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   if (p->resample) {
     ResampleArgs g{aa, p->d_h_poly.p, p->m.audio_upsamp, p->m.audio_decim, p->TA};
     dim3 grid(((int)n_audio + 127) / 128, B);
+    prof_begin(p, "k_audio_resample", s);
     if (p->stereo) k_audio_resample<true><<<grid, 128, 0, s>>>(g);
     else k_audio_resample<false><<<grid, 128, 0, s>>>(g);
     if ((rc = check_launch(p, "k_audio_resample"))) return rc;
@@ -609,6 +694,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
       return rc;
     if (p->stereo) {
       dim3 g2(((int)(p->HA + n_if) + 127) / 128, B);
+      prof_begin(p, "k_mixer", s);
       k_mixer<<<g2, 128, 0, s>>>(p->stf.p, p->stf_stride, p->nco.p, p->nco_stride, 0,
                                  (int)(p->HA + n_if), p->mix.p, p->stf_stride);
       if ((rc = check_launch(p, "k_mixer"))) return rc;
@@ -617,6 +703,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
         return rc;
     }
     dim3 g3(((int)n_audio + 127) / 128, B);
+    prof_begin(p, "k_pcm_pack", s);
     k_pcm_pack<<<g3, 128, 0, s>>>(p->t_audio.p, p->stereo ? p->t_stfinal.p : nullptr,
                                   p->tap_audio_stride, (int)n_audio, d_pcm, pcm_stride);
     if ((rc = check_launch(p, "k_pcm_pack"))) return rc;
@@ -624,13 +711,16 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   if (taps && p->stereo) {
     // Intermediates that the carry below would clobber are copied out first.
     dim3 g2(((int)(p->HA + n_if) + 127) / 128, B);
+    prof_begin(p, "k_mixer", s);
     k_mixer<<<g2, 128, 0, s>>>(p->stf.p, p->stf_stride, p->nco.p, p->nco_stride, 0,
                                (int)(p->HA + n_if), p->mix.p, p->stf_stride);
     if ((rc = check_launch(p, "k_mixer"))) return rc;
     dim3 g3(((int)n_if + 127) / 128, B);
+    prof_begin(p, "k_copy_rows", s);
     k_copy_rows<<<g3, 128, 0, s>>>(p->nco.p, p->nco_stride, p->HA, p->t_nco.p, p->tap_if_stride,
                                    (int)n_if);
     if ((rc = check_launch(p, "k_copy_rows"))) return rc;
+    prof_begin(p, "k_copy_rows", s);
     k_copy_rows<<<g3, 128, 0, s>>>(p->demod.p, p->demod_stride, p->HD - p->delay, p->t_allpass.p,
                                    p->tap_if_stride, (int)n_if);
     if ((rc = check_launch(p, "k_copy_rows"))) return rc;
@@ -662,6 +752,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   // When taps are kept the carry would overwrite what sdr_pipeline_tap reads
   // (history-prefixed rows), so the tap accessor accounts for it via last_n_if.
   size_t sh = std::max<size_t>((size_t)std::max(p->HD, p->HA + 1) * sizeof(float), (size_t)2 * p->HR);
+  prof_begin(p, "k_carry", s);
   k_carry<<<B, 128, sh, s>>>(ca);
   if ((rc = check_launch(p, "k_carry"))) return rc;
   p->last_n_if = n_if;
