@@ -169,17 +169,29 @@ BLOCK_BYTES = {0: 102400, 1: 61440, 2: 112000, 3: 134400}
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
-def make_device_batch(torch, mode, batch, blocks, kind, device):
-    """[batch, nbytes] uint8 on the device: a few distinct synthetic captures, tiled with a
+def make_host_batch(mode, batch, blocks, kind, out=None):
+    """[batch, nbytes] uint8 on the host: a few distinct synthetic captures, tiled with a
     per-capture circular shift so that every row is a different valid capture."""
     from sdr_b200 import siggen
     distinct = min(batch, 8)
-    base = torch.from_numpy(np.stack([siggen.make_capture(c, mode, blocks, kind) for c in range(distinct)])).to(device)
-    out = torch.empty((batch, base.shape[1]), dtype=torch.uint8, device=device)
+    base = [siggen.make_capture(c, mode, blocks, kind) for c in range(distinct)]
+    n = base[0].size
+    if out is None:
+        out = np.empty((batch, n), np.uint8)
     for c in range(batch):
-        rot = 2 * ((c // distinct) * 977 % (base.shape[1] // 2))
-        out[c] = torch.roll(base[c % distinct], rot) if rot else base[c % distinct]
+        rot = 2 * ((c // distinct) * 977 % (n // 2))
+        src = base[c % distinct]
+        if rot:
+            out[c, :rot] = src[n - rot:]
+            out[c, rot:] = src[:n - rot]
+        else:
+            out[c] = src
     return out
+
+
+def make_device_batch(torch, mode, batch, blocks, kind, device):
+    """Built on the host and uploaded once (not timed), so that no torch kernels run."""
+    return torch.from_numpy(make_host_batch(mode, batch, blocks, kind)).to(device)
 
 
 def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, world, profile=True):
@@ -237,14 +249,9 @@ def time_e2e(torch, sdr, args, steps, dist, world):
     from sdr_b200 import siggen
     dev_index = torch.cuda.current_device()
     blocks = min(args.blocks, args.e2e_blocks)
-    distinct = min(args.batch, 8)
-    base = np.stack([siggen.make_capture(c, args.mode, blocks, "stereo") for c in range(distinct)])
-    nbytes = base.shape[1]
+    nbytes = blocks * BLOCK_BYTES[args.mode]
     h_iq = torch.empty((args.batch, nbytes), dtype=torch.uint8).pin_memory()
-    hv = h_iq.numpy()
-    for c in range(args.batch):
-        rot = 2 * ((c // distinct) * 977 % (nbytes // 2))
-        hv[c] = np.roll(base[c % distinct], rot) if rot else base[c % distinct]
+    make_host_batch(args.mode, args.batch, blocks, "stereo", out=h_iq.numpy())
     p = sdr.Pipeline(mode=args.mode, channels=args.audio_channels, batch=args.batch, device=dev_index,
                      max_bytes_per_channel=nbytes, **TAPS)
     n_pcm = p.pcm_count(nbytes)

@@ -169,6 +169,11 @@ int sdr_pipeline_tap(sdr_pipeline *p, int stage, int channel, float *dst, size_t
  * counter (bench.py reports it as gpu_launches). */
 int sdr_pipeline_launch_count(sdr_pipeline *p, uint64_t *count, int reset);
 
+/* Page-locked host memory for callers that have no CUDA headers (the C++ CLI):
+ * buffers from sdr_host_alloc are DMA-able, so process_host skips its staging copy. */
+int sdr_host_alloc(size_t bytes, void **out);
+int sdr_host_free(void *ptr);
+
 /* Per-kernel device timing (CUDA events on the launching stream, recorded around
  * every kernel of this handle while enabled).  sdr_pipeline_kernel_times walks the
  * kernels by index: returns 0 and fills name/total/count, or 1 past the last one. */

@@ -75,6 +75,8 @@ ABI = {
     "sdr_pipeline_keep_taps": (C.c_int, [_vp, C.c_int]),
     "sdr_pipeline_tap": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sdr_pipeline_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
+    "sdr_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "sdr_host_free": (C.c_int, [_vp]),
     "sdr_pipeline_profile": (C.c_int, [_vp, C.c_int]),
     "sdr_pipeline_kernel_times": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_size_t,
                                             C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),

@@ -541,6 +541,23 @@ extern "C" int sdr_pipeline_launch_count(sdr_pipeline *p, uint64_t *count, int r
   return SDR_OK;
 }
 
+extern "C" int sdr_host_alloc(size_t bytes, void **out) {
+  if (!out) return fail(SDR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(SDR_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+  }
+  SDR_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+  return SDR_OK;
+}
+
+extern "C" int sdr_host_free(void *ptr) {
+  if (ptr) SDR_CUDA(cudaFreeHost(ptr));
+  return SDR_OK;
+}
+
 extern "C" int sdr_pipeline_profile(sdr_pipeline *p, int enable) {
   if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
   p->profiling = enable != 0;

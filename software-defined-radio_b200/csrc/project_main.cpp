@@ -1,0 +1,193 @@
+// project_main.cpp -- drop-in for the reference's `project` executable
+// (src/project.cpp:385-500) and its mono twin `threadMonoOnly`
+// (src/threadMonoOnly.cpp:206-288): raw interleaved unsigned 8-bit I/Q on stdin,
+// native-endian int16 PCM on stdout (mono: one stream; stereo: L,R interleaved),
+// 48 kS/s in modes 0/1 and 44.1 kS/s in modes 2/3.
+//
+//   rtl_sdr -f 99.9M -s 2.4M - | sdr_project 0 2 | aplay -c 2 -f S16_LE -r 48000
+//
+// Usage:  sdr_project                       mode 0, mono          (project.cpp:390-392)
+//         sdr_project <mode>                mode 0-3, mono        (threadMonoOnly.cpp:210-217)
+//         sdr_project <mode> <channels>     channels 1|2          (project.cpp:393-411)
+//   options: --taps rf,audio,stereo   tap counts (default 151,101,151: the functional set of
+//                                     threadMonoOnly.cpp:66,229-232 and model/stereo.py:74-78;
+//                                     project.cpp as shipped is the 13,13,13 timing build)
+//            --blocks N               reference blocks per device call (default 1 = the
+//                                     reference's latency; larger is faster)
+//            --device D               CUDA ordinal
+//
+// The reference's two threads and bounded std::queue (project.cpp:141-149,181-189,471-496)
+// become: a reader thread filling two page-locked buffers, and the main thread handing
+// each full buffer to sdr_pipeline_process_host, which overlaps upload, kernels and
+// download on CUDA streams.  Deliberate deviations: diagnostics go to stderr only, the
+// program drains every complete block and exits 0 at end of input (the reference exits 1
+// from the producer thread and drops up to QUEUE_ELEMS+1 blocks); a trailing partial
+// block is discarded as in the reference (project.cpp:78-79).
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "sdr_b200.h"
+
+namespace {
+
+struct Slot {
+  uint8_t *data = nullptr;
+  size_t bytes = 0;  // valid bytes (multiple of the reference block)
+  bool full = false;
+};
+
+int die(const char *what) {
+  std::fprintf(stderr, "sdr_project: %s: %s\n", what, sdr_last_error());
+  return 2;
+}
+
+void usage(const char *argv0) {
+  std::fprintf(stderr,
+               "Usage: %s\nor\nUsage: %s <mode> [<channels>] [--taps rf,audio,stereo] [--blocks N] [--device D]\n"
+               "\t\t <mode> is a value from 0 to 3, <channels> is 1 (mono) or 2 (stereo)\n",
+               argv0, argv0);
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+  int mode = 0, channels = 1, device = 0, blocks = 1;
+  int rf_taps = 151, audio_taps = 101, stereo_taps = 151;
+  std::vector<std::string> pos;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "--taps" && i + 1 < argc) {
+      if (std::sscanf(argv[++i], "%d,%d,%d", &rf_taps, &audio_taps, &stereo_taps) != 3) {
+        usage(argv[0]);
+        return 1;
+      }
+    } else if (a == "--blocks" && i + 1 < argc) {
+      blocks = std::atoi(argv[++i]);
+    } else if (a == "--device" && i + 1 < argc) {
+      device = std::atoi(argv[++i]);
+    } else if (a == "-h" || a == "--help") {
+      usage(argv[0]);
+      return 0;
+    } else {
+      pos.push_back(a);
+    }
+  }
+  if (pos.size() > 2 || blocks < 1) {
+    usage(argv[0]);
+    return 1;
+  }
+  if (pos.size() >= 1) mode = std::atoi(pos[0].c_str());
+  if (pos.size() == 2) channels = std::atoi(pos[1].c_str());
+  if (mode < 0 || mode > 3) {  // project.cpp:396-399 (the reference lets negatives through atoi)
+    std::fprintf(stderr, "Wrong mode %d\n", mode);
+    return 1;
+  }
+  if (channels < 1 || channels > 2) {  // project.cpp:405-408
+    std::fprintf(stderr, "Wrong number of channels %d\n", channels);
+    return 1;
+  }
+  std::fprintf(stderr, "Operating in mode %d, %s, taps %d/%d/%d\n", mode,
+               channels == 2 ? "stereo" : "mono", rf_taps, audio_taps, stereo_taps);
+
+  sdr_mode_info mi;
+  if (sdr_mode_lookup(mode, channels, &mi)) return die("sdr_mode_lookup");
+  const size_t block_bytes = (size_t)mi.block_bytes;  // project.cpp:55-57
+  const size_t call_bytes = block_bytes * (size_t)blocks;
+  std::fprintf(stderr, "block_size = %zu, %d block(s) per device call\n", block_bytes, blocks);
+
+  sdr_config cfg{};
+  cfg.mode = mode;
+  cfg.channels = channels;
+  cfg.rf_taps = rf_taps;
+  cfg.audio_taps = audio_taps;
+  cfg.stereo_taps = stereo_taps;
+  cfg.batch = 1;
+  cfg.device = device;
+  cfg.variant = SDR_VARIANT_EXACT;
+  cfg.max_bytes_per_channel = call_bytes;
+  sdr_pipeline *pipe = nullptr;
+  if (sdr_pipeline_create(&cfg, &pipe)) return die("sdr_pipeline_create");
+  size_t pcm_per_call = 0;
+  if (sdr_pipeline_pcm_count(pipe, call_bytes, &pcm_per_call)) return die("sdr_pipeline_pcm_count");
+
+  Slot slots[2];
+  int16_t *pcm = nullptr;
+  for (auto &s : slots)
+    if (sdr_host_alloc(call_bytes, reinterpret_cast<void **>(&s.data))) return die("sdr_host_alloc");
+  if (sdr_host_alloc(pcm_per_call * sizeof(int16_t), reinterpret_cast<void **>(&pcm)))
+    return die("sdr_host_alloc");
+
+  std::mutex mu;
+  std::condition_variable cv;
+  bool eof = false;
+
+  // Producer: fills the two pinned buffers alternately (the reference's RF_FrontEnd read loop).
+  std::thread reader([&] {
+    for (int k = 0;; k ^= 1) {
+      Slot &s = slots[k];
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !s.full; });
+      }
+      size_t got = 0;
+      while (got < call_bytes) {
+        size_t n = std::fread(s.data + got, 1, call_bytes - got, stdin);
+        if (n == 0) break;
+        got += n;
+      }
+      const size_t whole = got / block_bytes * block_bytes;  // partial block is dropped
+      std::unique_lock<std::mutex> lk(mu);
+      s.bytes = whole;
+      s.full = true;
+      if (got < call_bytes) eof = true;
+      cv.notify_all();
+      if (eof) return;
+    }
+  });
+
+  // Consumer: device calls + PCM out (the reference's RF_MONO / RF_STEREO loop).
+  int rc = 0;
+  size_t total_in = 0, total_out = 0;
+  for (int k = 0;; k ^= 1) {
+    Slot &s = slots[k];
+    bool last;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return s.full; });
+      last = eof;
+    }
+    if (s.bytes) {
+      size_t n_pcm = 0;
+      sdr_pipeline_pcm_count(pipe, s.bytes, &n_pcm);
+      if (sdr_pipeline_process_host(pipe, s.data, s.bytes, s.bytes, pcm, n_pcm)) {
+        rc = die("sdr_pipeline_process_host");
+        break;
+      }
+      std::fwrite(pcm, sizeof(int16_t), n_pcm, stdout);
+      total_in += s.bytes;
+      total_out += n_pcm;
+    }
+    const bool short_read = s.bytes < call_bytes;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      s.full = false;
+      cv.notify_all();
+    }
+    if (last && short_read) break;
+  }
+  std::fflush(stdout);
+  if (rc) std::_Exit(rc);  // reader may be blocked in fread
+  reader.join();
+  std::fprintf(stderr, "End of input stream reached: %zu bytes in, %zu PCM samples out\n", total_in,
+               total_out);
+  for (auto &s : slots) sdr_host_free(s.data);
+  sdr_host_free(pcm);
+  sdr_pipeline_destroy(pipe);
+  return 0;
+}
