@@ -28,10 +28,14 @@ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // Taps travel as a kernel parameter: with the tap index a compile-time constant
 // after unrolling, every tap is a constant-bank operand of its FMUL and costs no
 // load instruction and no register.
-template <int T>
+template <int N>
 struct TapArray {
-  float h[round_up(T, 4)];
+  float h[N];
 };
+// Tap storage needed by the two FIR cores for a T-tap, decimate-by-D filter.
+constexpr int taps_window(int T) { return round_up(T, 4); }
+constexpr int fir_groups_count(int T, int D, int R) { return round_up((T + D - 1) / D, R); }
+constexpr int taps_groups(int T, int D, int R) { return fir_groups_count(T, D, R) * D; }
 
 // ---------------------------------------------------------------------------
 // Register-tiled FIR core.  One thread produces R consecutive outputs of a
@@ -40,16 +44,27 @@ struct TapArray {
 // window is walked from the newest sample to the oldest so that each accumulator
 // sees its taps in ascending order (n = r*D - e grows as e falls).
 // ---------------------------------------------------------------------------
+// Shared-memory rows are stored in groups of G = R*D samples (one thread's share of a
+// tile) separated by PAD floats, chosen so that the per-thread stride (G+PAD)/4 is odd:
+// a quarter-warp's LDS.128 then touches 8 distinct 16-byte bank groups (no conflict).
+constexpr int fir_pad(int G) { return ((G / 4) % 2 == 1) ? 0 : 4; }
+constexpr int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+// Offset (in floats) of sample `e` relative to the first sample of a thread's own group.
+constexpr int fir_off(int e, int G) { return e + fir_pad(G) * floordiv(e, G); }
+
 template <int T, int D, int R, int HALO>
-__device__ __forceinline__ void fir_window(const float *__restrict__ w, const TapArray<T> &taps,
-                                           float (&acc)[R]) {
+__device__ __forceinline__ void fir_window(const float *__restrict__ w,
+                                           const TapArray<taps_window(T)> &taps, float (&acc)[R]) {
+  // `w` points at the sample of the thread's FIRST output (e = 0).
   static_assert(HALO % 4 == 0 && HALO >= T - 1, "halo must cover the filter and be float4-aligned");
+  static_assert((R * D) % 4 == 0, "group size must keep float4 alignment");
+  constexpr int G = R * D;
   constexpr int NEWEST = (R - 1) * D;              // newest sample used, relative to first output
   constexpr int C_HI = (HALO + NEWEST) / 4;        // chunk holding the newest sample
   constexpr int C_LO = (HALO - (T - 1)) / 4;       // chunk holding the oldest sample
 #pragma unroll
   for (int c = C_HI; c >= C_LO; --c) {
-    const float4 v = *reinterpret_cast<const float4 *>(w + 4 * c);
+    const float4 v = *reinterpret_cast<const float4 *>(w + fir_off(4 * c - HALO, G));
 #pragma unroll
     for (int j = 3; j >= 0; --j) {
       const int e = 4 * c + j - HALO;
@@ -63,16 +78,145 @@ __device__ __forceinline__ void fir_window(const float *__restrict__ w, const Ta
   }
 }
 
-// Same sum for ONE output with a run-time loop (used once per segment for the
-// sample that precedes the segment; not performance relevant).
-template <int T>
-__device__ __forceinline__ float fir_single(const float *__restrict__ newest,
-                                            const TapArray<T> &taps) {
-  float acc = 0.0f;
+// ---------------------------------------------------------------------------
+// Looped FIR core ("tap groups").  The T taps are cut into groups of D:
+//   y_r = sum_g sum_j h[D*g + j] * x[D*(r-g) - j]
+// so that in step g every one of the thread's R outputs uses the SAME D taps (which
+// therefore live in uniform registers / the constant bank) and the input block
+// b = r-g of D samples.  Going from g to g+1 the R blocks in flight shift by one:
+// R-1 stay in registers, one new block (b = -g) is loaded.  Unrolling the g loop by
+// R makes the register renaming static, the loop body stays R*R*D multiply-adds
+// however long the filter is -- a few KB of code instead of the tens of KB of the
+// fully unrolled window walk, which is what the instruction cache needs (profiles/).
+// Per output the taps are still visited in ascending order n = D*g + j with one
+// rounding per multiply and per add, i.e. bit-identical to the reference loops.
+// The tap array is zero-padded to a whole number of groups; a zero tap adds +-0 to
+// an accumulator that is never -0, so padding changes no bit as long as the inputs
+// are finite (true for every signal inside the pipeline).
+// `w` points at the thread's first output's newest sample (e = 0) inside a padded
+// row (RowGeom); one thread's share of a tile is exactly one group of G = R*D floats.
+// ---------------------------------------------------------------------------
+template <int T, int D, int R>
+__device__ __forceinline__ void fir_groups(const float *__restrict__ w,
+                                           const TapArray<taps_groups(T, D, R)> &taps,
+                                           float (&acc)[R]) {
+  constexpr int G = R * D;
+  constexpr int STRIDE = G + fir_pad(G);
+  constexpr int NG = fir_groups_count(T, D, R);
+  static_assert(G % 4 == 0, "group must keep float4 alignment");
+  float xb[R][D];  // block in slot s holds x[D*b - j], j = 0..D-1, for the block b == s (mod R)
+  // prologue: blocks 1..R-1 lie in the thread's own group, e in [1, D*(R-1)]
+  {
+    constexpr int NCH = (D * (R - 1)) / 4 + 1;
+    float own[NCH * 4];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const float4 v = *reinterpret_cast<const float4 *>(w + 4 * c);
+      own[4 * c] = v.x; own[4 * c + 1] = v.y; own[4 * c + 2] = v.z; own[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int b = 1; b < R; ++b)
+#pragma unroll
+      for (int j = 0; j < D; ++j) xb[b][j] = own[D * b - j];
+  }
 #pragma unroll 1
-  for (int n = 0; n < T; ++n) acc = xmac(acc, taps.h[n], newest[-n]);
-  return acc;
+  for (int p = 0; p < NG / R; ++p) {
+    const float *base = w - p * STRIDE;   // e = -G*p
+    const float *hp = taps.h + p * G;     // taps of groups R*p .. R*p+R-1
+    // samples e_rel in [-G, 3]: the previous group (one STRIDE back) plus the first chunk here
+    float xv[G + 4];
+#pragma unroll
+    for (int c = 0; c < G / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4 *>(base - STRIDE + 4 * c);
+      xv[4 * c] = v.x; xv[4 * c + 1] = v.y; xv[4 * c + 2] = v.z; xv[4 * c + 3] = v.w;
+    }
+    {
+      const float4 v = *reinterpret_cast<const float4 *>(base);
+      xv[G] = v.x; xv[G + 1] = v.y; xv[G + 2] = v.z; xv[G + 3] = v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      // new block b = -(R*p + c): e_rel = -D*c - j  ->  xv[G - D*c - j]
+#pragma unroll
+      for (int j = 0; j < D; ++j) xb[(R - c) % R][j] = xv[G - D * c - j];
+#pragma unroll
+      for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = xmac(acc[r], hp[D * c + j], xb[(r - c + R) % R][j]);
+    }
+  }
 }
+
+// Two filters over the same input window (the stereo and pilot band-pass filters read
+// the same demodulated samples): identical walk, two tap sets, two accumulator sets.
+template <int T, int D, int R>
+__device__ __forceinline__ void fir_groups2(const float *__restrict__ w,
+                                            const TapArray<taps_groups(T, D, R)> &taps_a,
+                                            const TapArray<taps_groups(T, D, R)> &taps_b,
+                                            float (&acc_a)[R], float (&acc_b)[R]) {
+  constexpr int G = R * D;
+  constexpr int STRIDE = G + fir_pad(G);
+  constexpr int NG = fir_groups_count(T, D, R);
+  static_assert(G % 4 == 0, "group must keep float4 alignment");
+  float xb[R][D];
+  {
+    constexpr int NCH = (D * (R - 1)) / 4 + 1;
+    float own[NCH * 4];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const float4 v = *reinterpret_cast<const float4 *>(w + 4 * c);
+      own[4 * c] = v.x; own[4 * c + 1] = v.y; own[4 * c + 2] = v.z; own[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int b = 1; b < R; ++b)
+#pragma unroll
+      for (int j = 0; j < D; ++j) xb[b][j] = own[D * b - j];
+  }
+#pragma unroll 1
+  for (int p = 0; p < NG / R; ++p) {
+    const float *base = w - p * STRIDE;
+    const float *ha = taps_a.h + p * G;
+    const float *hb = taps_b.h + p * G;
+    float xv[G + 4];
+#pragma unroll
+    for (int c = 0; c < G / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4 *>(base - STRIDE + 4 * c);
+      xv[4 * c] = v.x; xv[4 * c + 1] = v.y; xv[4 * c + 2] = v.z; xv[4 * c + 3] = v.w;
+    }
+    {
+      const float4 v = *reinterpret_cast<const float4 *>(base);
+      xv[G] = v.x; xv[G + 1] = v.y; xv[G + 2] = v.z; xv[G + 3] = v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) xb[(R - c) % R][j] = xv[G - D * c - j];
+#pragma unroll
+      for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc_a[r] = xmac(acc_a[r], ha[D * c + j], xb[(r - c + R) % R][j]);
+          acc_b[r] = xmac(acc_b[r], hb[D * c + j], xb[(r - c + R) % R][j]);
+        }
+    }
+  }
+}
+
+// Geometry of one padded shared-memory row holding tile samples [-HALO, TILE_IN).
+template <int D, int R, int NT, int HALO>
+struct RowGeom {
+  static constexpr int G = R * D;
+  static constexpr int PAD = fir_pad(G);
+  static constexpr int HALO_G = (HALO + G - 1) / G;       // groups in front of sample 0
+  static constexpr int ORIGIN = HALO_G * (G + PAD);       // float position of sample 0
+  static constexpr int FLOATS = ORIGIN + NT * (G + PAD) + 8;
+  // position of tile sample a (a >= -HALO); a may be a run-time value
+  __device__ static __forceinline__ int pos(int a) {
+    const int ap = a + HALO_G * G;
+    return ap + PAD * (ap / G);
+  }
+  __device__ static __forceinline__ int thread_base(int t) { return ORIGIN + t * (G + PAD); }
+};
 
 // ---------------------------------------------------------------------------
 // K1: RF front end.  uint8 I/Q -> (u8-128)/128 -> low-pass + decimate (I and Q)
@@ -118,19 +262,24 @@ __device__ __forceinline__ void rf_fetch_pair(const RfArgs &a, const uint8_t *ro
   fq = u8_centered(bq);
 }
 
-template <int T, int D, int R, int NT>
+template <int T, int D, int R, int NT, int ALGO>
 struct RfCfg {
-  static constexpr int HALO = round_up(T - 1 + D, 8);
+  static constexpr int NTAPS = ALGO ? taps_groups(T, D, R) : taps_window(T);
+  static constexpr int HALO_MIN = ALGO ? (fir_groups_count(T, D, R) * D + D) : (T - 1 + D);
+  static constexpr int HALO = round_up(HALO_MIN, 8);
   static constexpr int TILE_OUT = NT * R;
   static constexpr int TILE_IN = TILE_OUT * D;
-  static constexpr int ROW = HALO + TILE_IN + 8;  // floats per component in smem
+  using Geom = RowGeom<D, R, NT, HALO>;
+  static constexpr int ROW = round_up(Geom::FLOATS, 4);  // floats per component in smem
   static constexpr size_t SMEM = (size_t)ROW * 2 * sizeof(float);
 };
 
-template <int T, int D, int R, int NT>
+// ALGO 0: fully unrolled window walk (fir_window); ALGO 1: looped tap groups (fir_groups).
+template <int T, int D, int R, int NT, bool MERGE, int ALGO>
 __global__ void __launch_bounds__(NT)
-k_rf_demod(const RfArgs a, const __grid_constant__ TapArray<T> taps) {
-  using Cfg = RfCfg<T, D, R, NT>;
+k_rf_demod(const RfArgs a, const __grid_constant__ TapArray<RfCfg<T, D, R, NT, ALGO>::NTAPS> taps) {
+  using Cfg = RfCfg<T, D, R, NT, ALGO>;
+  using Geom = typename Cfg::Geom;
   constexpr int HALO = Cfg::HALO;
   extern __shared__ __align__(16) float smem[];
   float *xi = smem;
@@ -172,12 +321,11 @@ k_rf_demod(const RfArgs a, const __grid_constant__ TapArray<T> taps) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) rf_fetch_pair<T, D>(a, row, hrow, i + k, fi[k], fq[k]);
       }
-      float4 *di = reinterpret_cast<float4 *>(xi + 8 * q);
-      float4 *dq = reinterpret_cast<float4 *>(xq + 8 * q);
-      di[0] = make_float4(fi[0], fi[1], fi[2], fi[3]);
-      di[1] = make_float4(fi[4], fi[5], fi[6], fi[7]);
-      dq[0] = make_float4(fq[0], fq[1], fq[2], fq[3]);
-      dq[1] = make_float4(fq[4], fq[5], fq[6], fq[7]);
+      const int p0 = Geom::pos(8 * q - HALO), p1 = Geom::pos(8 * q + 4 - HALO);
+      *reinterpret_cast<float4 *>(xi + p0) = make_float4(fi[0], fi[1], fi[2], fi[3]);
+      *reinterpret_cast<float4 *>(xi + p1) = make_float4(fi[4], fi[5], fi[6], fi[7]);
+      *reinterpret_cast<float4 *>(xq + p0) = make_float4(fq[0], fq[1], fq[2], fq[3]);
+      *reinterpret_cast<float4 *>(xq + p1) = make_float4(fq[4], fq[5], fq[6], fq[7]);
     }
     __syncthreads();
     // ---- I,Q of the output that precedes this segment (fmDemod's prev_i/prev_q) ----
@@ -186,17 +334,42 @@ k_rf_demod(const RfArgs a, const __grid_constant__ TapArray<T> taps) {
       if (o_begin == 0) {
         v = a.prev_in[2 * b + t];
       } else {
-        const float *src = (t == 0 ? xi : xq) + HALO - D;  // sample (o0-1)*D
-        v = xmul(fir_single<T>(src, taps), 0.0078125f);
+        const float *src = (t == 0 ? xi : xq);
+        float acc = 0.0f;  // output o0-1: newest sample is tile sample -D
+#pragma unroll 1
+        for (int n = 0; n < T; ++n) acc = xmac(acc, taps.h[n], src[Geom::pos(-D - n)]);
+        v = xmul(acc, 0.0078125f);
       }
       (t == 0 ? edge_i : edge_q)[0] = v;
     }
     // ---- R outputs per thread for I and Q ----
     float ai[R], aq[R];
+    if (MERGE) {
+      // one copy of the unrolled FIR body, run twice: halves the instruction footprint
+#pragma unroll 1
+      for (int comp = 0; comp < 2; ++comp) {
+        float acc[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) ai[r] = aq[r] = 0.0f;
-    fir_window<T, D, R, HALO>(xi + t * (R * D), taps, ai);
-    fir_window<T, D, R, HALO>(xq + t * (R * D), taps, aq);
+        for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+        if constexpr (ALGO) fir_groups<T, D, R>(smem + comp * Cfg::ROW + Geom::thread_base(t), taps, acc);
+        else fir_window<T, D, R, HALO>(smem + comp * Cfg::ROW + Geom::thread_base(t), taps, acc);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (comp == 0) ai[r] = acc[r];
+          else aq[r] = acc[r];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) ai[r] = aq[r] = 0.0f;
+      if constexpr (ALGO) {
+        fir_groups<T, D, R>(xi + Geom::thread_base(t), taps, ai);
+        fir_groups<T, D, R>(xq + Geom::thread_base(t), taps, aq);
+      } else {
+        fir_window<T, D, R, HALO>(xi + Geom::thread_base(t), taps, ai);
+        fir_window<T, D, R, HALO>(xq + Geom::thread_base(t), taps, aq);
+      }
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {  // exact power-of-two scaling: (u8-128)/128
       ai[r] = xmul(ai[r], 0.0078125f);
@@ -321,13 +494,15 @@ struct AudioCfg {
   static constexpr int HALO = round_up(T - 1, 4);
   static constexpr int TILE_OUT = NT * R;
   static constexpr int TILE_IN = TILE_OUT * D;
-  static constexpr int ROW = HALO + TILE_IN + 4;
+  using Geom = RowGeom<D, R, NT, HALO>;
+  static constexpr int ROW = round_up(Geom::FLOATS, 4);
 };
 
 template <int T, int D, int R, int NT, bool STEREO>
 __global__ void __launch_bounds__(NT)
-k_audio_fir(const AudioArgs a, const __grid_constant__ TapArray<T> taps) {
+k_audio_fir(const AudioArgs a, const __grid_constant__ TapArray<taps_window(T)> taps) {
   using Cfg = AudioCfg<T, D, R, NT>;
+  using Geom = typename Cfg::Geom;
   constexpr int HALO = Cfg::HALO;
   extern __shared__ __align__(16) float smem[];
   float *xm = smem;             // mono-path input
@@ -347,15 +522,16 @@ k_audio_fir(const AudioArgs a, const __grid_constant__ TapArray<T> taps) {
     for (int q = t; q < HALO + Cfg::TILE_IN; q += NT) {
       const long long i = s0 + q;
       const bool ok = i < n_in;  // history prefix makes negative indices valid
-      xm[q] = ok ? drow[i] : 0.0f;
-      if (STEREO) xs[q] = ok ? xmul(xmul(srow[i], nrow[i]), 2.0f) : 0.0f;
+      const int pq = Geom::pos(q - HALO);
+      xm[pq] = ok ? drow[i] : 0.0f;
+      if (STEREO) xs[pq] = ok ? xmul(xmul(srow[i], nrow[i]), 2.0f) : 0.0f;
     }
     __syncthreads();
     float am[R], as[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) am[r] = as[r] = 0.0f;
-    fir_window<T, D, R, HALO>(xm + t * (R * D), taps, am);
-    if (STEREO) fir_window<T, D, R, HALO>(xs + t * (R * D), taps, as);
+    fir_window<T, D, R, HALO>(xm + Geom::thread_base(t), taps, am);
+    if (STEREO) fir_window<T, D, R, HALO>(xs + Geom::thread_base(t), taps, as);
     const int o = o0 + t * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -452,6 +628,110 @@ static __global__ void k_audio_resample(const ResampleArgs g) {
   if (a.audio_filt) a.audio_filt[(size_t)b * a.tap_stride + j] = am;
 }
 
+// K6r, throughput form: one LANE per capture.  Consecutive outputs of one capture use
+// different polyphase rows and input offsets that are not multiples of anything useful,
+// so with lanes along time every shared-memory access conflicts.  With 32 captures across
+// the lanes instead, the tap is the same for the whole warp (one broadcast LDS.128 brings
+// four taps) and the 32 inputs x[c][i] sit in 32 different banks of a transposed tile.
+// CTA = 32 captures x RS_J outputs; warp w computes outputs w, w+NW, ... of the tile.
+constexpr int RS_J = 32;    // outputs per tile
+constexpr int RS_NW = 8;    // warps per CTA
+constexpr int RS_PITCH = 33;
+
+template <bool STEREO>
+static __global__ void __launch_bounds__(RS_NW * 32)
+k_audio_resample_v2(const ResampleArgs g, int batch, int rows_cap) {
+  const AudioArgs &a = g.a;
+  extern __shared__ __align__(16) float smem[];
+  const int TA4 = (g.TA + 3) & ~3;
+  float *hs = smem;                                  // [RS_J][TA4] taps of the tile's phases
+  float *xs = hs + RS_J * TA4;                       // [rows_cap][33] mono-path input, transposed
+  float *xs2 = xs + (size_t)rows_cap * RS_PITCH;     // stereo-path input (mixer), transposed
+  int16_t *ps = reinterpret_cast<int16_t *>(xs + (size_t)rows_cap * RS_PITCH * (STEREO ? 2 : 1));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = blockIdx.x * RS_J;
+  const int jn = min(RS_J, a.n_out - j0);
+  const int c0 = blockIdx.y * 32;
+  const long long m0 = (long long)j0 * g.D;
+  const long long i_lo = m0 / g.U - (g.TA - 1);                    // oldest input of the tile
+  const long long i_hi = ((long long)(j0 + jn - 1) * g.D) / g.U;   // newest input of the tile
+  const int rows = (int)(i_hi - i_lo + 1);
+  // ---- taps of the jn phases, zero padded to TA4 ----
+  for (int idx = threadIdx.x; idx < jn * TA4; idx += blockDim.x) {
+    const int jj = idx / TA4, k = idx - jj * TA4;
+    const int ph = (int)(((long long)(j0 + jj) * g.D) % g.U);
+    hs[idx] = (k < g.TA) ? __ldg(g.hp + (size_t)ph * g.TA + k) : 0.0f;
+  }
+  // ---- transposed input tiles: each warp streams whole rows of its captures ----
+  for (int c = warp; c < 32; c += RS_NW) {
+    const int ch = c0 + c;
+    if (ch < batch) {
+      const float *drow = a.demod + (size_t)ch * a.demod_stride + a.demod_off - a.delay + i_lo;
+      const float *srow = STEREO ? a.stf + (size_t)ch * a.stf_stride + a.hist_off + i_lo : nullptr;
+      const float *nrow = STEREO ? a.nco + (size_t)ch * a.nco_stride + a.hist_off + i_lo : nullptr;
+      for (int i = lane; i < rows; i += 32) {
+        xs[i * RS_PITCH + c] = drow[i];
+        if (STEREO) xs2[i * RS_PITCH + c] = xmul(xmul(srow[i], nrow[i]), 2.0f);
+      }
+    } else {
+      for (int i = lane; i < rows; i += 32) {
+        xs[i * RS_PITCH + c] = 0.0f;
+        if (STEREO) xs2[i * RS_PITCH + c] = 0.0f;
+      }
+    }
+  }
+  __syncthreads();
+  const float fu = (float)g.U;
+  for (int jj = warp; jj < jn; jj += RS_NW) {
+    const long long m = (long long)(j0 + jj) * g.D;
+    const int top = (int)(m / g.U - i_lo);   // row of the newest input of this output
+    const float *h = hs + jj * TA4;
+    const float *x = xs + top * RS_PITCH + lane;
+    const float *x2 = xs2 + top * RS_PITCH + lane;
+    float am = 0.0f, as = 0.0f;
+    int k = 0;
+    for (; k + 4 <= g.TA; k += 4) {
+      const float4 hv = *reinterpret_cast<const float4 *>(h + k);
+      am = xmac(am, hv.x, x[-(k + 0) * RS_PITCH]);
+      am = xmac(am, hv.y, x[-(k + 1) * RS_PITCH]);
+      am = xmac(am, hv.z, x[-(k + 2) * RS_PITCH]);
+      am = xmac(am, hv.w, x[-(k + 3) * RS_PITCH]);
+      if (STEREO) {
+        as = xmac(as, hv.x, x2[-(k + 0) * RS_PITCH]);
+        as = xmac(as, hv.y, x2[-(k + 1) * RS_PITCH]);
+        as = xmac(as, hv.z, x2[-(k + 2) * RS_PITCH]);
+        as = xmac(as, hv.w, x2[-(k + 3) * RS_PITCH]);
+      }
+    }
+    for (; k < g.TA; ++k) {
+      am = xmac(am, h[k], x[-k * RS_PITCH]);
+      if (STEREO) as = xmac(as, h[k], x2[-k * RS_PITCH]);
+    }
+    am = xadd(am, xmul(am, fu));  // filter.cpp:213
+    if (STEREO) as = xadd(as, xmul(as, fu));
+    const int ch = c0 + lane;
+    if (STEREO) {
+      ps[(lane * RS_J + jj) * 2] = pcm16(xadd(as, am));
+      ps[(lane * RS_J + jj) * 2 + 1] = pcm16(xsub(am, as));
+    } else {
+      ps[lane * RS_J + jj] = pcm16(am);
+    }
+    if (ch < batch) {
+      if (a.audio_filt) a.audio_filt[(size_t)ch * a.tap_stride + j0 + jj] = am;
+      if (STEREO && a.stereo_final) a.stereo_final[(size_t)ch * a.tap_stride + j0 + jj] = as;
+    }
+  }
+  __syncthreads();
+  // ---- PCM rows out: one capture per warp pass, contiguous int16 along time ----
+  constexpr int PER = STEREO ? 2 : 1;
+  for (int c = warp; c < 32; c += RS_NW) {
+    const int ch = c0 + c;
+    if (ch >= batch) continue;
+    int16_t *dst = a.pcm + (size_t)ch * a.pcm_stride + (size_t)j0 * PER;
+    for (int q = lane; q < jn * PER; q += 32) dst[q] = ps[c * RS_J * PER + q];
+  }
+}
+
 // Stand-alone resampler on float in/out (no PCM), for sdr_fir_resample.
 struct ResampleOpArgs {
   const float *x;  // sample 0 at x_off, TA-1 history before it
@@ -526,11 +806,12 @@ struct BpfArgs {
 
 template <int T, int R, int NT>
 __global__ void __launch_bounds__(NT)
-k_bpf_dual(const BpfArgs a, const __grid_constant__ TapArray<T> h_stereo,
-           const __grid_constant__ TapArray<T> h_pilot) {
-  constexpr int HALO = round_up(T - 1, 4);
+k_bpf_dual(const BpfArgs a, const __grid_constant__ TapArray<taps_groups(T, 1, R)> h_stereo,
+           const __grid_constant__ TapArray<taps_groups(T, 1, R)> h_pilot) {
+  constexpr int HALO = round_up(taps_groups(T, 1, R) + R, 4);
   constexpr int TILE = NT * R;
-  __shared__ __align__(16) float xs[HALO + TILE + 4];
+  using Geom = RowGeom<1, R, NT, HALO>;
+  __shared__ __align__(16) float xs[round_up(Geom::FLOATS, 4)];
   const int t = threadIdx.x;
   const int b = blockIdx.y;
   const int o_begin = blockIdx.x * a.outs_per_seg;
@@ -540,14 +821,15 @@ k_bpf_dual(const BpfArgs a, const __grid_constant__ TapArray<T> h_stereo,
     __syncthreads();
     for (int q = t; q < HALO + TILE; q += NT) {
       const int i = o0 - HALO + q;
-      xs[q] = (i < a.n_if) ? drow[i] : 0.0f;
+      // the padded taps reach further back than the real filter: those samples only meet
+      // zero taps, but they must be finite, so positions before the history read as 0
+      xs[Geom::pos(q - HALO)] = (i < a.n_if && i >= -a.demod_off) ? drow[i] : 0.0f;
     }
     __syncthreads();
     float as[R], ap[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) as[r] = ap[r] = 0.0f;
-    fir_window<T, 1, R, HALO>(xs + t * R, h_stereo, as);
-    fir_window<T, 1, R, HALO>(xs + t * R, h_pilot, ap);
+    fir_groups2<T, 1, R>(xs + Geom::thread_base(t), h_stereo, h_pilot, as, ap);
     const int o = o0 + t * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -591,19 +873,37 @@ static __global__ void k_pll(const PllArgs a) {
   // filter.cpp:68: 2*PI*(freq/Fs) evaluated in double from the float quotient
   const double w = __dmul_rn(6.283185307179586476925286766559, (double)xdiv(a.freq, a.Fs));
   float last = st[4];
+  // The NCO output of sample k is not fed back, so it is evaluated one iteration late,
+  // next to (and overlapped with) the feedback chain of sample k+1.
+  float pending_arg = 0.0f;
+  bool have_pending = false;
+  float xnext = (a.n > 0) ? in[0] : 0.0f;
   for (int k = 0; k < a.n; ++k) {
-    const float x = in[k];
+    const float x = xnext;
+    if (k + 1 < a.n) xnext = in[k + 1];
     const float eI = xmul(x, fbI);
     const float eQ = xmul(x, -fbQ);
-    const float eD = atan2f_glibc(eQ, eI);
+    float eD;
+    if (!atan2f_common(eQ, eI, eD)) eD = atan2f_glibc(eQ, eI);
+    {
+      const float c = cosf_glibc_bf(pending_arg);  // NCO output of sample k-1
+      if (have_pending) {
+        last = c;
+        out[k] = c;
+      }
+    }
     integrator = xadd(integrator, xmul(Ki, eD));
     phaseEst = xadd(xadd(phaseEst, xmul(Kp, eD)), integrator);
     trigOffset = xadd(trigOffset, 1.0f);
     const float trigArg =
         __double2float_rn(__dadd_rn(__dmul_rn(w, (double)trigOffset), (double)phaseEst));
-    sincosf_glibc(trigArg, fbQ, fbI);
-    last = cosf_glibc(xadd(xmul(trigArg, a.ncoScale), a.phaseAdjust));
-    out[k + 1] = last;
+    sincosf_glibc_bf(trigArg, fbQ, fbI);
+    pending_arg = xadd(xmul(trigArg, a.ncoScale), a.phaseAdjust);
+    have_pending = true;
+  }
+  if (have_pending) {
+    last = cosf_glibc_bf(pending_arg);
+    out[a.n] = last;
   }
   st[0] = integrator;
   st[1] = phaseEst;

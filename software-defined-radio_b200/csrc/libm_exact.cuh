@@ -217,4 +217,116 @@ __device__ __forceinline__ float cosf_glibc(float y) {
   return (r.n & 1) ? trig_sin_poly(r.x, x2, r.q) : trig_cos_poly(x2, r.q);
 }
 
+
+// ---------------------------------------------------------------------------
+// Branch-free forms for the PLL's inner loop.  One lane walks one capture
+// sequentially, so the loop is bound by the LATENCY of its dependent chain, not by
+// issue slots; removing the data-dependent branches lets the scheduler overlap the
+// independent pieces (the two Horner chains of atanf, the sine and cosine
+// polynomials, the NCO output of the previous sample).  Every value is produced by
+// the same operations as in the branchy forms above; only the selection of
+// constants and results is done with selects instead of jumps.
+// ---------------------------------------------------------------------------
+
+// atan2f for the common case: x, y finite and non-zero, x != 1.0f, exponents within 2^60
+// of each other, |y/x| < 2^25.  Returns false (and leaves `out` alone) otherwise; the
+// caller then falls back to atan2f_glibc.
+__device__ __forceinline__ bool atan2f_common(float y, float x, float &out) {
+  const float pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+  const int32_t hx = __float_as_int(x), hy = __float_as_int(y);
+  const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+  const int32_t k = (iy - ix) >> 23;
+  const float t = fabsf(xdiv(y, x));
+  const int32_t it = __float_as_int(t);
+  const bool common = (iy != 0) & (ix != 0) & (ix < 0x7f800000) & (iy < 0x7f800000) &
+                      (hx != 0x3f800000) & (k <= 60) & (k >= -60) & (it < 0x4c000000);
+  if (!common) return false;
+  // atanf(t), t >= 0: argument reduction x = num/den with per-range constants
+  //   range        num                den               hi/lo
+  //   t < 7/16     t                  1                 0
+  //   < 11/16      2t - 1             2 + t             atan(0.5)
+  //   < 19/16      t - 1              t + 1             atan(1)
+  //   < 39/16      t - 1.5            1 + 1.5t          atan(1.5)
+  //   else         -1                 t                 atan(inf)
+  const bool r0 = it < 0x3ee00000, r1 = it < 0x3f300000, r2 = it < 0x3f980000, r3 = it < 0x401c0000;
+  const float na = r0 ? 1.0f : r1 ? 2.0f : r3 ? 1.0f : 0.0f;
+  const float nb = r0 ? 0.0f : r2 ? -1.0f : r3 ? -1.5f : -1.0f;
+  const float da = r0 ? 0.0f : r2 ? 1.0f : r3 ? 1.5f : 1.0f;
+  const float db = r0 ? 1.0f : r1 ? 2.0f : r3 ? 1.0f : 0.0f;
+  const float hi = r0 ? 0.0f : r1 ? 4.6364760399e-01f : r2 ? 7.8539812565e-01f : r3 ? 9.8279368877e-01f : 1.5707962513e+00f;
+  const float lo = r0 ? 0.0f : r1 ? 5.0121582440e-09f : r2 ? 3.7748947079e-08f : r3 ? 3.4473217170e-08f : 7.5497894159e-08f;
+  const float num = xadd(xmul(na, t), nb);
+  const float den = xadd(xmul(da, t), db);
+  const float xr = xdiv(num, den);
+  const float a0 = 3.3333334327e-01f, a1 = -2.0000000298e-01f, a2 = 1.4285714924e-01f,
+              a3 = -1.1111110449e-01f, a4 = 9.0908870101e-02f, a5 = -7.6918758452e-02f,
+              a6 = 6.6610731184e-02f, a7 = -5.8335702866e-02f, a8 = 4.9768779427e-02f,
+              a9 = -3.6531571299e-02f, a10 = 1.6285819933e-02f;
+  const float z = xmul(xr, xr);
+  const float w = xmul(z, z);
+  const float s1 = xmul(z, xadd(a0, xmul(w, xadd(a2, xmul(w, xadd(a4, xmul(w, xadd(a6, xmul(w, xadd(a8, xmul(w, a10)))))))))));
+  const float s2 = xmul(w, xadd(a1, xmul(w, xadd(a3, xmul(w, xadd(a5, xmul(w, xadd(a7, xmul(w, a9)))))))));
+  const float ts = xmul(xr, xadd(s1, s2));
+  // r0: x - x*(s1+s2); otherwise hi - ((x*(s1+s2) - lo) - x).  With hi = lo = 0 the second
+  // form evaluates to the first one bit for bit (negation commutes with rounding).
+  const float zz = xsub(hi, xsub(xsub(ts, lo), xr));
+  // quadrant (e_atan2f.c switch on m = 2*sign(x) + sign(y))
+  const float zl = xsub(zz, pi_lo);
+  const bool xneg = hx < 0, yneg = hy < 0;
+  const float pos = xneg ? xsub(pi, zl) : zz;
+  const float neg = xneg ? xsub(zl, pi) : __int_as_float(__float_as_int(zz) ^ (int32_t)0x80000000);
+  out = yneg ? neg : pos;
+  return true;
+}
+
+// Branch-free argument reduction: all three glibc paths are evaluated and the one
+// that applies is selected.  `special`: 0 normal, 1 |y| < 2^-12, 2 inf/nan.
+__device__ __forceinline__ int trig_reduce_bf(float y, TrigRed &r) {
+  const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+  const uint32_t bits = __float_as_uint(y);
+  const uint32_t top = (bits >> 20) & 0x7ff;
+  const double xd = (double)y;
+  // reduce_fast (|y| < 120)
+  const double tf = __dmul_rn(xd, hpi_inv);
+  const int nf = (__double2int_rz(tf) + 0x800000) >> 24;
+  const double xf = __fma_rn(-(double)nf, hpi, xd);
+  // reduce_large
+  const uint32_t *arr = &k_inv_pio4[(bits >> 26) & 15];
+  const int shift = (bits >> 23) & 7;
+  const uint32_t xi = ((bits & 0xffffffu) | 0x800000u) << shift;
+  uint64_t res0 = (uint32_t)(xi * arr[0]);
+  const uint64_t res1 = (uint64_t)xi * arr[4];
+  const uint64_t res2 = (uint64_t)xi * arr[8];
+  res0 = (res2 >> 32) | (res0 << 32);
+  res0 += res1;
+  const uint64_t nn = (res0 + (1ULL << 61)) >> 62;
+  res0 -= nn << 62;
+  const double xl = __dmul_rn((double)(int64_t)res0, 0x1.921FB54442D18p-62);
+  const bool small = top < 0x3f4, fast = top < 0x42f;
+  r.x = small ? xd : fast ? xf : xl;
+  r.n = small ? 0 : fast ? nf : (int)nn;
+  r.q = small ? 0 : fast ? nf : (int)nn + (int)(bits >> 31);
+  return (top < 0x398) ? 1 : (top >= 0x7f8) ? 2 : 0;
+}
+
+__device__ __forceinline__ void sincosf_glibc_bf(float y, float &sinv, float &cosv) {
+  TrigRed r;
+  const int special = trig_reduce_bf(y, r);
+  const double x2 = __dmul_rn(r.x, r.x);
+  const float fs = trig_sin_poly(r.x, x2, r.q);
+  const float fc = trig_cos_poly(x2, r.q);
+  float s = (r.n & 1) ? fc : fs;
+  float c = (r.n & 1) ? fs : fc;
+  if (special == 1) { s = y; c = 1.0f; }
+  if (special == 2) { s = c = xsub(y, y); }
+  sinv = s;
+  cosv = c;
+}
+
+__device__ __forceinline__ float cosf_glibc_bf(float y) {
+  float s, c;
+  sincosf_glibc_bf(y, s, c);
+  return c;
+}
+
 }  // namespace sdr

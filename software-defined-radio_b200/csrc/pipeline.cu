@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -187,20 +188,19 @@ static int pick_segments(int n_out, int tile_out, int batch, int *outs_per_seg) 
   return (n_tiles + tiles_per_seg - 1) / tiles_per_seg;
 }
 
-template <int T>
-static TapArray<T> make_taps(const std::vector<float> &h) {
-  TapArray<T> t;
-  std::memset(&t, 0, sizeof t);
-  std::memcpy(t.h, h.data(), sizeof(float) * T);
+template <int N>
+static TapArray<N> make_taps(const std::vector<float> &h) {
+  TapArray<N> t;
+  std::memset(&t, 0, sizeof t);  // zero padding: see fir_groups
+  std::memcpy(t.h, h.data(), sizeof(float) * std::min<size_t>(h.size(), N));
   return t;
 }
 
 // ---- K1 dispatch -------------------------------------------------------------
-template <int T, int D, int R>
+template <int T, int D, int R, int NT, bool MERGE, int ALGO = 0>
 static int launch_rf(sdr_pipeline *p, RfArgs a, cudaStream_t s) {
-  constexpr int NT = 128;
-  using Cfg = RfCfg<T, D, R, NT>;
-  auto kern = k_rf_demod<T, D, R, NT>;
+  using Cfg = RfCfg<T, D, R, NT, ALGO>;
+  auto kern = k_rf_demod<T, D, R, NT, MERGE, ALGO>;
   static std::once_flag once[16];
   int dev = p->cfg.device;
   std::call_once(once[dev & 15], [&] {
@@ -209,8 +209,18 @@ static int launch_rf(sdr_pipeline *p, RfArgs a, cudaStream_t s) {
   int segs = pick_segments(a.n_if, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
   prof_begin(p, "k_rf_demod", s);
-  kern<<<grid, NT, Cfg::SMEM, s>>>(a, make_taps<T>(p->h_rf));
+  kern<<<grid, NT, Cfg::SMEM, s>>>(a, make_taps<Cfg::NTAPS>(p->h_rf));
   return check_launch(p, "k_rf_demod");
+}
+
+// Tuning knob for experiments (profiles/): SDR_RF_VARIANT selects the tile shape of the
+// 151-tap, decimate-by-10 front end.  Every variant produces identical bits.
+static int rf_variant() {
+  static const int v = [] {
+    const char *e = std::getenv("SDR_RF_VARIANT");
+    return e ? std::atoi(e) : -1;
+  }();
+  return v;
 }
 
 static bool rf_fast_available(int T, int D) {
@@ -220,12 +230,28 @@ static bool rf_fast_available(int T, int D) {
 static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
   const int T = p->cfg.rf_taps, D = p->m.rf_decim;
   if (p->rf_fast) {
-    if (T == 151 && D == 10) return launch_rf<151, 10, 6>(p, a, s);
-    if (T == 151 && D == 5) return launch_rf<151, 5, 12>(p, a, s);
-    if (T == 151 && D == 3) return launch_rf<151, 3, 12>(p, a, s);
-    if (T == 13 && D == 10) return launch_rf<13, 10, 6>(p, a, s);
-    if (T == 13 && D == 5) return launch_rf<13, 5, 12>(p, a, s);
-    if (T == 13 && D == 3) return launch_rf<13, 3, 12>(p, a, s);
+    if (T == 151 && D == 10) {
+      switch (rf_variant()) {
+        case 0: return launch_rf<151, 10, 6, 128, false>(p, a, s);
+        case 1: return launch_rf<151, 10, 6, 128, true>(p, a, s);
+        case 2: return launch_rf<151, 10, 6, 64, true>(p, a, s);
+        case 3: return launch_rf<151, 10, 4, 128, true>(p, a, s);
+        case 4: return launch_rf<151, 10, 4, 64, true>(p, a, s);
+        case 5: return launch_rf<151, 10, 2, 128, true>(p, a, s);
+        case 10: return launch_rf<151, 10, 4, 128, true, 1>(p, a, s);
+        case 11: return launch_rf<151, 10, 4, 64, true, 1>(p, a, s);
+        case 12: return launch_rf<151, 10, 8, 64, true, 1>(p, a, s);
+        case 13: return launch_rf<151, 10, 8, 128, true, 1>(p, a, s);
+        case 14: return launch_rf<151, 10, 4, 128, false, 1>(p, a, s);
+        case 15: return launch_rf<151, 10, 4, 256, true, 1>(p, a, s);
+        default: return launch_rf<151, 10, 2, 128, true>(p, a, s);
+      }
+    }
+    if (T == 151 && D == 5) return launch_rf<151, 5, 4, 128, true>(p, a, s);
+    if (T == 151 && D == 3) return launch_rf<151, 3, 4, 128, true>(p, a, s);
+    if (T == 13 && D == 10) return launch_rf<13, 10, 6, 128, false>(p, a, s);
+    if (T == 13 && D == 5) return launch_rf<13, 5, 12, 128, false>(p, a, s);
+    if (T == 13 && D == 3) return launch_rf<13, 3, 12, 128, false>(p, a, s);
   }
   RfGenericArgs g;
   g.a = a;
@@ -257,7 +283,7 @@ static int launch_audio(sdr_pipeline *p, AudioArgs a, cudaStream_t s) {
   int segs = pick_segments(a.n_out, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
   prof_begin(p, "k_audio_fir", s);
-  kern<<<grid, NT, SMEM, s>>>(a, make_taps<T>(p->h_audio));
+  kern<<<grid, NT, SMEM, s>>>(a, make_taps<taps_window(T)>(p->h_audio));
   return check_launch(p, "k_audio_fir");
 }
 
@@ -266,10 +292,10 @@ static bool audio_fast_available(int T, int D) { return (T == 101 || T == 13) &&
 template <bool STEREO>
 static int run_audio_fir_fast(sdr_pipeline *p, const AudioArgs &a, cudaStream_t s) {
   const int T = p->TA, D = p->m.audio_decim;
-  if (T == 101 && D == 5) return launch_audio<101, 5, 12, STEREO>(p, a, s);
-  if (T == 101 && D == 6) return launch_audio<101, 6, 6, STEREO>(p, a, s);
-  if (T == 13 && D == 5) return launch_audio<13, 5, 12, STEREO>(p, a, s);
-  if (T == 13 && D == 6) return launch_audio<13, 6, 6, STEREO>(p, a, s);
+  if (T == 101 && D == 5) return launch_audio<101, 5, 4, STEREO>(p, a, s);
+  if (T == 101 && D == 6) return launch_audio<101, 6, 2, STEREO>(p, a, s);
+  if (T == 13 && D == 5) return launch_audio<13, 5, 4, STEREO>(p, a, s);
+  if (T == 13 && D == 6) return launch_audio<13, 6, 2, STEREO>(p, a, s);
   return fail(SDR_ERR_INVALID, "no specialised audio kernel");
 }
 
@@ -280,7 +306,8 @@ static int launch_bpf(sdr_pipeline *p, BpfArgs a, cudaStream_t s) {
   int segs = pick_segments(a.n_if, NT * R, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
   prof_begin(p, "k_bpf_dual", s);
-  k_bpf_dual<T, R, NT><<<grid, NT, 0, s>>>(a, make_taps<T>(p->h_stereo), make_taps<T>(p->h_pilot));
+  k_bpf_dual<T, R, NT><<<grid, NT, 0, s>>>(a, make_taps<taps_groups(T, 1, R)>(p->h_stereo),
+                                           make_taps<taps_groups(T, 1, R)>(p->h_pilot));
   return check_launch(p, "k_bpf_dual");
 }
 
@@ -695,11 +722,31 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   aa.n_out = (int)n_audio;
   if (p->resample) {
     ResampleArgs g{aa, p->d_h_poly.p, p->m.audio_upsamp, p->m.audio_decim, p->TA};
-    dim3 grid(((int)n_audio + 127) / 128, B);
-    prof_begin(p, "k_audio_resample", s);
-    if (p->stereo) k_audio_resample<true><<<grid, 128, 0, s>>>(g);
-    else k_audio_resample<false><<<grid, 128, 0, s>>>(g);
-    if ((rc = check_launch(p, "k_audio_resample"))) return rc;
+    static const bool use_v1 = std::getenv("SDR_RESAMPLE_V1") != nullptr;
+    if (use_v1) {
+      dim3 grid(((int)n_audio + 127) / 128, B);
+      prof_begin(p, "k_audio_resample", s);
+      if (p->stereo) k_audio_resample<true><<<grid, 128, 0, s>>>(g);
+      else k_audio_resample<false><<<grid, 128, 0, s>>>(g);
+      if ((rc = check_launch(p, "k_audio_resample"))) return rc;
+    } else {
+      // rows of the transposed tile: inputs spanned by RS_J outputs plus the filter history
+      const int rows_cap = (int)(((long long)RS_J * p->m.audio_decim) / p->m.audio_upsamp) + p->TA + 2;
+      const int TA4 = (p->TA + 3) & ~3;
+      const size_t smem = ((size_t)RS_J * TA4 + (size_t)rows_cap * RS_PITCH * (p->stereo ? 2 : 1)) * sizeof(float) +
+                          (size_t)32 * RS_J * (p->stereo ? 2 : 1) * sizeof(int16_t);
+      dim3 grid(((int)n_audio + RS_J - 1) / RS_J, (B + 31) / 32);
+      static std::once_flag once[16];
+      std::call_once(once[p->cfg.device & 15], [&] {
+        cudaFuncSetAttribute(k_audio_resample_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_audio_resample_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      });
+      if (smem > 200 * 1024) return fail(SDR_ERR_INVALID, "resampler tile does not fit in shared memory");
+      prof_begin(p, "k_audio_resample_v2", s);
+      if (p->stereo) k_audio_resample_v2<true><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
+      else k_audio_resample_v2<false><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
+      if ((rc = check_launch(p, "k_audio_resample_v2"))) return rc;
+    }
   } else if (p->audio_fast) {
     rc = p->stereo ? run_audio_fir_fast<true>(p, aa, s) : run_audio_fir_fast<false>(p, aa, s);
     if (rc) return rc;
