@@ -160,7 +160,9 @@ def workload_config(args):
                         f"{' / stereo 151' if args.audio_channels == 2 else ''}",
             "mode": args.mode, "audio_channels": args.audio_channels, "batch_per_gpu": args.batch,
             "blocks_per_capture": args.blocks, "l2_policy": "input batch larger than L2 (no flush needed)",
-            "variant": "exact"}
+            "variant": ("fast (tensor-core RF front end; PCM within +-1 LSB of the reference)"
+                        if args.variant == "fast" and args.audio_channels == 1 and args.mode in (0, 2)
+                        else "exact (bit-identical to the reference)")}
 
 
 BLOCK_BYTES = {0: 102400, 1: 61440, 2: 112000, 3: 134400}
@@ -194,15 +196,26 @@ def make_device_batch(torch, mode, batch, blocks, kind, device):
     return torch.from_numpy(make_host_batch(mode, batch, blocks, kind)).to(device)
 
 
-def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, world, profile=True):
+def pick_variant(sdr, args, mode, audio_channels):
+    """FAST exists for mono with rf_decim 10 (modes 0, 2); everything else runs the exact path."""
+    if args.variant == "fast" and audio_channels == 1 and mode in (0, 2):
+        return sdr.VARIANT_FAST, "fast"
+    return sdr.VARIANT_EXACT, "exact"
+
+
+def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, world, profile=True,
+                force_exact=False):
     """Device-resident timing of one configuration.  Returns dict with ms/step (max over ranks),
     per-kernel times and launches."""
     dev = torch.device("cuda", torch.cuda.current_device())
     kind = "stereo"
     d_iq = make_device_batch(torch, mode, args.batch, args.blocks, kind, dev)
     nbytes = d_iq.shape[1]
+    variant, vname = pick_variant(sdr, args, mode, audio_channels)
+    if force_exact:
+        variant, vname = sdr.VARIANT_EXACT, "exact"
     p = sdr.Pipeline(mode=mode, channels=audio_channels, batch=args.batch, device=dev.index,
-                     max_bytes_per_channel=nbytes, **TAPS)
+                     max_bytes_per_channel=nbytes, variant=variant, **TAPS)
     n_pcm = p.pcm_count(nbytes)
     d_pcm = torch.zeros((args.batch, n_pcm), dtype=torch.int16, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -240,7 +253,7 @@ def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, wor
     del d_iq, d_pcm
     torch.cuda.empty_cache()
     return {"ms_per_step": ms / steps, "samples_per_step": samples_per_step, "launches": launches,
-            "kernels": ktimes, "nbytes": nbytes, "n_pcm": n_pcm, "checksum": checksum}
+            "kernels": ktimes, "nbytes": nbytes, "n_pcm": n_pcm, "checksum": checksum, "variant": vname}
 
 
 def time_e2e(torch, sdr, args, steps, dist, world):
@@ -253,7 +266,8 @@ def time_e2e(torch, sdr, args, steps, dist, world):
     h_iq = torch.empty((args.batch, nbytes), dtype=torch.uint8).pin_memory()
     make_host_batch(args.mode, args.batch, blocks, "stereo", out=h_iq.numpy())
     p = sdr.Pipeline(mode=args.mode, channels=args.audio_channels, batch=args.batch, device=dev_index,
-                     max_bytes_per_channel=nbytes, **TAPS)
+                     max_bytes_per_channel=nbytes, variant=pick_variant(sdr, args, args.mode, args.audio_channels)[0],
+                     **TAPS)
     n_pcm = p.pcm_count(nbytes)
     h_pcm = torch.empty((args.batch, n_pcm), dtype=torch.int16).pin_memory()
 
@@ -311,11 +325,14 @@ def run_ours(args):
 
     others = {}
     if args.others and world == 1:
-        for name, (m, ch) in {"mono_mode0": (0, 1), "stereo_mode0": (0, 2), "stereo_mode2": (2, 2)}.items():
-            r = time_config(torch, sdr, args, m, ch, max(2, args.steps // 4), 3, dist, world, profile=True)
+        for name, (m, ch, ex) in {"mono_mode0": (0, 1, False), "mono_mode2_exact": (2, 1, True),
+                                  "mono_mode0_exact": (0, 1, True), "stereo_mode0": (0, 2, False),
+                                  "stereo_mode2": (2, 2, False)}.items():
+            r = time_config(torch, sdr, args, m, ch, max(2, args.steps // 4), 3, dist, world, profile=True,
+                            force_exact=ex)
             msps = r["samples_per_step"] / (r["ms_per_step"] * 1e-3) / 1e6
             peak, _ = measured_peak()
-            others[name] = {"value": msps, "unit": UNIT, "ms_per_step": r["ms_per_step"],
+            others[name] = {"value": msps, "unit": UNIT, "variant": r["variant"], "ms_per_step": r["ms_per_step"],
                             "hbm_frac": msps * 1e6 * algorithmic_bytes_per_sample(m, ch) / 1e9 / peak,
                             "kernel_ms_per_step": {k: v[0] / max(1, v[1]) * (v[1] / max(2, args.steps // 4))
                                                    for k, v in r["kernels"].items()}}
@@ -372,6 +389,8 @@ def main():
     ap.add_argument("--e2e-blocks", type=int, default=8)
     ap.add_argument("--others", action="store_true", help="also time mono mode 0 / stereo configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="fast", choices=["fast", "exact"],
+                    help="fast: tensor-core RF front end (mono, +-1 LSB PCM); exact: bit-identical CUDA-core path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

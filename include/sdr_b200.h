@@ -43,6 +43,12 @@ extern "C" {
 
 /* Arithmetic variants of the batched pipeline. */
 #define SDR_VARIANT_EXACT 0 /* CUDA-core path, bit-identical to the reference */
+/* Tensor-core RF front end (tcgen05 kind::i8 over the raw byte stream), mono and
+ * rf_decim == 10 (modes 0 and 2) only.  I/Q are the exactly rounded fixed-point FIR
+ * outputs (tap quantisation 2^-34) instead of the reference's sequential float sums:
+ * float intermediates agree to >= 100 dB SNR and PCM to +-1 LSB, not bit for bit.
+ * Stereo is refused: the PLL amplifies 1-ulp differences beyond the parity bound. */
+#define SDR_VARIANT_FAST 1
 
 /* Intermediate signals that sdr_pipeline_tap can return (same numbering as the
  * oracle, oracle/fm_oracle.h).  Names follow src/project.cpp's variables. */

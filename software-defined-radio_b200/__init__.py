@@ -22,6 +22,7 @@ TAP_NAMES = ["i_filt", "q_filt", "demod", "allpass", "stereo_filt", "carrier_fil
              "mixer", "audio_filt", "stereo_final"]
 
 VARIANT_EXACT = 0
+VARIANT_FAST = 1
 
 
 class SdrError(RuntimeError):

@@ -18,6 +18,7 @@
 #include "../../include/sdr_b200.h"
 #include "design.h"
 #include "kernels.cuh"
+#include "rf_tc.cuh"
 
 namespace sdr {
 
@@ -109,6 +110,11 @@ struct sdr_pipeline {
   bool rf_fast, audio_fast, bpf_fast;  // specialised kernels available for these tap counts
   std::vector<float> h_rf, h_audio, h_pilot, h_stereo, h_poly;
   DevBuf<float> d_h_rf, d_h_audio, d_h_pilot, d_h_stereo, d_h_poly;
+  // tensor-core front end (SDR_VARIANT_FAST)
+  DevBuf<int8_t> tc_bmat;
+  DevBuf<int32_t> tc_hq;
+  long long tc_corr = 0;
+  float tc_scale = 0.0f;
   DevBuf<uint8_t> rf_hist;
   DevBuf<float> prev, prev_new, demod, stf, car, nco, pll_state;
   // optional intermediates (keep_taps or generic-taps path)
@@ -229,6 +235,23 @@ static bool rf_fast_available(int T, int D) {
 
 static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
   const int T = p->cfg.rf_taps, D = p->m.rf_decim;
+  if (p->cfg.variant == SDR_VARIANT_FAST) {
+    RfTcArgs g;
+    g.a = a;
+    g.bmat = p->tc_bmat.p;
+    g.hq = p->tc_hq.p;
+    g.corr = p->tc_corr;
+    g.scale = p->tc_scale;
+    g.ntaps = T;
+    const long long n_tiles = (a.n_rf + TC_TILE - 1) / TC_TILE;
+    long long want = std::max<long long>(1, std::min<long long>((148 * 16 * 4 + p->cfg.batch - 1) / p->cfg.batch, n_tiles));
+    g.tiles_per_seg = (int)((n_tiles + want - 1) / want);
+    const int segs = (int)((n_tiles + g.tiles_per_seg - 1) / g.tiles_per_seg);
+    dim3 grid(segs, p->cfg.batch);
+    prof_begin(p, "k_rf_demod_tc", s);
+    k_rf_demod_tc<<<grid, TC_ROWS, 0, s>>>(g);
+    return check_launch(p, "k_rf_demod_tc");
+  }
   if (p->rf_fast) {
     if (T == 151 && D == 10) {
       switch (rf_variant()) {
@@ -425,8 +448,15 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   if (cfg->rf_taps < 2 || cfg->rf_taps > 1024 || cfg->audio_taps < 2 || cfg->audio_taps > 1024 ||
       cfg->stereo_taps < 3 || cfg->stereo_taps > 1024)
     return fail(SDR_ERR_INVALID, "tap counts out of range");
-  if (cfg->variant != SDR_VARIANT_EXACT) return fail(SDR_ERR_INVALID, "unknown variant");
+  if (cfg->variant != SDR_VARIANT_EXACT && cfg->variant != SDR_VARIANT_FAST)
+    return fail(SDR_ERR_INVALID, "unknown variant");
   const ModeRow &m = kModes[cfg->mode];
+  if (cfg->variant == SDR_VARIANT_FAST) {
+    if (cfg->channels != 1)
+      return fail(SDR_ERR_INVALID, "SDR_VARIANT_FAST is mono only: stereo parity needs the bit-exact front end");
+    if (m.rf_decim != 10 || cfg->rf_taps > 151)
+      return fail(SDR_ERR_INVALID, "SDR_VARIANT_FAST needs rf_decim == 10 (modes 0, 2) and rf_taps <= 151");
+  }
   if ((long long)cfg->audio_taps * m.audio_upsamp > 65535)
     return fail(SDR_ERR_INVALID, "audio_taps*audio_upsamp exceeds unsigned short (filter.h:24)");
   int rc = use_device(cfg->device);
@@ -440,6 +470,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   p->TA = cfg->audio_taps;
   p->delay = p->stereo ? (cfg->stereo_taps - 1) / 2 : 0;
   p->HR = round_up(cfg->rf_taps - 1 + m.rf_decim, 8);
+  if (cfg->variant == SDR_VARIANT_FAST) p->HR = std::max(p->HR, TC_LEAD + TC_EXTRA);
   p->HA = round_up(p->TA - 1, 4);
   p->HD = round_up(std::max(p->stereo ? cfg->stereo_taps - 1 : 0, p->TA - 1 + p->delay), 4);
   sdr_mode_info mi;
@@ -485,6 +516,37 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
       for (int k = 0; k < p->TA; ++k) p->h_poly[(size_t)ph * p->TA + k] = p->h_audio[ph + (size_t)k * U];
   }
 
+  std::vector<int8_t> tc_b;
+  std::vector<int32_t> tc_h;
+  if (cfg->variant == SDR_VARIANT_FAST) {
+    // fixed-point taps: hq = round(h * 2^S), |hq| < 2^30, four balanced base-256 digits
+    float hmax = 0.0f;
+    for (float h : p->h_rf) hmax = std::max(hmax, std::fabs(h));
+    int S = 0;
+    while (S < 60 && std::ldexp((double)hmax, S + 1) < 1073741823.0) ++S;
+    tc_h.assign(152, 0);
+    long long hsum = 0;
+    for (int t = 0; t < cfg->rf_taps; ++t) {
+      tc_h[t] = (int32_t)std::llrint(std::ldexp((double)p->h_rf[t], S));  // round half to even
+      hsum += tc_h[t];
+    }
+    p->tc_corr = 128 * hsum;
+    p->tc_scale = (float)std::ldexp(1.0, -(S + 7));
+    tc_b.assign((size_t)TC_N * TC_K, 0);
+    auto put = [&](int col, int kbyte, int8_t val) {  // canonical no-swizzle K-major order
+      const size_t off = ((size_t)(kbyte / 16) * (TC_N / 8) + col / 8) * 128 + (col % 8) * 16 + (kbyte % 16);
+      tc_b[off] = val;
+    };
+    for (int t = 0; t < cfg->rf_taps; ++t) {
+      long long v = tc_h[t];
+      for (int d = 0; d < 4; ++d) {
+        const int digit = (int)(((v + 128) & 255) - 128);
+        v = (v - digit) >> 8;
+        for (int th = 0; th < 4; ++th)
+          for (int iq = 0; iq < 2; ++iq) put(th * 8 + iq * 4 + d, 2 * (2 * th + 150 - t) + iq, (int8_t)digit);
+      }
+    }
+  }
   const size_t B = (size_t)cfg->batch;
   p->demod_stride = round_up((int)(p->HD + p->cap_if + 8), 4);
   p->stf_stride = round_up((int)(p->HA + p->cap_if + 8), 4);
@@ -503,6 +565,15 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   TRY(upload(p->d_h_rf, p->h_rf));
   TRY(upload(p->d_h_audio, p->h_audio));
   if (p->resample) TRY(upload(p->d_h_poly, p->h_poly));
+  if (cfg->variant == SDR_VARIANT_FAST) {
+    TRY(p->tc_bmat.alloc(tc_b.size()));
+    TRY(p->tc_hq.alloc(tc_h.size()));
+    rc = cudaMemcpy(p->tc_bmat.p, tc_b.data(), tc_b.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(p->tc_hq.p, tc_h.data(), tc_h.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess
+             ? SDR_OK
+             : SDR_ERR_CUDA;
+    TRY(rc);
+  }
   TRY(p->rf_hist.alloc(B * 2 * p->HR));
   TRY(p->prev.alloc(B * 2));
   TRY(p->prev_new.alloc(B * 2));
