@@ -242,14 +242,17 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     g.hq = p->tc_hq.p;
     g.corr = p->tc_corr;
     g.scale = p->tc_scale;
-    g.ntaps = T;
-    const long long n_tiles = (a.n_rf + TC_TILE - 1) / TC_TILE;
-    long long want = std::max<long long>(1, std::min<long long>((148 * 16 * 4 + p->cfg.batch - 1) / p->cfg.batch, n_tiles));
-    g.tiles_per_seg = (int)((n_tiles + want - 1) / want);
-    const int segs = (int)((n_tiles + g.tiles_per_seg - 1) / g.tiles_per_seg);
+    const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
+    const int want = std::max(1, std::min((148 * 3 * 6 + p->cfg.batch - 1) / p->cfg.batch, n_tiles));
+    g.tiles_per_seg = (n_tiles + want - 1) / want;
+    const int segs = (n_tiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
+    static std::once_flag once[16];
+    std::call_once(once[p->cfg.device & 15], [&] {
+      cudaFuncSetAttribute(k_rf_demod_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    });
     dim3 grid(segs, p->cfg.batch);
     prof_begin(p, "k_rf_demod_tc", s);
-    k_rf_demod_tc<<<grid, TC_ROWS, 0, s>>>(g);
+    k_rf_demod_tc<<<grid, TC_ROWS, TC_SMEM, s>>>(g);
     return check_launch(p, "k_rf_demod_tc");
   }
   if (p->rf_fast) {
@@ -470,7 +473,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   p->TA = cfg->audio_taps;
   p->delay = p->stereo ? (cfg->stereo_taps - 1) / 2 : 0;
   p->HR = round_up(cfg->rf_taps - 1 + m.rf_decim, 8);
-  if (cfg->variant == SDR_VARIANT_FAST) p->HR = std::max(p->HR, TC_LEAD + TC_EXTRA);
+  if (cfg->variant == SDR_VARIANT_FAST) p->HR = std::max(p->HR, TC_HIST);
   p->HA = round_up(p->TA - 1, 4);
   p->HD = round_up(std::max(p->stereo ? cfg->stereo_taps - 1 : 0, p->TA - 1 + p->delay), 4);
   sdr_mode_info mi;
@@ -524,7 +527,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     for (float h : p->h_rf) hmax = std::max(hmax, std::fabs(h));
     int S = 0;
     while (S < 60 && std::ldexp((double)hmax, S + 1) < 1073741823.0) ++S;
-    tc_h.assign(152, 0);
+    tc_h.assign(TC_D * TC_Q, 0);
     long long hsum = 0;
     for (int t = 0; t < cfg->rf_taps; ++t) {
       tc_h[t] = (int32_t)std::llrint(std::ldexp((double)p->h_rf[t], S));  // round half to even
@@ -532,18 +535,19 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     }
     p->tc_corr = 128 * hsum;
     p->tc_scale = (float)std::ldexp(1.0, -(S + 7));
-    tc_b.assign((size_t)TC_N * TC_K, 0);
-    auto put = [&](int col, int kbyte, int8_t val) {  // canonical no-swizzle K-major order
-      const size_t off = ((size_t)(kbyte / 16) * (TC_N / 8) + col / 8) * 128 + (col % 8) * 16 + (kbyte % 16);
+    // B tile of phase ph: column 4*delta+d carries digit_d(h[10q+ph]) at k = delta + 15 - q
+    tc_b.assign((size_t)TC_D * TC_BP, 0);
+    auto put = [&](int ph, int col, int k, int8_t val) {  // canonical no-swizzle K-major order
+      const size_t off = (size_t)ph * TC_BP + ((size_t)(k / 16) * (TC_N / 8) + col / 8) * 128 + (col % 8) * 16 + (k % 16);
       tc_b[off] = val;
     };
     for (int t = 0; t < cfg->rf_taps; ++t) {
+      const int q = t / TC_D, ph = t % TC_D;
       long long v = tc_h[t];
       for (int d = 0; d < 4; ++d) {
         const int digit = (int)(((v + 128) & 255) - 128);
         v = (v - digit) >> 8;
-        for (int th = 0; th < 4; ++th)
-          for (int iq = 0; iq < 2; ++iq) put(th * 8 + iq * 4 + d, 2 * (2 * th + 150 - t) + iq, (int8_t)digit);
+        for (int delta = 0; delta < 16; ++delta) put(ph, 4 * delta + d, delta + 15 - q, (int8_t)digit);
       }
     }
   }

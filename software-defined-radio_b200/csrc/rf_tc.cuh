@@ -1,48 +1,53 @@
 // rf_tc.cuh -- tensor-core RF front end (SDR_VARIANT_FAST, mono, rf_decim = 10).
 //
-// Why: the bit-exact CUDA-core front end is FP32-issue bound (profiles/: FMA pipe is the
-// top pipe, DRAM < 10 %): 30.2 multiply-adds per input sample against 2 bytes, and the
-// exact form needs two instructions per multiply-add.  north_star admits a Toeplitz
+// Why: the bit-exact CUDA-core front end is FP32-issue bound (profiles/: the FMA pipe is the
+// busiest unit, DRAM below 10 %): 30.2 multiply-adds per input sample against 2 bytes, and
+// the exact form needs two instructions per multiply-add.  north_star admits a Toeplitz
 // GEMM in exactly that situation.
 //
-// How: the raw interleaved uint8 stream is consumed by tcgen05.mma kind::i8 directly,
-// with no conversion, de-interleave or im2col pass.  Row m of the A operand is the 320
-// bytes starting 16 bytes (8 complex samples) after row m-1: a shared-memory matrix
-// descriptor with leading-byte-offset 16 and stride-byte-offset 128 turns the byte
-// stream into that overlapping-row (Hankel) matrix in place.  The B operand holds the
-// filter: taps are scaled to 31-bit fixed point and split into four signed base-256
-// digits; column (theta, I|Q, digit) has digit(h[t]) at byte 2*(theta+150-t) + (I:0,Q:1).
-// Row m therefore yields, for the one output j with 10*j = c_m + theta + 150, the exact
-// integer sums  sum_t digit_d(h[t]) * u8[...]  in int32.  The epilogue recombines the
-// digits in int64, removes the 128 offset of the unsigned samples, and rounds ONCE to
-// float: the result is the exactly-rounded fixed-point FIR output (tap quantisation
-// 2^-34), which differs from the reference's sequential float sum only by the
-// reference's own accumulated rounding (~1e-7 relative; >= 100 dB SNR, tests).
-// fmDemod follows in the same kernel with the reference's float operations.
+// How (polyphase Hankel GEMM on tcgen05, kind::i8):
+//   y[j] = sum_n h[n] x[10j - n] = sum_p sum_q h[10q+p] * xp[p][j-q],   xp[p][i] = x[10i - p]
+// 1. A CUDA-core pass transposes the raw interleaved bytes into 20 byte streams (10 phases x
+//    {I,Q}) in shared memory -- no conversion, the bytes stay unsigned 8-bit.
+// 2. For each stream, row m of the MMA's A operand is the 32 bytes starting 16 bytes after
+//    row m-1: a matrix descriptor with leading-byte-offset 16 and stride-byte-offset 128
+//    turns the stream into that overlapping-row (Hankel) matrix in place, so row m sees
+//    xp[p][j0+16m-15 .. j0+16m+16] and produces the 16 outputs j0+16m+delta.
+// 3. The B operand of phase p holds the taps h[10q+p], scaled to 31-bit fixed point and
+//    split into four signed base-256 digits: column 4*delta+d has digit_d at k = delta+15-q.
+//    Ten MMAs (one per phase) accumulate sum_t digit_d(h[t]) * u8[...] exactly in int32.
+// 4. The epilogue recombines the digits in int64, removes the 128 offset of the unsigned
+//    samples and rounds ONCE to float: the exactly rounded fixed-point FIR output (tap
+//    quantisation 2^-34).  It differs from the reference's sequential float sum only by the
+//    reference's own accumulated rounding (~1e-7 relative; >= 100 dB SNR, PCM +-1 LSB).
+//    fmDemod follows in the same kernel with the reference's float operations; the
+//    one-sample state travels between rows by warp shuffle.
+// Per 128-row tile: 2048 outputs = 20480 input pairs, 20 MMAs of 128 x 64 x 32.
 #pragma once
 
 #include "kernels.cuh"
 
 namespace sdr {
 
-constexpr int TC_ROWS = 128;                // A rows per tile (TMEM lanes)
-constexpr int TC_ROW_SHIFT = 8;             // complex samples between consecutive rows
-constexpr int TC_TILE = TC_ROWS * TC_ROW_SHIFT;  // 1024 complex samples per tile
-constexpr int TC_LEAD = 152;                // window of row 0 starts this far before the tile
-constexpr int TC_EXTRA = 16;                // extra samples in front (predecessor output)
-constexpr int TC_K = 320;                   // bytes per row window (10 k-steps of 32)
-constexpr int TC_N = 32;                    // 4 thetas x (I,Q) x 4 digits
-constexpr int TC_STAGE = 2 * TC_EXTRA + 16 * (TC_ROWS - 1) + TC_K;  // 2384 bytes
-constexpr int TC_STAGE_PAD = 2432;
-constexpr int TC_MAX_OUT = 104;             // outputs owned by one tile (<= 103)
+constexpr int TC_ROWS = 128;                 // A rows per tile (= TMEM lanes = threads)
+constexpr int TC_OUT_PER_ROW = 16;
+constexpr int TC_TILE_OUT = TC_ROWS * TC_OUT_PER_ROW;  // 2048 outputs per tile
+constexpr int TC_D = 10;                     // decimation
+constexpr int TC_Q = 16;                     // taps per phase (151 = 15*10 + 1)
+constexpr int TC_FRONT = 16;                 // spare stream entries in front of row 0's window
+constexpr int TC_STREAM = TC_FRONT + 16 * (TC_ROWS - 1) + 32;  // 2080 bytes per stream
+constexpr int TC_NSTREAM = 2 * TC_D;         // 10 phases x {I,Q}
+constexpr int TC_N = 64;                     // 16 deltas x 4 digits
+constexpr int TC_BP = TC_N * 32;             // bytes of one phase's B tile
+constexpr int TC_HIST = 320;                 // raw history pairs the first tile reaches back
+constexpr size_t TC_SMEM = (size_t)TC_NSTREAM * TC_STREAM + (size_t)TC_D * TC_BP;
 
 struct RfTcArgs {
   RfArgs a;
-  const int8_t *bmat;   // [TC_N x TC_K] in canonical no-swizzle K-major core-matrix order
-  const int32_t *hq;    // fixed-point taps, 151 entries (zero padded)
+  const int8_t *bmat;   // [10 phases][64 x 32] in canonical no-swizzle K-major core-matrix order
+  const int32_t *hq;    // fixed-point taps, 160 entries (zero padded)
   long long corr;       // 128 * sum(hq): offset of the unsigned samples
   float scale;          // 2^-(S+7)
-  int ntaps;
   int tiles_per_seg;
 };
 
@@ -54,35 +59,52 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32
          ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
 }
 
+// 16 accumulator columns of this warp's 32 TMEM lanes.
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ float tc_combine(const uint32_t *d, long long corr, float scale) {
+  const long long v =
+      ((((long long)(int32_t)d[3] * 256 + (int32_t)d[2]) * 256 + (int32_t)d[1]) * 256 + (int32_t)d[0]) - corr;
+  return xmul(__ll2float_rn(v), scale);
+}
+
 static __global__ void __launch_bounds__(TC_ROWS)
 k_rf_demod_tc(const RfTcArgs g) {
   const RfArgs &a = g.a;
-  __shared__ __align__(128) uint8_t stage[TC_STAGE_PAD];
-  __shared__ __align__(128) int8_t bs[TC_N * TC_K];
-  __shared__ float iq_i[TC_MAX_OUT + 1], iq_q[TC_MAX_OUT + 1];
+  extern __shared__ __align__(128) uint8_t tc_smem[];
+  uint8_t *streams = tc_smem;                                      // [20][TC_STREAM]
+  int8_t *bs = reinterpret_cast<int8_t *>(tc_smem + TC_NSTREAM * TC_STREAM);  // [10][TC_BP]
+  __shared__ float carry_iq[2];
+  __shared__ float edge[2][4];
   __shared__ long long red[2][4];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_slot;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int b = blockIdx.y;
-  const long long n_tiles = (a.n_rf + TC_TILE - 1) / TC_TILE;
-  const long long tile_begin = (long long)blockIdx.x * g.tiles_per_seg;
-  const long long tile_end = min(tile_begin + (long long)g.tiles_per_seg, n_tiles);
+  const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
+  const int tile_begin = blockIdx.x * g.tiles_per_seg;
+  const int tile_end = min(tile_begin + g.tiles_per_seg, n_tiles);
   if (tile_begin >= tile_end) return;
   const uint8_t *row = a.iq + (size_t)b * a.iq_stride;
   const uint8_t *hrow = a.hist + (size_t)b * 2 * a.rf_hist_len;
   const bool row_aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
 
-  // ---- one-time setup: filter matrix, barrier, tensor memory ----
-  for (int i = t; i < TC_N * TC_K / 16; i += TC_ROWS)
+  // ---- one-time setup: filter tiles, barrier, tensor memory ----
+  for (int i = t; i < TC_D * TC_BP / 16; i += TC_ROWS)
     reinterpret_cast<uint4 *>(bs)[i] = __ldg(reinterpret_cast<const uint4 *>(g.bmat) + i);
   if (t == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(tc_smem_u32(&tmem_slot)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tc_smem_u32(&tmem_slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -94,70 +116,93 @@ k_rf_demod_tc(const RfTcArgs g) {
                          ((uint32_t)(TC_ROWS >> 4) << 24);
   uint32_t phase = 0;
 
-  for (long long tile = tile_begin; tile < tile_end; ++tile) {
-    const long long tile_c0 = tile * TC_TILE;
-    const long long byte0 = 2 * (tile_c0 - TC_LEAD - TC_EXTRA);  // stream byte of stage[0]
-    // ---- stage the raw bytes (no conversion): 16-byte chunks ----
-    for (int q = t; q < TC_STAGE_PAD / 16; q += TC_ROWS) {
-      const long long pos = byte0 + 16ll * q;
-      uint4 v;
-      if (row_aligned && pos >= 0 && pos + 16 <= 2 * a.n_rf) {
-        v = __ldg(reinterpret_cast<const uint4 *>(row + pos));
-      } else {
-        uint8_t tmp[16];
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const long long j0 = (long long)tile * TC_TILE_OUT;
+    // ---- 1. transpose raw bytes into the 20 phase streams ----
+    // stream entry s' holds x[10*(j0 - 31 + s') - p]; a thread builds 4 consecutive entries
+    // of all 20 streams from 40 consecutive input pairs (80 bytes, 2 bytes into an aligned
+    // 96-byte window).
+    for (int grp = t; grp < TC_STREAM / 4; grp += TC_ROWS) {
+      const long long c_lo = 10 * j0 + 40ll * grp - 319;
+      const long long w0 = 2 * c_lo - 2;  // stream byte of the window start (multiple of 16)
+      if (row_aligned && w0 >= 0 && w0 + 96 <= 2 * a.n_rf) {
+        uint32_t w[24];
+        const uint4 *src = reinterpret_cast<const uint4 *>(row + w0);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const long long p = pos + k;
-          uint8_t val = 128;  // centred zero beyond either end
-          if (p < 0) {
-            const long long h = 2ll * a.rf_hist_len + p;
-            if (h >= 0) val = hrow[h];
-          } else if (p < 2 * a.n_rf) {
-            val = row[p];
-          }
-          tmp[k] = val;
+        for (int k = 0; k < 6; ++k) {
+          const uint4 v = __ldg(src + k);
+          w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
         }
-        v = *reinterpret_cast<uint4 *>(tmp);
+#pragma unroll
+        for (int p = 0; p < TC_D; ++p) {
+#pragma unroll
+          for (int comp = 0; comp < 2; ++comp) {
+            // byte for entry ds: pair 9 + 10*ds - p of the 40, +2 bytes window offset
+            const int P0 = 2 * (9 - p) + comp + 2, P1 = P0 + 20, P2 = P0 + 40, P3 = P0 + 60;
+            const uint32_t ab = __byte_perm(w[P0 >> 2], w[P1 >> 2], (P0 & 3) | ((4 + (P1 & 3)) << 4));
+            const uint32_t cd = __byte_perm(w[P2 >> 2], w[P3 >> 2], (P2 & 3) | ((4 + (P3 & 3)) << 4));
+            *reinterpret_cast<uint32_t *>(streams + (2 * p + comp) * TC_STREAM + 4 * grp) =
+                __byte_perm(ab, cd, 0x5410);
+          }
+        }
+      } else {
+        // edges of the capture (history before it, nothing after it) and unaligned rows
+#pragma unroll 1
+        for (int sc = 0; sc < TC_NSTREAM; ++sc) {
+          const int p = sc >> 1, comp = sc & 1;
+          uint32_t word = 0;
+#pragma unroll 1
+          for (int ds = 0; ds < 4; ++ds) {
+            const long long pos = w0 + 2 * (9 + 10 * ds - p) + comp + 2;
+            uint32_t val = 128;  // centred zero beyond either end
+            if (pos < 0) {
+              const long long h = 2ll * a.rf_hist_len + pos;
+              if (h >= 0) val = hrow[h];
+            } else if (pos < 2 * a.n_rf) {
+              val = row[pos];
+            }
+            word |= val << (8 * ds);
+          }
+          *reinterpret_cast<uint32_t *>(streams + sc * TC_STREAM + 4 * grp) = word;
+        }
       }
-      reinterpret_cast<uint4 *>(stage)[q] = v;
     }
     asm volatile("fence.proxy.async.shared::cta;");  // generic-proxy writes -> tensor-core reads
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
-    // ---- 10 MMAs: D[128 x 32] = A(hankel bytes) * B(filter digits) ----
+    // ---- 2. 20 MMAs: D_I, D_Q [128 x 64] += A_p(hankel bytes) * B_p(filter digits) ----
     if (t == 0) {
-      const uint32_t a0 = tc_smem_u32(stage) + 2 * TC_EXTRA, b0 = tc_smem_u32(bs);
+      const uint32_t s0 = tc_smem_u32(streams) + TC_FRONT, b0 = tc_smem_u32(bs);
 #pragma unroll
-      for (int ks = 0; ks < TC_K / 32; ++ks) {
-        const uint64_t da = tc_desc(a0 + 32 * ks, 16, 128);
-        const uint64_t db = tc_desc(b0 + ks * 2 * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
-        const uint32_t acc = ks > 0;
-        asm volatile(
-            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
-            "l"(da), "l"(db), "r"(idesc), "r"(acc));
+      for (int comp = 0; comp < 2; ++comp) {
+#pragma unroll
+        for (int p = 0; p < TC_D; ++p) {
+          const uint64_t da = tc_desc(s0 + (2 * p + comp) * TC_STREAM, 16, 128);
+          const uint64_t db = tc_desc(b0 + p * TC_BP, (TC_N / 8) * 128, 128);
+          const uint32_t acc = p > 0;
+          asm volatile(
+              "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+              "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + comp * TC_N),
+              "l"(da), "l"(db), "r"(idesc), "r"(acc));
+        }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
           tc_smem_u32(&mbar)));
     }
-    // ---- outputs owned by this tile; predecessor of the first one ----
-    const long long base10 = tile_c0 - 2;                       // 10*j lies in [base10, base10+1024)
-    const long long j_lo = (base10 + 9 >= 0) ? (base10 + 9) / 10 : 0;
+    // ---- predecessor of the segment's first output ----
     if (tile == tile_begin) {
-      if (j_lo == 0) {
-        if (t < 2) (t == 0 ? iq_i : iq_q)[0] = a.prev_in[2 * b + t];
+      if (j0 == 0) {
+        if (t < 2) carry_iq[t] = a.prev_in[2 * b + t];
       } else {
-        // integer evaluation of output j_lo-1 on the CUDA cores (same fixed-point taps,
-        // integer sums are order independent): newest sample 10*(j_lo-1)
-        const long long newest = 10 * (j_lo - 1);
+        // output j0-1 evaluated in integers on the CUDA cores (same fixed-point taps; integer
+        // sums are order independent): tap 10q+p meets xp[p][j0-1-q] = stream entry 30-q
         long long si = 0, sq = 0;
-        for (int n = t; n < g.ntaps; n += TC_ROWS) {
-          const long long c = newest - n;
-          const int off = (int)(2 * c - byte0);
+        for (int n = t; n < TC_D * TC_Q; n += TC_ROWS) {
+          const int q = n / TC_D, p = n - q * TC_D;
           const long long h = g.hq[n];
-          si += h * ((int)stage[off] - 128);
-          sq += h * ((int)stage[off + 1] - 128);
+          si += h * ((int)streams[(2 * p) * TC_STREAM + 30 - q] - 128);
+          sq += h * ((int)streams[(2 * p + 1) * TC_STREAM + 30 - q] - 128);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -170,7 +215,7 @@ k_rf_demod_tc(const RfTcArgs g) {
         }
       }
     }
-    // ---- wait for the accumulator ----
+    // ---- 3. wait for the accumulators ----
     {
       uint32_t done = 0;
       while (!done) {
@@ -182,81 +227,90 @@ k_rf_demod_tc(const RfTcArgs g) {
       phase ^= 1;
     }
     asm volatile("tcgen05.fence::after_thread_sync;");
-    uint32_t v[32];
-    {
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
-          "%28,%29,%30,%31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
-            "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-            "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;");
-    }
-    // row t: window starts at c = tile_c0 - 152 + 8t; it owns the output with
-    // 10*j = c + 150 + theta, theta in {0,2,4,6} (rows with theta == 8 own none).
-    // All per-thread index math is 32-bit, relative to 10*j_lo.
-    const int u2 = (int)(base10 - 10 * j_lo) + 8 * t + 10;   // (c + 150) - 10*j_lo + 10  >= 1
-    const int theta = (10 - u2 % 10) % 10;
-    const int jrel = (u2 + theta) / 10 - 1;
-    const long long j = j_lo + jrel;
-    const bool owns = theta < 8 && j < a.n_if;
-    const int th = theta >> 1;
-    long long vi = 0, vq = 0;
-    {
-      int32_t di[4], dq[4];
+    // ---- 4. epilogue: row t owns outputs j0 + 16t + delta ----
+    float fi[TC_OUT_PER_ROW], fq[TC_OUT_PER_ROW];
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        di[d] = (th == 0) ? v[d] : (th == 1) ? v[8 + d] : (th == 2) ? v[16 + d] : v[24 + d];
-        dq[d] = (th == 0) ? v[4 + d] : (th == 1) ? v[12 + d] : (th == 2) ? v[20 + d] : v[28 + d];
+    for (int c = 0; c < 4; ++c) {
+      uint32_t vi[16], vq[16];
+      tc_ld16(trow + 16 * c, vi);
+      tc_ld16(trow + TC_N + 16 * c, vq);
+      asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        fi[4 * c + k] = tc_combine(&vi[4 * k], g.corr, g.scale);
+        fq[4 * c + k] = tc_combine(&vq[4 * k], g.corr, g.scale);
       }
-      vi = (((long long)di[3] * 256 + di[2]) * 256 + di[1]) * 256 + di[0] - g.corr;
-      vq = (((long long)dq[3] * 256 + dq[2]) * 256 + dq[1]) * 256 + dq[0] - g.corr;
     }
-    const float fi = xmul(__ll2float_rn(vi), g.scale);
-    const float fq = xmul(__ll2float_rn(vq), g.scale);
-    const int slot = jrel + 1;
-    if (owns) {
-      iq_i[slot] = fi;
-      iq_q[slot] = fq;
+    // one-sample state: previous row's last output, by shuffle inside the warp and through
+    // shared memory across warps / tiles
+    float pi = __shfl_up_sync(0xffffffffu, fi[15], 1), pq = __shfl_up_sync(0xffffffffu, fq[15], 1);
+    if (lane == 31) {
+      edge[0][warp] = fi[15];
+      edge[1][warp] = fq[15];
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
-    if (owns) {
-      float pi = iq_i[slot - 1], pq = iq_q[slot - 1];
-      if (slot == 1 && tile == tile_begin && j_lo > 0) {
-        // predecessor of the segment's first output: the integer sums reduced above
+    if (lane == 0) {
+      if (warp > 0) {
+        pi = edge[0][warp - 1];
+        pq = edge[1][warp - 1];
+      } else if (tile == tile_begin && j0 != 0) {
         pi = xmul(__ll2float_rn(red[0][0] + red[0][1] + red[0][2] + red[0][3]), g.scale);
         pq = xmul(__ll2float_rn(red[1][0] + red[1][1] + red[1][2] + red[1][3]), g.scale);
-      }
-      const float d = fm_demod_one(fi, fq, pi, pq);
-      a.demod[(size_t)b * a.demod_stride + a.demod_off + j] = d;
-      if (a.i_filt) {
-        a.i_filt[(size_t)b * a.tap_stride + j] = fi;
-        a.q_filt[(size_t)b * a.tap_stride + j] = fq;
-      }
-      if (j == a.n_if - 1) {
-        a.prev_out[2 * b] = fi;
-        a.prev_out[2 * b + 1] = fq;
+      } else {
+        pi = carry_iq[0];
+        pq = carry_iq[1];
       }
     }
-    // carry the tile's last output to slot 0 for the next tile
-    const long long j_hi = min((long long)a.n_if, (base10 + 1024 + 9) / 10);  // exclusive
-    __syncthreads();
-    if (t < 2 && j_hi > j_lo) {
-      float *arr = (t == 0 ? iq_i : iq_q);
-      arr[0] = arr[(int)(j_hi - j_lo)];
+    const long long jrow = j0 + 16 * t;
+    float dm[TC_OUT_PER_ROW];
+#pragma unroll
+    for (int k = 0; k < TC_OUT_PER_ROW; ++k) {
+      dm[k] = fm_demod_one(fi[k], fq[k], pi, pq);
+      pi = fi[k];
+      pq = fq[k];
     }
-    // (the next iteration's first __syncthreads orders this write before any read)
+    float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
+    if (jrow + TC_OUT_PER_ROW <= a.n_if && ((a.demod_stride | a.demod_off) & 3) == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4 *>(drow + jrow + 4 * k) = make_float4(dm[4 * k], dm[4 * k + 1], dm[4 * k + 2], dm[4 * k + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < TC_OUT_PER_ROW; ++k)
+        if (jrow + k < a.n_if) drow[jrow + k] = dm[k];
+    }
+    if (a.i_filt) {
+#pragma unroll
+      for (int k = 0; k < TC_OUT_PER_ROW; ++k)
+        if (jrow + k < a.n_if) {
+          a.i_filt[(size_t)b * a.tap_stride + jrow + k] = fi[k];
+          a.q_filt[(size_t)b * a.tap_stride + jrow + k] = fq[k];
+        }
+    }
+    {
+      const long long last = (long long)a.n_if - 1 - jrow;  // position of the call's last output
+      if (last >= 0 && last < TC_OUT_PER_ROW) {
+#pragma unroll
+        for (int k = 0; k < TC_OUT_PER_ROW; ++k)
+          if (k == last) {
+            a.prev_out[2 * b] = fi[k];
+            a.prev_out[2 * b + 1] = fq[k];
+          }
+      }
+    }
+    __syncthreads();  // edge/carry reads done
+    if (t == TC_ROWS - 1) {
+      carry_iq[0] = fi[15];
+      carry_iq[1] = fq[15];
+    }
+    // (the next tile's first __syncthreads orders this write before any read)
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
 }
 
 }  // namespace sdr
