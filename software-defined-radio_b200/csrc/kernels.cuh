@@ -652,15 +652,24 @@ k_audio_resample_v2(const ResampleArgs g, int batch, int rows_cap) {
   const int j0 = blockIdx.x * RS_J;
   const int jn = min(RS_J, a.n_out - j0);
   const int c0 = blockIdx.y * 32;
-  const long long m0 = (long long)j0 * g.D;
-  const long long i_lo = m0 / g.U - (g.TA - 1);                    // oldest input of the tile
-  const long long i_hi = ((long long)(j0 + jn - 1) * g.D) / g.U;   // newest input of the tile
-  const int rows = (int)(i_hi - i_lo + 1);
+  // All positions fit in 32 bits: the pipeline caps n_if * U below 2^31.
+  const unsigned U = (unsigned)g.U, D = (unsigned)g.D;
+  const unsigned m0 = (unsigned)j0 * D;
+  const int i_lo = (int)(m0 / U) - (g.TA - 1);                          // oldest input of the tile
+  const int i_hi = (int)(((unsigned)(j0 + jn - 1) * D) / U);            // newest input of the tile
+  const int rows = i_hi - i_lo + 1;
+  __shared__ int s_phase[RS_J], s_top[RS_J];
+  if (threadIdx.x < RS_J) {
+    const unsigned m = (unsigned)(j0 + threadIdx.x) * D;
+    const unsigned q = m / U;
+    s_phase[threadIdx.x] = (int)(m - q * U);
+    s_top[threadIdx.x] = (int)q - i_lo;   // row of the newest input of this output
+  }
+  __syncthreads();
   // ---- taps of the jn phases, zero padded to TA4 ----
-  for (int idx = threadIdx.x; idx < jn * TA4; idx += blockDim.x) {
-    const int jj = idx / TA4, k = idx - jj * TA4;
-    const int ph = (int)(((long long)(j0 + jj) * g.D) % g.U);
-    hs[idx] = (k < g.TA) ? __ldg(g.hp + (size_t)ph * g.TA + k) : 0.0f;
+  for (int jj = warp; jj < jn; jj += RS_NW) {
+    const float *src = g.hp + (size_t)s_phase[jj] * g.TA;
+    for (int k = lane; k < TA4; k += 32) hs[jj * TA4 + k] = (k < g.TA) ? __ldg(src + k) : 0.0f;
   }
   // ---- transposed input tiles: each warp streams whole rows of its captures ----
   for (int c = warp; c < 32; c += RS_NW) {
@@ -683,8 +692,7 @@ k_audio_resample_v2(const ResampleArgs g, int batch, int rows_cap) {
   __syncthreads();
   const float fu = (float)g.U;
   for (int jj = warp; jj < jn; jj += RS_NW) {
-    const long long m = (long long)(j0 + jj) * g.D;
-    const int top = (int)(m / g.U - i_lo);   // row of the newest input of this output
+    const int top = s_top[jj];
     const float *h = hs + jj * TA4;
     const float *x = xs + top * RS_PITCH + lane;
     const float *x2 = xs2 + top * RS_PITCH + lane;
