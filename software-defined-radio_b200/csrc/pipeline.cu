@@ -249,10 +249,13 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     static std::once_flag once[16];
     std::call_once(once[p->cfg.device & 15], [&] {
       cudaFuncSetAttribute(k_rf_demod_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+      cudaFuncSetAttribute(k_rf_demod_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC3_SMEM);
     });
+    static const bool single_role = std::getenv("SDR_TC_SINGLE_ROLE") != nullptr;
     dim3 grid(segs, p->cfg.batch);
     prof_begin(p, "k_rf_demod_tc", s);
-    k_rf_demod_tc<<<grid, TC_ROWS, TC_SMEM, s>>>(g);
+    if (single_role) k_rf_demod_tc<<<grid, TC_ROWS, TC_SMEM, s>>>(g);
+    else k_rf_demod_tc3<<<grid, 2 * TC_ROWS, TC3_SMEM, s>>>(g);
     return check_launch(p, "k_rf_demod_tc");
   }
   if (p->rf_fast) {

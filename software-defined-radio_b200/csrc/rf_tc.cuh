@@ -313,4 +313,286 @@ k_rf_demod_tc(const RfTcArgs g) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
 }
 
+
+// ---------------------------------------------------------------------------
+// Throughput form of the same computation (the default).  The single-role kernel above is
+// latency bound (profiles/r1b: long-scoreboard 44 %, 3 CTAs per SM, every tile waits for its
+// global loads, then its MMAs, then runs its epilogue).  A first warp-specialised version
+// (4 producer + 4 consumer warps, profiles/r1c) was slower: the producers stayed bound by
+// global-load latency and the consumers starved.  This version keeps every warp busy with
+// both kinds of work instead:
+//   * the raw bytes of the NEXT tile are fetched with fully coalesced 16-byte cp.async copies
+//     into a staging buffer while the current tile is processed (the transposer's own access
+//     pattern -- 96-byte windows 80 bytes apart -- costs ~20 L1 lines per warp load when done
+//     straight from global memory; from shared memory it is conflict free);
+//   * 8 warps; all of them transpose (LDS.128 x6 + PRMT + STS per 40 input pairs);
+//   * accumulators are double buffered: the MMAs of tile i run while the CTA does the
+//     epilogue of tile i-1;
+//   * a TMEM lane quarter is readable by warps w and w+4, so the two warps split a row's 16
+//     outputs (delta 0-7 / 8-15); the one-sample demod state crosses via shared memory.
+// ---------------------------------------------------------------------------
+constexpr int TC_RAW_CHUNKS = (80 * (TC_STREAM / 4 - 1) + 96) / 16;   // 2601 16-byte chunks per tile
+constexpr int TC_RAW = ((TC_RAW_CHUNKS * 16 + 127) / 128) * 128;     // raw staging bytes (padded)
+constexpr size_t TC3_SMEM = (size_t)TC_RAW + (size_t)TC_NSTREAM * TC_STREAM + (size_t)TC_D * TC_BP;
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(tc_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+      tc_smem_u32(bar)) : "memory");
+}
+
+// Transposes 40 input pairs (aligned 96-byte window, 2 bytes in) into 4 entries of all 20 streams.
+__device__ __forceinline__ void tc_transpose_group(const uint32_t (&w)[24], uint8_t *streams, int grp) {
+#pragma unroll
+  for (int p = 0; p < TC_D; ++p) {
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp) {
+      const int P0 = 2 * (9 - p) + comp + 2, P1 = P0 + 20, P2 = P0 + 40, P3 = P0 + 60;
+      const uint32_t ab = __byte_perm(w[P0 >> 2], w[P1 >> 2], (P0 & 3) | ((4 + (P1 & 3)) << 4));
+      const uint32_t cd = __byte_perm(w[P2 >> 2], w[P3 >> 2], (P2 & 3) | ((4 + (P3 & 3)) << 4));
+      *reinterpret_cast<uint32_t *>(streams + (2 * p + comp) * TC_STREAM + 4 * grp) = __byte_perm(ab, cd, 0x5410);
+    }
+  }
+}
+
+static __global__ void __launch_bounds__(2 * TC_ROWS, 2)
+k_rf_demod_tc3(const RfTcArgs g) {
+  const RfArgs &a = g.a;
+  extern __shared__ __align__(128) uint8_t tc_smem[];
+  uint8_t *raw = tc_smem;                                   // [TC_RAW] staged input bytes
+  uint8_t *streams = tc_smem + TC_RAW;                      // [20][TC_STREAM]
+  int8_t *bs = reinterpret_cast<int8_t *>(tc_smem + TC_RAW + TC_NSTREAM * TC_STREAM);
+  __shared__ float last_i[2][TC_ROWS], last_q[2][TC_ROWS];  // [half][row]: I,Q of delta 7 / 15
+  __shared__ float carry_iq[2];
+  __shared__ long long red[2][8];
+  __shared__ __align__(8) uint64_t mma_done[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rowi = (warp & 3) * 32 + lane;  // TMEM lane = A row served by this thread
+  const int half = warp >> 2;               // which 8 of the row's 16 outputs
+  const int b = blockIdx.y;
+  const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
+  const int tile_begin = blockIdx.x * g.tiles_per_seg;
+  const int tile_end = min(tile_begin + g.tiles_per_seg, n_tiles);
+  if (tile_begin >= tile_end) return;
+  const uint8_t *row = a.iq + (size_t)b * a.iq_stride;
+  const uint8_t *hrow = a.hist + (size_t)b * 2 * a.rf_hist_len;
+  const bool row_aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+
+  for (int i = tid; i < TC_D * TC_BP / 16; i += 2 * TC_ROWS)
+    reinterpret_cast<uint4 *>(bs)[i] = __ldg(reinterpret_cast<const uint4 *>(g.bmat) + i);
+  if (tid == 0) {
+    mbar_init(&mma_done[0], 1);
+    mbar_init(&mma_done[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tc_smem_u32(&tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;");  // bs written by the generic proxy
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+                         ((uint32_t)(TC_ROWS >> 4) << 24);
+  bool have_pred = false;  // predecessor of the segment's first output comes from `red`
+
+  // Epilogue of tile `tile` (accumulator set buf, completion number `use` of mma_done[buf]).
+  auto epilogue = [&](int tile, int buf, int use) {
+    const long long j0 = (long long)tile * TC_TILE_OUT;
+    mbar_wait(&mma_done[buf], use & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    float fi[8], fq[8];
+    const uint32_t trow = tmem + buf * 2 * TC_N + 32 * half + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t vi[16], vq[16];
+      tc_ld16(trow + 16 * c, vi);
+      tc_ld16(trow + TC_N + 16 * c, vq);
+      asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        fi[4 * c + k] = tc_combine(&vi[4 * k], g.corr, g.scale);
+        fq[4 * c + k] = tc_combine(&vq[4 * k], g.corr, g.scale);
+      }
+    }
+    last_i[half][rowi] = fi[7];
+    last_q[half][rowi] = fq[7];
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    float pi, pq;
+    if (half == 1) {            // delta 8 follows delta 7 of the same row
+      pi = last_i[0][rowi];
+      pq = last_q[0][rowi];
+    } else if (rowi > 0) {      // delta 0 follows delta 15 of the previous row
+      pi = last_i[1][rowi - 1];
+      pq = last_q[1][rowi - 1];
+    } else if (tile == tile_begin && have_pred) {
+      pi = xmul(__ll2float_rn(red[0][0] + red[0][1] + red[0][2] + red[0][3] + red[0][4] + red[0][5] + red[0][6] + red[0][7]), g.scale);
+      pq = xmul(__ll2float_rn(red[1][0] + red[1][1] + red[1][2] + red[1][3] + red[1][4] + red[1][5] + red[1][6] + red[1][7]), g.scale);
+    } else {
+      pi = carry_iq[0];
+      pq = carry_iq[1];
+    }
+    const long long jrow = j0 + 16 * rowi + 8 * half;
+    float dm[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      dm[k] = fm_demod_one(fi[k], fq[k], pi, pq);
+      pi = fi[k];
+      pq = fq[k];
+    }
+    float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
+    if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 3) == 0) {
+      *reinterpret_cast<float4 *>(drow + jrow) = make_float4(dm[0], dm[1], dm[2], dm[3]);
+      *reinterpret_cast<float4 *>(drow + jrow + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (jrow + k < a.n_if) drow[jrow + k] = dm[k];
+    }
+    if (a.i_filt) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (jrow + k < a.n_if) {
+          a.i_filt[(size_t)b * a.tap_stride + jrow + k] = fi[k];
+          a.q_filt[(size_t)b * a.tap_stride + jrow + k] = fq[k];
+        }
+    }
+    {
+      const long long last = (long long)a.n_if - 1 - jrow;
+      if (last >= 0 && last < 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k == last) {
+            a.prev_out[2 * b] = fi[k];
+            a.prev_out[2 * b + 1] = fq[k];
+          }
+      }
+    }
+    __syncthreads();  // last_* / carry reads done before they are rewritten
+    if (half == 1 && rowi == TC_ROWS - 1) {
+      carry_iq[0] = fi[7];
+      carry_iq[1] = fq[7];
+    }
+  };
+
+  if (tile_begin == 0 && tid < 2) carry_iq[tid] = a.prev_in[2 * b + tid];
+
+  // Stage the raw bytes of a tile: stream bytes [20*j0 - 640, +TC_RAW_CHUNKS*16), coalesced.
+  auto issue_raw = [&](int tile) {
+    const long long wbase = 20ll * tile * TC_TILE_OUT - 640;
+    for (int q = tid; q < TC_RAW_CHUNKS; q += 2 * TC_ROWS) {
+      const long long pos = wbase + 16ll * q;
+      if (row_aligned && pos >= 0 && pos + 16 <= 2 * a.n_rf) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc_smem_u32(raw + 16 * q)), "l"(row + pos)
+                     : "memory");
+      } else {  // edges of the capture (history before it, centred zeros after it), unaligned rows
+        for (int k = 0; k < 16; ++k) {
+          const long long p = pos + k;
+          uint8_t val = 128;
+          if (p < 0) {
+            const long long h = 2ll * a.rf_hist_len + p;
+            if (h >= 0) val = hrow[h];
+          } else if (p < 2 * a.n_rf) {
+            val = row[p];
+          }
+          raw[16 * q + k] = val;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_raw(tile_begin);
+
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int it = tile - tile_begin, buf = it & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");                 // my copies of this tile landed
+    if (it > 0) mbar_wait(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);      // MMAs of tile it-1 have read `streams`
+    __syncthreads();                                                     // everyone's copies are visible
+    // ---- 1. transpose raw -> 20 phase streams (each thread: 40 input pairs per group) ----
+    for (int grp = tid; grp < TC_STREAM / 4; grp += 2 * TC_ROWS) {
+      uint32_t w[24];
+      const uint4 *src = reinterpret_cast<const uint4 *>(raw + 80 * grp);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const uint4 v = src[k];
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+      }
+      tc_transpose_group(w, streams, grp);
+    }
+    asm volatile("fence.proxy.async.shared::cta;");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // ---- 2. MMAs of this tile into accumulator set buf (drained by the epilogue of tile it-2) ----
+    if (tid == 0) {
+      const uint32_t s0 = tc_smem_u32(streams) + TC_FRONT, b0 = tc_smem_u32(bs);
+      const uint32_t d0 = tmem + buf * 2 * TC_N;
+#pragma unroll
+      for (int comp = 0; comp < 2; ++comp) {
+#pragma unroll
+        for (int p = 0; p < TC_D; ++p) {
+          const uint64_t da = tc_desc(s0 + (2 * p + comp) * TC_STREAM, 16, 128);
+          const uint64_t db = tc_desc(b0 + p * TC_BP, (TC_N / 8) * 128, 128);
+          const uint32_t acc = p > 0;
+          asm volatile(
+              "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+              "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d0 + comp * TC_N),
+              "l"(da), "l"(db), "r"(idesc), "r"(acc));
+        }
+      }
+      tc_commit(&mma_done[buf]);
+    }
+    // ---- predecessor of the segment's first output, in integers (see the single-role kernel) ----
+    if (tile == tile_begin && tile != 0) {
+      long long si = 0, sq = 0;
+      for (int n = tid; n < TC_D * TC_Q; n += 2 * TC_ROWS) {
+        const int q = n / TC_D, p = n - q * TC_D;
+        const long long h = g.hq[n];
+        si += h * ((int)streams[(2 * p) * TC_STREAM + 30 - q] - 128);
+        sq += h * ((int)streams[(2 * p + 1) * TC_STREAM + 30 - q] - 128);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      }
+      if (lane == 0) {
+        red[0][warp] = si;
+        red[1][warp] = sq;
+      }
+      have_pred = true;  // visible to everyone after the epilogue's first __syncthreads
+    }
+    // ---- 3. next tile's bytes start flowing; epilogue of the previous tile meanwhile ----
+    if (tile + 1 < tile_end) issue_raw(tile + 1);   // `raw` is free: all reads precede the sync above
+    if (it > 0) epilogue(tile - 1, buf ^ 1, (it - 1) >> 1);
+  }
+  {
+    const int it = tile_end - 1 - tile_begin;
+    epilogue(tile_end - 1, it & 1, it >> 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+}
+
 }  // namespace sdr
