@@ -68,10 +68,27 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
-__device__ __forceinline__ float tc_combine(const uint32_t *d, long long corr, float scale) {
-  const long long v =
-      ((((long long)(int32_t)d[3] * 256 + (int32_t)d[2]) * 256 + (int32_t)d[1]) * 256 + (int32_t)d[0]) - corr;
-  return xmul(__ll2float_rn(v), scale);
+// Recombine the four base-256 digit sums into the fixed-point FIR output and round once.
+// v = d0 + 2^8 d1 + 2^16 d2 + 2^24 d3 - corr is an integer below 2^48: both int32 halves and
+// the two fused multiply-adds are exact in double, so the only rounding is double -> float
+// (scaling by the power of two `sc` commutes with that rounding).
+struct TcScale {
+  double sc;     // 2^-(S+7)
+  double sc16;   // 2^16 * sc
+  double c0;     // -corr * sc
+};
+__device__ __forceinline__ float tc_combine(const uint32_t *d, const TcScale &k) {
+  const int lo = (int32_t)d[0] + 256 * (int32_t)d[1];
+  const int hi = (int32_t)d[2] + 256 * (int32_t)d[3];
+  const double r = __fma_rn((double)hi, k.sc16, __fma_rn((double)lo, k.sc, k.c0));
+  return __double2float_rn(r);
+}
+// fmDemod on the fast path: same formula, approximate reciprocal (the fast variant is held to
+// 100 dB / +-1 LSB against the reference, not to bit equality; I/Q already differ by ~1e-7).
+__device__ __forceinline__ float tc_demod(float i, float q, float pi, float pq) {
+  const float den = i * i + q * q;
+  if (den == 0.0f) return 0.0f;
+  return __fdividef(i * (q - pq) - q * (i - pi), den);
 }
 
 static __global__ void __launch_bounds__(TC_ROWS)
@@ -115,6 +132,7 @@ k_rf_demod_tc(const RfTcArgs g) {
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                          ((uint32_t)(TC_ROWS >> 4) << 24);
   uint32_t phase = 0;
+  const TcScale ks{(double)g.scale, (double)g.scale * 65536.0, -(double)g.corr * (double)g.scale};
 
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const long long j0 = (long long)tile * TC_TILE_OUT;
@@ -238,8 +256,8 @@ k_rf_demod_tc(const RfTcArgs g) {
       asm volatile("tcgen05.wait::ld.sync.aligned;");
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        fi[4 * c + k] = tc_combine(&vi[4 * k], g.corr, g.scale);
-        fq[4 * c + k] = tc_combine(&vq[4 * k], g.corr, g.scale);
+        fi[4 * c + k] = tc_combine(&vi[4 * k], ks);
+        fq[4 * c + k] = tc_combine(&vq[4 * k], ks);
       }
     }
     // one-sample state: previous row's last output, by shuffle inside the warp and through
@@ -380,7 +398,7 @@ k_rf_demod_tc3(const RfTcArgs g) {
   __shared__ float last_i[2][TC_ROWS], last_q[2][TC_ROWS];  // [half][row]: I,Q of delta 7 / 15
   __shared__ float carry_iq[2];
   __shared__ long long red[2][8];
-  __shared__ __align__(8) uint64_t mma_done[2];
+  __shared__ __align__(8) uint64_t mma_done[2], raw_full;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -400,6 +418,7 @@ k_rf_demod_tc3(const RfTcArgs g) {
   if (tid == 0) {
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
+    mbar_init(&raw_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
@@ -414,6 +433,7 @@ k_rf_demod_tc3(const RfTcArgs g) {
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                          ((uint32_t)(TC_ROWS >> 4) << 24);
   bool have_pred = false;  // predecessor of the segment's first output comes from `red`
+  const TcScale ks{(double)g.scale, (double)g.scale * 65536.0, -(double)g.corr * (double)g.scale};
 
   // Epilogue of tile `tile` (accumulator set buf, completion number `use` of mma_done[buf]).
   auto epilogue = [&](int tile, int buf, int use) {
@@ -430,8 +450,8 @@ k_rf_demod_tc3(const RfTcArgs g) {
       asm volatile("tcgen05.wait::ld.sync.aligned;");
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        fi[4 * c + k] = tc_combine(&vi[4 * k], g.corr, g.scale);
-        fq[4 * c + k] = tc_combine(&vq[4 * k], g.corr, g.scale);
+        fi[4 * c + k] = tc_combine(&vi[4 * k], ks);
+        fq[4 * c + k] = tc_combine(&vq[4 * k], ks);
       }
     }
     last_i[half][rowi] = fi[7];
@@ -456,7 +476,7 @@ k_rf_demod_tc3(const RfTcArgs g) {
     float dm[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      dm[k] = fm_demod_one(fi[k], fq[k], pi, pq);
+      dm[k] = tc_demod(fi[k], fq[k], pi, pq);
       pi = fi[k];
       pq = fq[k];
     }
@@ -497,18 +517,38 @@ k_rf_demod_tc3(const RfTcArgs g) {
 
   if (tile_begin == 0 && tid < 2) carry_iq[tid] = a.prev_in[2 * b + tid];
 
-  // Stage the raw bytes of a tile: stream bytes [20*j0 - 640, +TC_RAW_CHUNKS*16), coalesced.
+  // Stage the raw bytes of a tile: stream bytes [20*j0 - 640, +TC_RAW_CHUNKS*16).  A tile that
+  // lies entirely inside the capture is one bulk asynchronous copy (TMA, completes on raw_full);
+  // tiles that touch the history in front of the capture or its end are assembled chunk by chunk.
+  auto tile_is_bulk = [&](int tile) -> bool {
+    const long long wbase = 20ll * tile * TC_TILE_OUT - 640;
+    return row_aligned && wbase >= 0 && wbase + 16ll * TC_RAW_CHUNKS <= 2 * a.n_rf;
+  };
+  uint32_t raw_phase = 0;
   auto issue_raw = [&](int tile) {
     const long long wbase = 20ll * tile * TC_TILE_OUT - 640;
+    if (tile_is_bulk(tile)) {
+      if (tid == 0) {
+        constexpr uint32_t BYTES = TC_RAW_CHUNKS * 16;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(&raw_full)), "r"(BYTES)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                tc_smem_u32(raw)),
+            "l"(row + wbase), "r"(BYTES), "r"(tc_smem_u32(&raw_full))
+            : "memory");
+      }
+      return;
+    }
     for (int q = tid; q < TC_RAW_CHUNKS; q += 2 * TC_ROWS) {
       const long long pos = wbase + 16ll * q;
       if (row_aligned && pos >= 0 && pos + 16 <= 2 * a.n_rf) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc_smem_u32(raw + 16 * q)), "l"(row + pos)
                      : "memory");
-      } else {  // edges of the capture (history before it, centred zeros after it), unaligned rows
+      } else {
         for (int k = 0; k < 16; ++k) {
           const long long p = pos + k;
-          uint8_t val = 128;
+          uint8_t val = 128;  // centred zero beyond either end
           if (p < 0) {
             const long long h = 2ll * a.rf_hist_len + p;
             if (h >= 0) val = hrow[h];
@@ -521,11 +561,19 @@ k_rf_demod_tc3(const RfTcArgs g) {
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  auto wait_raw = [&](int tile) {
+    if (tile_is_bulk(tile)) {
+      mbar_wait(&raw_full, raw_phase);
+      raw_phase ^= 1;
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+  };
   issue_raw(tile_begin);
 
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int it = tile - tile_begin, buf = it & 1;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");                 // my copies of this tile landed
+    wait_raw(tile);                                                      // this tile's bytes have landed
     if (it > 0) mbar_wait(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);      // MMAs of tile it-1 have read `streams`
     __syncthreads();                                                     // everyone's copies are visible
     // ---- 1. transpose raw -> 20 phase streams (each thread: 40 input pairs per group) ----
@@ -583,7 +631,9 @@ k_rf_demod_tc3(const RfTcArgs g) {
       have_pred = true;  // visible to everyone after the epilogue's first __syncthreads
     }
     // ---- 3. next tile's bytes start flowing; epilogue of the previous tile meanwhile ----
-    if (tile + 1 < tile_end) issue_raw(tile + 1);   // `raw` is free: all reads precede the sync above
+    // `raw` is free: every thread's reads precede the __syncthreads above (and that barrier's
+    // fence.proxy.async orders them before the bulk copy's async-proxy writes)
+    if (tile + 1 < tile_end) issue_raw(tile + 1);
     if (it > 0) epilogue(tile - 1, buf ^ 1, (it - 1) >> 1);
   }
   {
