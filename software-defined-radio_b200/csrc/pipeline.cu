@@ -820,8 +820,23 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
         cudaFuncSetAttribute(k_audio_resample_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       });
       if (smem > 200 * 1024) return fail(SDR_ERR_INVALID, "resampler tile does not fit in shared memory");
-      prof_begin(p, "k_audio_resample_v2", s);
-      if (p->stereo) k_audio_resample_v2<true><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
+      const size_t smem3 = smem + 32 * 2 * sizeof(int16_t);  // padded PCM rows
+      static std::once_flag once3[16];
+      std::call_once(once3[p->cfg.device & 15], [&] {
+        cudaFuncSetAttribute(k_audio_resample_v3<true, 101>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_audio_resample_v3<false, 101>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_audio_resample_v3<true, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_audio_resample_v3<false, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      });
+      auto launch3 = [&](void (*kern)(const ResampleArgs, int, int)) {
+        kern<<<grid, RS_NW * 32, smem3, s>>>(g, B, rows_cap);
+      };
+      prof_begin(p, "k_audio_resample", s);
+      if (p->TA == 101 && p->stereo) launch3(k_audio_resample_v3<true, 101>);
+      else if (p->TA == 101) launch3(k_audio_resample_v3<false, 101>);
+      else if (p->TA == 13 && p->stereo) launch3(k_audio_resample_v3<true, 13>);
+      else if (p->TA == 13) launch3(k_audio_resample_v3<false, 13>);
+      else if (p->stereo) k_audio_resample_v2<true><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
       else k_audio_resample_v2<false><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
       if ((rc = check_launch(p, "k_audio_resample_v2"))) return rc;
     }
