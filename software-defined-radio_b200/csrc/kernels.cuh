@@ -1009,10 +1009,16 @@ static __global__ void k_pll(const PllArgs a) {
   // next to (and overlapped with) the feedback chain of sample k+1.
   float pending_arg = 0.0f;
   bool have_pending = false;
-  float xnext = (a.n > 0) ? in[0] : 0.0f;
+  // input samples are fetched 8 steps ahead (each lane walks its own row, so every load is a
+  // separate line: its latency must not sit on the recurrence)
+  float xq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xq[i] = (i < a.n) ? in[i] : 0.0f;
   for (int k = 0; k < a.n; ++k) {
-    const float x = xnext;
-    if (k + 1 < a.n) xnext = in[k + 1];
+    const float x = xq[0];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) xq[i] = xq[i + 1];
+    xq[7] = (k + 8 < a.n) ? in[k + 8] : 0.0f;
     const float eI = xmul(x, fbI);
     const float eQ = xmul(x, -fbQ);
     float eD;

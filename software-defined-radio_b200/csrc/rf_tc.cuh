@@ -69,19 +69,25 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 // Recombine the four base-256 digit sums into the fixed-point FIR output and round once.
-// v = d0 + 2^8 d1 + 2^16 d2 + 2^24 d3 - corr is an integer below 2^48: both int32 halves and
-// the two fused multiply-adds are exact in double, so the only rounding is double -> float
-// (scaling by the power of two `sc` commutes with that rounding).
+// v = d0 + 2^8 d1 + 2^16 d2 + 2^24 d3 - corr is an integer below 2^47.  It is cut into
+// H = v >> 23 (|H| < 2^24) and L = v & (2^23-1): both are exactly representable floats, so
+// fma(H, 2^23 * sc, L * sc) performs the ONLY rounding, and it is the round-to-nearest of v * sc
+// (sc is a power of two).  No 64-bit conversion and no FP64 pipe (profiles/r1d, r1f: I2F.S64 was
+// the most stalled instruction; the double-precision form throttled the FP64 pipe).
 struct TcScale {
-  double sc;     // 2^-(S+7)
-  double sc16;   // 2^16 * sc
-  double c0;     // -corr * sc
+  long long corr;
+  float sc;     // 2^-(S+7)
+  float sc23;   // 2^23 * sc
 };
 __device__ __forceinline__ float tc_combine(const uint32_t *d, const TcScale &k) {
   const int lo = (int32_t)d[0] + 256 * (int32_t)d[1];
   const int hi = (int32_t)d[2] + 256 * (int32_t)d[3];
-  const double r = __fma_rn((double)hi, k.sc16, __fma_rn((double)lo, k.sc, k.c0));
-  return __double2float_rn(r);
+  const long long v = (long long)hi * 65536 + lo - k.corr;
+  const int H = (int)(v >> 23);
+  const uint32_t L = (uint32_t)v & 0x7fffffu;
+  // float(L) without a convert: L sits in the mantissa of 2^23
+  const float Lf = __fsub_rn(__uint_as_float(0x4B000000u | L), 8388608.0f);
+  return __fmaf_rn(__int2float_rn(H), k.sc23, __fmul_rn(Lf, k.sc));
 }
 // fmDemod on the fast path: same formula, approximate reciprocal (the fast variant is held to
 // 100 dB / +-1 LSB against the reference, not to bit equality; I/Q already differ by ~1e-7).
@@ -132,7 +138,7 @@ k_rf_demod_tc(const RfTcArgs g) {
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                          ((uint32_t)(TC_ROWS >> 4) << 24);
   uint32_t phase = 0;
-  const TcScale ks{(double)g.scale, (double)g.scale * 65536.0, -(double)g.corr * (double)g.scale};
+  const TcScale ks{g.corr, g.scale, g.scale * 8388608.0f};
 
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const long long j0 = (long long)tile * TC_TILE_OUT;
@@ -433,7 +439,7 @@ k_rf_demod_tc3(const RfTcArgs g) {
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                          ((uint32_t)(TC_ROWS >> 4) << 24);
   bool have_pred = false;  // predecessor of the segment's first output comes from `red`
-  const TcScale ks{(double)g.scale, (double)g.scale * 65536.0, -(double)g.corr * (double)g.scale};
+  const TcScale ks{g.corr, g.scale, g.scale * 8388608.0f};
 
   // Epilogue of tile `tile` (accumulator set buf, completion number `use` of mma_done[buf]).
   auto epilogue = [&](int tile, int buf, int use) {
