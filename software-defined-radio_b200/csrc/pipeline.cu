@@ -525,11 +525,11 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   std::vector<int8_t> tc_b;
   std::vector<int32_t> tc_h;
   if (cfg->variant == SDR_VARIANT_FAST) {
-    // fixed-point taps: hq = round(h * 2^S), |hq| < 2^30, four balanced base-256 digits
+    // fixed-point taps: hq = round(h * 2^S), |hq| < 2^22, three balanced base-256 digits
     float hmax = 0.0f;
     for (float h : p->h_rf) hmax = std::max(hmax, std::fabs(h));
     int S = 0;
-    while (S < 60 && std::ldexp((double)hmax, S + 1) < 1073741823.0) ++S;
+    while (S < 60 && std::ldexp((double)hmax, S + 1) < 4194303.0) ++S;
     tc_h.assign(TC_D * TC_Q, 0);
     long long hsum = 0;
     for (int t = 0; t < cfg->rf_taps; ++t) {
@@ -538,7 +538,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     }
     p->tc_corr = 128 * hsum;
     p->tc_scale = (float)std::ldexp(1.0, -(S + 7));
-    // B tile of phase ph: column 4*delta+d carries digit_d(h[10q+ph]) at k = delta + 15 - q
+    // B tile of phase ph: column 3*delta+d carries digit_d(h[10q+ph]) at k = delta + 15 - q
     tc_b.assign((size_t)TC_D * TC_BP, 0);
     auto put = [&](int ph, int col, int k, int8_t val) {  // canonical no-swizzle K-major order
       const size_t off = (size_t)ph * TC_BP + ((size_t)(k / 16) * (TC_N / 8) + col / 8) * 128 + (col % 8) * 16 + (k % 16);
@@ -547,10 +547,10 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     for (int t = 0; t < cfg->rf_taps; ++t) {
       const int q = t / TC_D, ph = t % TC_D;
       long long v = tc_h[t];
-      for (int d = 0; d < 4; ++d) {
+      for (int d = 0; d < TC_ND; ++d) {
         const int digit = (int)(((v + 128) & 255) - 128);
         v = (v - digit) >> 8;
-        for (int delta = 0; delta < 16; ++delta) put(ph, 4 * delta + d, delta + 15 - q, (int8_t)digit);
+        for (int delta = 0; delta < 16; ++delta) put(ph, TC_ND * delta + d, delta + 15 - q, (int8_t)digit);
       }
     }
   }

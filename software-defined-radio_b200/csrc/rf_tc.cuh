@@ -13,16 +13,16 @@
 //    row m-1: a matrix descriptor with leading-byte-offset 16 and stride-byte-offset 128
 //    turns the stream into that overlapping-row (Hankel) matrix in place, so row m sees
 //    xp[p][j0+16m-15 .. j0+16m+16] and produces the 16 outputs j0+16m+delta.
-// 3. The B operand of phase p holds the taps h[10q+p], scaled to 31-bit fixed point and
-//    split into four signed base-256 digits: column 4*delta+d has digit_d at k = delta+15-q.
+// 3. The B operand of phase p holds the taps h[10q+p], scaled to 23-bit fixed point and
+//    split into three signed base-256 digits: column 3*delta+d has digit_d at k = delta+15-q.
 //    Ten MMAs (one per phase) accumulate sum_t digit_d(h[t]) * u8[...] exactly in int32.
 // 4. The epilogue recombines the digits in int64, removes the 128 offset of the unsigned
 //    samples and rounds ONCE to float: the exactly rounded fixed-point FIR output (tap
-//    quantisation 2^-34).  It differs from the reference's sequential float sum only by the
+//    quantisation 2^-26, i.e. below the reference's own float rounding).  It differs from the reference's sequential float sum only by the
 //    reference's own accumulated rounding (~1e-7 relative; >= 100 dB SNR, PCM +-1 LSB).
 //    fmDemod follows in the same kernel with the reference's float operations; the
 //    one-sample state travels between rows by warp shuffle.
-// Per 128-row tile: 2048 outputs = 20480 input pairs, 20 MMAs of 128 x 64 x 32.
+// Per 128-row tile: 2048 outputs = 20480 input pairs, 20 MMAs of 128 x 48 x 32.
 #pragma once
 
 #include "kernels.cuh"
@@ -37,7 +37,8 @@ constexpr int TC_Q = 16;                     // taps per phase (151 = 15*10 + 1)
 constexpr int TC_FRONT = 16;                 // spare stream entries in front of row 0's window
 constexpr int TC_STREAM = TC_FRONT + 16 * (TC_ROWS - 1) + 32;  // 2080 bytes per stream
 constexpr int TC_NSTREAM = 2 * TC_D;         // 10 phases x {I,Q}
-constexpr int TC_N = 64;                     // 16 deltas x 4 digits
+constexpr int TC_ND = 3;                     // signed base-256 digits per tap (23-bit fixed point)
+constexpr int TC_N = 16 * TC_ND;             // 16 deltas x 3 digits = 48 accumulator columns
 constexpr int TC_BP = TC_N * 32;             // bytes of one phase's B tile
 constexpr int TC_HIST = 320;                 // raw history pairs the first tile reaches back
 constexpr size_t TC_SMEM = (size_t)TC_NSTREAM * TC_STREAM + (size_t)TC_D * TC_BP;
@@ -68,26 +69,39 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
-// Recombine the four base-256 digit sums into the fixed-point FIR output and round once.
-// v = d0 + 2^8 d1 + 2^16 d2 + 2^24 d3 - corr is an integer below 2^47.  It is cut into
-// H = v >> 23 (|H| < 2^24) and L = v & (2^23-1): both are exactly representable floats, so
-// fma(H, 2^23 * sc, L * sc) performs the ONLY rounding, and it is the round-to-nearest of v * sc
-// (sc is a power of two).  No 64-bit conversion and no FP64 pipe (profiles/r1d, r1f: I2F.S64 was
-// the most stalled instruction; the double-precision form throttled the FP64 pipe).
+// Recombine the three base-256 digit sums into the fixed-point FIR output and round once.
+// v = d0 + 2^8 d1 + 2^16 d2 - corr is an integer below 2^39.  It is cut into H = v >> 17
+// (|H| < 2^22) and L = v & (2^17-1): both are exactly representable floats, produced without a
+// convert instruction by planting them in the mantissa of a magic constant, so
+// fma(H, 2^17 * sc, L * sc) performs the ONLY rounding, and it is the round-to-nearest of v * sc
+// (sc is a power of two).  (profiles/r1d, r1f: I2F.S64 was the most stalled instruction of the
+// first version; a double-precision form throttled the FP64 pipe.)
 struct TcScale {
   long long corr;
   float sc;     // 2^-(S+7)
-  float sc23;   // 2^23 * sc
+  float sc17;   // 2^17 * sc
 };
+// 24 accumulator columns (8 outputs x 3 digits): one x16 and one x8 load.
+__device__ __forceinline__ void tc_ld24(uint32_t taddr, uint32_t (&v)[24]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                 "=r"(v[23])
+               : "r"(taddr + 16));
+}
+
 __device__ __forceinline__ float tc_combine(const uint32_t *d, const TcScale &k) {
   const int lo = (int32_t)d[0] + 256 * (int32_t)d[1];
-  const int hi = (int32_t)d[2] + 256 * (int32_t)d[3];
-  const long long v = (long long)hi * 65536 + lo - k.corr;
-  const int H = (int)(v >> 23);
-  const uint32_t L = (uint32_t)v & 0x7fffffu;
-  // float(L) without a convert: L sits in the mantissa of 2^23
+  const long long v = (long long)(int32_t)d[2] * 65536 + lo - k.corr;
+  const int H = (int)(v >> 17);
+  const uint32_t L = (uint32_t)v & 0x1ffffu;
+  const float Hf = __fsub_rn(__int_as_float(0x4B400000 + H), 12582912.0f);   // 2^23 + 2^22 + H
   const float Lf = __fsub_rn(__uint_as_float(0x4B000000u | L), 8388608.0f);
-  return __fmaf_rn(__int2float_rn(H), k.sc23, __fmul_rn(Lf, k.sc));
+  return __fmaf_rn(Hf, k.sc17, __fmul_rn(Lf, k.sc));
 }
 // fmDemod on the fast path: same formula, approximate reciprocal (the fast variant is held to
 // 100 dB / +-1 LSB against the reference, not to bit equality; I/Q already differ by ~1e-7).
@@ -138,7 +152,7 @@ k_rf_demod_tc(const RfTcArgs g) {
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                          ((uint32_t)(TC_ROWS >> 4) << 24);
   uint32_t phase = 0;
-  const TcScale ks{g.corr, g.scale, g.scale * 8388608.0f};
+  const TcScale ks{g.corr, g.scale, g.scale * 131072.0f};
 
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const long long j0 = (long long)tile * TC_TILE_OUT;
@@ -255,15 +269,15 @@ k_rf_demod_tc(const RfTcArgs g) {
     float fi[TC_OUT_PER_ROW], fq[TC_OUT_PER_ROW];
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t vi[16], vq[16];
-      tc_ld16(trow + 16 * c, vi);
-      tc_ld16(trow + TC_N + 16 * c, vq);
+    for (int c = 0; c < 2; ++c) {   // 24 columns = 8 outputs per pass
+      uint32_t vi[24], vq[24];
+      tc_ld24(trow + 24 * c, vi);
+      tc_ld24(trow + TC_N + 24 * c, vq);
       asm volatile("tcgen05.wait::ld.sync.aligned;");
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        fi[4 * c + k] = tc_combine(&vi[4 * k], ks);
-        fq[4 * c + k] = tc_combine(&vq[4 * k], ks);
+      for (int k = 0; k < 8; ++k) {
+        fi[8 * c + k] = tc_combine(&vi[3 * k], ks);
+        fq[8 * c + k] = tc_combine(&vq[3 * k], ks);
       }
     }
     // one-sample state: previous row's last output, by shuffle inside the warp and through
@@ -439,7 +453,7 @@ k_rf_demod_tc3(const RfTcArgs g) {
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                          ((uint32_t)(TC_ROWS >> 4) << 24);
   bool have_pred = false;  // predecessor of the segment's first output comes from `red`
-  const TcScale ks{g.corr, g.scale, g.scale * 8388608.0f};
+  const TcScale ks{g.corr, g.scale, g.scale * 131072.0f};
 
   // Epilogue of tile `tile` (accumulator set buf, completion number `use` of mma_done[buf]).
   auto epilogue = [&](int tile, int buf, int use) {
@@ -447,17 +461,16 @@ k_rf_demod_tc3(const RfTcArgs g) {
     mbar_wait(&mma_done[buf], use & 1);
     asm volatile("tcgen05.fence::after_thread_sync;");
     float fi[8], fq[8];
-    const uint32_t trow = tmem + buf * 2 * TC_N + 32 * half + ((uint32_t)((warp & 3) * 32) << 16);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t vi[16], vq[16];
-      tc_ld16(trow + 16 * c, vi);
-      tc_ld16(trow + TC_N + 16 * c, vq);
+    const uint32_t trow = tmem + buf * 2 * TC_N + 24 * half + ((uint32_t)((warp & 3) * 32) << 16);
+    {
+      uint32_t vi[24], vq[24];
+      tc_ld24(trow, vi);
+      tc_ld24(trow + TC_N, vq);
       asm volatile("tcgen05.wait::ld.sync.aligned;");
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        fi[4 * c + k] = tc_combine(&vi[4 * k], ks);
-        fq[4 * c + k] = tc_combine(&vq[4 * k], ks);
+      for (int k = 0; k < 8; ++k) {
+        fi[k] = tc_combine(&vi[3 * k], ks);
+        fq[k] = tc_combine(&vq[3 * k], ks);
       }
     }
     last_i[half][rowi] = fi[7];

@@ -22,7 +22,7 @@ def fixed_point_model(iq, h):
     """I/Q of the tensor-core front end, evaluated exactly on the host."""
     hmax = float(np.max(np.abs(h)))
     S = 0
-    while S < 60 and np.ldexp(hmax, S + 1) < 1073741823.0:
+    while S < 60 and np.ldexp(hmax, S + 1) < 4194303.0:   # 23-bit fixed point: three base-256 digits
         S += 1
     hq = np.rint(np.ldexp(h.astype(np.float64), S)).astype(np.int64)
     out = []
