@@ -243,6 +243,12 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     g.corr = p->tc_corr;
     g.scale = p->tc_scale;
     const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
+    // SDR_TC_KERNEL=1 selects the first, single-role kernel (kept as the readable reference of the
+    // algorithm; same bits).  Default: 8 warps, two CTAs per SM, staged + double-buffered.
+    static const bool single_role = [] {
+      const char *e = std::getenv("SDR_TC_KERNEL");
+      return e && std::atoi(e) == 1;
+    }();
     const int want = std::max(1, std::min((148 * 3 * 6 + p->cfg.batch - 1) / p->cfg.batch, n_tiles));
     g.tiles_per_seg = (n_tiles + want - 1) / want;
     const int segs = (n_tiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
@@ -251,7 +257,6 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
       cudaFuncSetAttribute(k_rf_demod_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
       cudaFuncSetAttribute(k_rf_demod_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC3_SMEM);
     });
-    static const bool single_role = std::getenv("SDR_TC_SINGLE_ROLE") != nullptr;
     dim3 grid(segs, p->cfg.batch);
     prof_begin(p, "k_rf_demod_tc", s);
     if (single_role) k_rf_demod_tc<<<grid, TC_ROWS, TC_SMEM, s>>>(g);

@@ -664,4 +664,10 @@ k_rf_demod_tc3(const RfTcArgs g) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
 }
 
+
+// Tried and dropped (profiles/r1g): one CTA per SM with 16 warps sharing each tile and the copy of
+// tile i+2, the transpose and MMAs of tile i and the epilogue of tile i-1 all overlapped.  It was
+// slower (0.84 ms vs 0.56 ms): the per-thread fixed costs are paid by 512 threads per tile (7450
+// warp instructions per tile instead of 5500) and 38 % of the stall samples sat on block barriers.
+
 }  // namespace sdr
