@@ -351,8 +351,17 @@ def run_ours(args):
             dom_ms = kt[dom][0] / kt[dom][1]
             alg_bytes = main["samples_per_step"] * bps  # per launch: one launch covers the whole batch
             achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+            traffic = None
+            try:  # measured DRAM bytes per launch of this kernel (ncu --set full), default workload only
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                w = tj["workload"]
+                if (w["mode"], w["audio_channels"], w["batch_per_gpu"], w["blocks_per_capture"]) == \
+                        (args.mode, args.audio_channels, args.batch, args.blocks) and dom in tj:
+                    traffic = tj[dom]["dram_bytes_per_launch"]
+            except Exception:
+                pass
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
                         "kernel_share_of_step": kt[dom][0] / args.steps / step_kernel_ms,
                         "whole_step_frac": value * 1e6 * bps / 1e9 / peak / world,
