@@ -864,6 +864,143 @@ k_audio_resample_v3(const ResampleArgs g, int batch, int rows_cap) {
   }
 }
 
+// Pair form (the default): v3 sits at 79 % of the shared-memory wavefront peak (profiles/r1f) because
+// every multiply-add reads its own input word.  Two CONSECUTIVE outputs use input windows that are
+// only DU0 or DU0+1 = floor(D/U) (+1) rows apart, so a warp that computes them together loads each
+// input row once and feeds both accumulators: 0.79 instead of 1.25 shared-memory wavefronts per
+// multiply-add.  The row walk is unrolled for both possible offsets (a warp-uniform branch picks
+// one); every accumulator still sees its taps in ascending order.
+template <bool STEREO, int TA, int DELTA>
+__device__ __forceinline__ void rs_pair(const float *__restrict__ ha, const float *__restrict__ hb,
+                                        const float *__restrict__ xtop, const float *__restrict__ ytop,
+                                        float &ma, float &mb, float &sa, float &sb) {
+  // xtop/ytop point at the newest row of output b (this lane's column); output a starts DELTA rows down
+  float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+#pragma unroll
+  for (int kb = 0; kb < TA + DELTA; ++kb) {
+    const int ka = kb - DELTA;
+    if (kb < TA && (kb & 3) == 0) vb = *reinterpret_cast<const float4 *>(hb + kb);
+    if (ka >= 0 && ka < TA && (ka & 3) == 0) va = *reinterpret_cast<const float4 *>(ha + ka);
+    const float x = xtop[-kb * RS_PITCH];
+    const float y = STEREO ? ytop[-kb * RS_PITCH] : 0.0f;
+    if (kb < TA) {
+      const float t = (kb & 3) == 0 ? vb.x : (kb & 3) == 1 ? vb.y : (kb & 3) == 2 ? vb.z : vb.w;
+      mb = xmac(mb, t, x);
+      if (STEREO) sb = xmac(sb, t, y);
+    }
+    if (ka >= 0 && ka < TA) {
+      const float t = (ka & 3) == 0 ? va.x : (ka & 3) == 1 ? va.y : (ka & 3) == 2 ? va.z : va.w;
+      ma = xmac(ma, t, x);
+      if (STEREO) sa = xmac(sa, t, y);
+    }
+  }
+}
+
+template <bool STEREO, int TA, int DU0>
+static __global__ void __launch_bounds__(RS_NW * 32)
+k_audio_resample_v4(const ResampleArgs g, int batch, int rows_cap) {
+  const AudioArgs &a = g.a;
+  constexpr int TA4 = (TA + 3) & ~3;
+  constexpr int PER = STEREO ? 2 : 1;
+  constexpr int PSP = RS_J * PER + 2;                // padded PCM row (int16) -> fewer bank conflicts
+  extern __shared__ __align__(16) float smem[];
+  float *hs = smem;                                  // [RS_J][TA4]
+  float *xs = hs + RS_J * TA4;                       // [rows_cap][33]
+  float *xs2 = xs + (size_t)rows_cap * RS_PITCH;
+  int16_t *ps = reinterpret_cast<int16_t *>(xs + (size_t)rows_cap * RS_PITCH * PER);
+  __shared__ int s_phase[RS_J], s_top[RS_J];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = blockIdx.x * RS_J;
+  const int jn = min(RS_J, a.n_out - j0);
+  const int c0 = blockIdx.y * 32;
+  const unsigned U = (unsigned)g.U, D = (unsigned)g.D;
+  const int i_lo = (int)(((unsigned)j0 * D) / U) - (TA - 1);
+  const int i_hi = (int)(((unsigned)(j0 + jn - 1) * D) / U);
+  const int rows = i_hi - i_lo + 1;
+  if (threadIdx.x < RS_J) {
+    const unsigned m = (unsigned)(j0 + threadIdx.x) * D;
+    const unsigned q = m / U;
+    s_phase[threadIdx.x] = (int)(m - q * U);
+    s_top[threadIdx.x] = (int)q - i_lo;   // also for outputs past n_out: rows_cap covers a full tile
+  }
+  // ---- transposed input tile: warp w streams the rows of captures w, w+8, ... ----
+#pragma unroll
+  for (int cc = 0; cc < 32 / RS_NW; ++cc) {
+    const int c = warp + cc * RS_NW;
+    const int ch = min(c0 + c, batch - 1);           // lanes past the batch re-read the last capture
+    const float *drow = a.demod + (size_t)ch * a.demod_stride + (a.demod_off - a.delay + i_lo);
+    float *dst = xs + c + lane * RS_PITCH;
+    if (STEREO) {
+      const float *srow = a.stf + (size_t)ch * a.stf_stride + (a.hist_off + i_lo);
+      const float *nrow = a.nco + (size_t)ch * a.nco_stride + (a.hist_off + i_lo);
+      float *dst2 = xs2 + c + lane * RS_PITCH;
+      for (int i = lane; i < rows; i += 32, dst += 32 * RS_PITCH, dst2 += 32 * RS_PITCH) {
+        *dst = drow[i];
+        *dst2 = xmul(xmul(srow[i], nrow[i]), 2.0f);
+      }
+    } else {
+      int i = lane;
+      for (; i + 96 < rows; i += 128, dst += 128 * RS_PITCH) {  // four loads in flight
+        const float v0 = drow[i], v1 = drow[i + 32], v2 = drow[i + 64], v3 = drow[i + 96];
+        dst[0] = v0; dst[32 * RS_PITCH] = v1; dst[64 * RS_PITCH] = v2; dst[96 * RS_PITCH] = v3;
+      }
+      for (; i < rows; i += 32, dst += 32 * RS_PITCH) *dst = drow[i];
+    }
+  }
+  __syncthreads();   // s_phase visible
+  // ---- taps of the tile's phases (zero padded to TA4) ----
+  for (int jj = warp; jj < RS_J; jj += RS_NW) {
+    const float *src = g.hp + (size_t)s_phase[jj] * TA;
+#pragma unroll
+    for (int k0 = 0; k0 < TA4; k0 += 32) {
+      const int k = k0 + lane;
+      if (k < TA4) hs[jj * TA4 + k] = (k < TA) ? __ldg(src + k) : 0.0f;
+    }
+  }
+  __syncthreads();
+  const float fu = (float)g.U;
+  // ---- each warp: consecutive outputs (jj, jj+1) together, 32 captures across the lanes ----
+  for (int jj = 2 * warp; jj < RS_J; jj += 2 * RS_NW) {
+    const int jb = jj + 1;
+    const float *ha = hs + jj * TA4, *hb = hs + jb * TA4;
+    const int top_b = s_top[jb], delta = top_b - s_top[jj];
+    const float *xtop = xs + top_b * RS_PITCH + lane, *ytop = xs2 + top_b * RS_PITCH + lane;
+    float ma = 0.0f, mb = 0.0f, sa = 0.0f, sb = 0.0f;
+    if (delta == DU0) rs_pair<STEREO, TA, DU0>(ha, hb, xtop, ytop, ma, mb, sa, sb);
+    else rs_pair<STEREO, TA, DU0 + 1>(ha, hb, xtop, ytop, ma, mb, sa, sb);
+    ma = xadd(ma, xmul(ma, fu));  // filter.cpp:213
+    mb = xadd(mb, xmul(mb, fu));
+    if (STEREO) {
+      sa = xadd(sa, xmul(sa, fu));
+      sb = xadd(sb, xmul(sb, fu));
+      ps[lane * PSP + 2 * jj] = pcm16(xadd(sa, ma));
+      ps[lane * PSP + 2 * jj + 1] = pcm16(xsub(ma, sa));
+      ps[lane * PSP + 2 * jb] = pcm16(xadd(sb, mb));
+      ps[lane * PSP + 2 * jb + 1] = pcm16(xsub(mb, sb));
+    } else {
+      ps[lane * PSP + jj] = pcm16(ma);
+      ps[lane * PSP + jb] = pcm16(mb);
+    }
+    const int ch = c0 + lane;
+    if (ch < batch && a.audio_filt) {
+      if (jj < jn) a.audio_filt[(size_t)ch * a.tap_stride + j0 + jj] = ma;
+      if (jb < jn) a.audio_filt[(size_t)ch * a.tap_stride + j0 + jb] = mb;
+      if (STEREO && a.stereo_final) {
+        if (jj < jn) a.stereo_final[(size_t)ch * a.tap_stride + j0 + jj] = sa;
+        if (jb < jn) a.stereo_final[(size_t)ch * a.tap_stride + j0 + jb] = sb;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- PCM rows out: one capture per warp pass, contiguous int16 along time ----
+  for (int c = warp; c < 32; c += RS_NW) {
+    const int ch = c0 + c;
+    if (ch >= batch) continue;
+    int16_t *dst = a.pcm + (size_t)ch * a.pcm_stride + (size_t)j0 * PER;
+    for (int q = lane; q < jn * PER; q += 32) dst[q] = ps[c * PSP + q];
+  }
+}
+
 // Stand-alone resampler on float in/out (no PCM), for sdr_fir_resample.
 struct ResampleOpArgs {
   const float *x;  // sample 0 at x_off, TA-1 history before it

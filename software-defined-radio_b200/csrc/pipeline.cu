@@ -826,23 +826,24 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
       });
       if (smem > 200 * 1024) return fail(SDR_ERR_INVALID, "resampler tile does not fit in shared memory");
       const size_t smem3 = smem + 32 * 2 * sizeof(int16_t);  // padded PCM rows
-      static std::once_flag once3[16];
-      std::call_once(once3[p->cfg.device & 15], [&] {
-        cudaFuncSetAttribute(k_audio_resample_v3<true, 101>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_audio_resample_v3<false, 101>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_audio_resample_v3<true, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_audio_resample_v3<false, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      });
-      auto launch3 = [&](void (*kern)(const ResampleArgs, int, int)) {
-        kern<<<grid, RS_NW * 32, smem3, s>>>(g, B, rows_cap);
-      };
+      using ResKernel = void (*)(const ResampleArgs, int, int);
+      ResKernel kern = nullptr;
+      const int du0 = p->m.audio_decim / p->m.audio_upsamp;   // rows between consecutive outputs (floor)
+      static const bool no_pairs = std::getenv("SDR_RESAMPLE_V3") != nullptr;
+      if (p->TA == 101 && du0 == 5 && !no_pairs) kern = p->stereo ? k_audio_resample_v4<true, 101, 5> : k_audio_resample_v4<false, 101, 5>;
+      else if (p->TA == 101 && du0 == 7 && !no_pairs) kern = p->stereo ? k_audio_resample_v4<true, 101, 7> : k_audio_resample_v4<false, 101, 7>;
+      else if (p->TA == 101) kern = p->stereo ? k_audio_resample_v3<true, 101> : k_audio_resample_v3<false, 101>;
+      else if (p->TA == 13) kern = p->stereo ? k_audio_resample_v3<true, 13> : k_audio_resample_v3<false, 13>;
       prof_begin(p, "k_audio_resample", s);
-      if (p->TA == 101 && p->stereo) launch3(k_audio_resample_v3<true, 101>);
-      else if (p->TA == 101) launch3(k_audio_resample_v3<false, 101>);
-      else if (p->TA == 13 && p->stereo) launch3(k_audio_resample_v3<true, 13>);
-      else if (p->TA == 13) launch3(k_audio_resample_v3<false, 13>);
-      else if (p->stereo) k_audio_resample_v2<true><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
-      else k_audio_resample_v2<false><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
+      if (kern) {
+        // (attribute set per launch: cheap, and correct for every instantiation and device)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        kern<<<grid, RS_NW * 32, smem3, s>>>(g, B, rows_cap);
+      } else if (p->stereo) {
+        k_audio_resample_v2<true><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
+      } else {
+        k_audio_resample_v2<false><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
+      }
       if ((rc = check_launch(p, "k_audio_resample_v2"))) return rc;
     }
   } else if (p->audio_fast) {
