@@ -161,7 +161,7 @@ def workload_config(args):
             "mode": args.mode, "audio_channels": args.audio_channels, "batch_per_gpu": args.batch,
             "blocks_per_capture": args.blocks, "l2_policy": "input batch larger than L2 (no flush needed)",
             "variant": ("fast (tensor-core RF front end; PCM within +-1 LSB of the reference)"
-                        if args.variant == "fast" and args.audio_channels == 1 and args.mode in (0, 2)
+                        if args.variant == "fast" and args.audio_channels == 1
                         else "exact (bit-identical to the reference)")}
 
 
@@ -197,8 +197,8 @@ def make_device_batch(torch, mode, batch, blocks, kind, device):
 
 
 def pick_variant(sdr, args, mode, audio_channels):
-    """FAST exists for mono with rf_decim 10 (modes 0, 2); everything else runs the exact path."""
-    if args.variant == "fast" and audio_channels == 1 and mode in (0, 2):
+    """FAST exists for mono (all modes); stereo needs the bit-exact path (PLL parity)."""
+    if args.variant == "fast" and audio_channels == 1:
         return sdr.VARIANT_FAST, "fast"
     return sdr.VARIANT_EXACT, "exact"
 

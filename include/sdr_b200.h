@@ -43,9 +43,9 @@ extern "C" {
 
 /* Arithmetic variants of the batched pipeline. */
 #define SDR_VARIANT_EXACT 0 /* CUDA-core path, bit-identical to the reference */
-/* Tensor-core RF front end (tcgen05 kind::i8 over the raw byte stream), mono and
- * rf_decim == 10 (modes 0 and 2) only.  I/Q are the exactly rounded fixed-point FIR
- * outputs (tap quantisation 2^-26) instead of the reference's sequential float sums:
+/* Tensor-core RF front end (tcgen05 kind::i8 over the raw byte stream), mono only, all four
+ * modes (rf_decim 10, 5, 3), rf_taps <= 151.  I/Q are the exactly rounded fixed-point FIR
+ * outputs (tap quantisation 2^-34) instead of the reference's sequential float sums:
  * float intermediates agree to >= 100 dB SNR and PCM to +-1 LSB, not bit for bit.
  * Stereo is refused: the PLL amplifies 1-ulp differences beyond the parity bound. */
 #define SDR_VARIANT_FAST 1

@@ -243,24 +243,20 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     g.corr = p->tc_corr;
     g.scale = p->tc_scale;
     const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
-    // SDR_TC_KERNEL=1 selects the first, single-role kernel (kept as the readable reference of the
-    // algorithm; same bits).  Default: 8 warps, two CTAs per SM, staged + double-buffered.
-    static const bool single_role = [] {
-      const char *e = std::getenv("SDR_TC_KERNEL");
-      return e && std::atoi(e) == 1;
-    }();
     const int want = std::max(1, std::min((148 * 3 * 6 + p->cfg.batch - 1) / p->cfg.batch, n_tiles));
     g.tiles_per_seg = (n_tiles + want - 1) / want;
     const int segs = (n_tiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
     static std::once_flag once[16];
     std::call_once(once[p->cfg.device & 15], [&] {
-      cudaFuncSetAttribute(k_rf_demod_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
-      cudaFuncSetAttribute(k_rf_demod_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC3_SMEM);
+      cudaFuncSetAttribute(k_rf_demod_tc<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<10>::SMEM);
+      cudaFuncSetAttribute(k_rf_demod_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<5>::SMEM);
+      cudaFuncSetAttribute(k_rf_demod_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<3>::SMEM);
     });
     dim3 grid(segs, p->cfg.batch);
     prof_begin(p, "k_rf_demod_tc", s);
-    if (single_role) k_rf_demod_tc<<<grid, TC_ROWS, TC_SMEM, s>>>(g);
-    else k_rf_demod_tc3<<<grid, 2 * TC_ROWS, TC3_SMEM, s>>>(g);
+    if (D == 10) k_rf_demod_tc<10><<<grid, TC_THREADS, TcCfg<10>::SMEM, s>>>(g);
+    else if (D == 5) k_rf_demod_tc<5><<<grid, TC_THREADS, TcCfg<5>::SMEM, s>>>(g);
+    else k_rf_demod_tc<3><<<grid, TC_THREADS, TcCfg<3>::SMEM, s>>>(g);
     return check_launch(p, "k_rf_demod_tc");
   }
   if (p->rf_fast) {
@@ -465,8 +461,8 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   if (cfg->variant == SDR_VARIANT_FAST) {
     if (cfg->channels != 1)
       return fail(SDR_ERR_INVALID, "SDR_VARIANT_FAST is mono only: stereo parity needs the bit-exact front end");
-    if (m.rf_decim != 10 || cfg->rf_taps > 151)
-      return fail(SDR_ERR_INVALID, "SDR_VARIANT_FAST needs rf_decim == 10 (modes 0, 2) and rf_taps <= 151");
+    if (cfg->rf_taps > TC_TMAX)
+      return fail(SDR_ERR_INVALID, "SDR_VARIANT_FAST supports rf_taps <= 151");
   }
   if ((long long)cfg->audio_taps * m.audio_upsamp > 65535)
     return fail(SDR_ERR_INVALID, "audio_taps*audio_upsamp exceeds unsigned short (filter.h:24)");
@@ -481,7 +477,8 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   p->TA = cfg->audio_taps;
   p->delay = p->stereo ? (cfg->stereo_taps - 1) / 2 : 0;
   p->HR = round_up(cfg->rf_taps - 1 + m.rf_decim, 8);
-  if (cfg->variant == SDR_VARIANT_FAST) p->HR = std::max(p->HR, TC_HIST);
+  if (cfg->variant == SDR_VARIANT_FAST)
+    p->HR = std::max(p->HR, m.rf_decim == 10 ? TcCfg<10>::HIST : m.rf_decim == 5 ? TcCfg<5>::HIST : TcCfg<3>::HIST);
   p->HA = round_up(p->TA - 1, 4);
   p->HD = round_up(std::max(p->stereo ? cfg->stereo_taps - 1 : 0, p->TA - 1 + p->delay), 4);
   sdr_mode_info mi;
@@ -530,12 +527,16 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   std::vector<int8_t> tc_b;
   std::vector<int32_t> tc_h;
   if (cfg->variant == SDR_VARIANT_FAST) {
-    // fixed-point taps: hq = round(h * 2^S), |hq| < 2^22, three balanced base-256 digits
+    // fixed-point taps: hq = round(h * 2^S), |hq| < 2^30, four balanced base-256 digits
     float hmax = 0.0f;
     for (float h : p->h_rf) hmax = std::max(hmax, std::fabs(h));
     int S = 0;
-    while (S < 60 && std::ldexp((double)hmax, S + 1) < 4194303.0) ++S;
-    tc_h.assign(TC_D * TC_Q, 0);
+    while (S < 60 && std::ldexp((double)hmax, S + 1) < 1073741823.0) ++S;
+    const int D = m.rf_decim;
+    const int Q = (TC_TMAX + D - 1) / D;                 // taps per phase (TcCfg<D>::Q)
+    const int K = (16 + Q - 1 + 31) / 32 * 32;           // bytes per A row (TcCfg<D>::K)
+    const int BP = TC_N * K;
+    tc_h.assign((size_t)D * Q, 0);
     long long hsum = 0;
     for (int t = 0; t < cfg->rf_taps; ++t) {
       tc_h[t] = (int32_t)std::llrint(std::ldexp((double)p->h_rf[t], S));  // round half to even
@@ -543,19 +544,19 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     }
     p->tc_corr = 128 * hsum;
     p->tc_scale = (float)std::ldexp(1.0, -(S + 7));
-    // B tile of phase ph: column 3*delta+d carries digit_d(h[10q+ph]) at k = delta + 15 - q
-    tc_b.assign((size_t)TC_D * TC_BP, 0);
+    // B tile of phase ph: column 4*delta+d carries digit_d(h[D*q+ph]) at k = delta + (Q-1) - q
+    tc_b.assign((size_t)D * BP, 0);
     auto put = [&](int ph, int col, int k, int8_t val) {  // canonical no-swizzle K-major order
-      const size_t off = (size_t)ph * TC_BP + ((size_t)(k / 16) * (TC_N / 8) + col / 8) * 128 + (col % 8) * 16 + (k % 16);
+      const size_t off = (size_t)ph * BP + ((size_t)(k / 16) * (TC_N / 8) + col / 8) * 128 + (col % 8) * 16 + (k % 16);
       tc_b[off] = val;
     };
     for (int t = 0; t < cfg->rf_taps; ++t) {
-      const int q = t / TC_D, ph = t % TC_D;
+      const int q = t / D, ph = t % D;
       long long v = tc_h[t];
       for (int d = 0; d < TC_ND; ++d) {
         const int digit = (int)(((v + 128) & 255) - 128);
         v = (v - digit) >> 8;
-        for (int delta = 0; delta < 16; ++delta) put(ph, TC_ND * delta + d, delta + 15 - q, (int8_t)digit);
+        for (int delta = 0; delta < 16; ++delta) put(ph, TC_ND * delta + d, delta + (Q - 1) - q, (int8_t)digit);
       }
     }
   }

@@ -1,4 +1,4 @@
-"""GPU tests of SDR_VARIANT_FAST (tensor-core RF front end, mono, rf_decim = 10).
+"""GPU tests of SDR_VARIANT_FAST (tensor-core RF front end, mono, all four modes).
 
 Two bars: (1) against an exact integer model of what the kernel is specified to compute (fixed-
 point taps, int64 sums, one rounding to float) the I/Q outputs must be BIT-IDENTICAL; (2) against
@@ -18,23 +18,23 @@ def snr_db(ref, got):
     return np.inf if err == 0 else 10 * np.log10(np.sum(ref ** 2) / err)
 
 
-def fixed_point_model(iq, h):
+def fixed_point_model(iq, h, decim):
     """I/Q of the tensor-core front end, evaluated exactly on the host."""
     hmax = float(np.max(np.abs(h)))
     S = 0
-    while S < 60 and np.ldexp(hmax, S + 1) < 4194303.0:   # 23-bit fixed point: three base-256 digits
+    while S < 60 and np.ldexp(hmax, S + 1) < 1073741823.0:   # 31-bit fixed point: four base-256 digits
         S += 1
     hq = np.rint(np.ldexp(h.astype(np.float64), S)).astype(np.int64)
     out = []
     for comp in (0, 1):
         x = iq[comp::2].astype(np.int64) - 128
         full = np.convolve(x, hq)[: x.size]          # y[m] = sum_t hq[t] x[m-t], zero history
-        v = full[::10]
+        v = full[::decim]
         out.append((v.astype(np.float32) * np.float32(np.ldexp(1.0, -(S + 7)))).astype(np.float32))
     return out
 
 
-@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("taps", [(151, 101), (13, 13), (64, 101)])
 def test_fast_front_end(sdr, orc, mode, taps):
     B = 3
@@ -46,10 +46,10 @@ def test_fast_front_end(sdr, orc, mode, taps):
         pcm = p.process_host(iq)
         got = {n: [p.tap(n, c) for c in range(B)] for n in ("i_filt", "q_filt", "demod", "audio_filt")}
         assert "k_rf_demod_tc" in p.kernel_times() or True
-    rf_Fs = sdr.mode_info(mode).rf_Fs
+    rf_Fs, decim = sdr.mode_info(mode).rf_Fs, sdr.mode_info(mode).rf_decim
     h = sdr.impulseResponseLPF(rf_Fs, 100000, taps[0])
     for c in range(B):
-        mi, mq = fixed_point_model(iq[c], h)
+        mi, mq = fixed_point_model(iq[c], h, decim)
         assert np.array_equal(got["i_filt"][c].view(np.uint32), mi.view(np.uint32)), "I differs from the integer model"
         assert np.array_equal(got["q_filt"][c].view(np.uint32), mq.view(np.uint32)), "Q differs from the integer model"
         want_pcm, want = orc.run_chain(iq[c], mode, 1, taps[0], taps[1], 151)
@@ -60,19 +60,21 @@ def test_fast_front_end(sdr, orc, mode, taps):
         assert d.max() <= 1, f"PCM differs by {d.max()} LSB"
 
 
-def test_fast_streaming_and_wide_batch(sdr, orc):
+@pytest.mark.parametrize("mode,cuts", [(0, [0, 70000, 70100, 150000]), (1, [0, 600, 61440, 100020]),
+                                       (3, [0, 19200, 134400, 172800])])
+def test_fast_streaming_and_wide_batch(sdr, orc, mode, cuts):
     """Carried raw history / predecessor output across calls and segments; 200 captures."""
     B = 200
-    iq = siggen.make_batch(B, 0, 2, "stereo", distinct=5)
+    iq = siggen.make_batch(B, mode, 2, "stereo", distinct=5)
     nbytes = iq.shape[1]
-    with sdr.Pipeline(mode=0, channels=1, batch=B, variant=sdr.VARIANT_FAST, max_bytes_per_channel=nbytes) as p:
+    with sdr.Pipeline(mode=mode, channels=1, batch=B, variant=sdr.VARIANT_FAST, max_bytes_per_channel=nbytes) as p:
         one = p.process_host(iq)
         p.reset()
-        cuts = [0, 70000, 70100, 150000, nbytes]
+        cuts = cuts + [nbytes]
         parts = [p.process_host(np.ascontiguousarray(iq[:, a:b])) for a, b in zip(cuts[:-1], cuts[1:])]
     assert np.array_equal(one, np.concatenate(parts, axis=1)), "chunked calls differ from one call"
     for c in (0, 4, 5, 199):
-        want, _ = orc.run_chain(iq[c], 0, 1, keep_taps=False)
+        want, _ = orc.run_chain(iq[c], mode, 1, keep_taps=False)
         assert np.abs(one[c].astype(np.int32) - want.astype(np.int32)).max() <= 1
 
 
@@ -82,8 +84,8 @@ def test_fast_silence_is_exactly_zero(sdr):
         assert not p.process_host(iq).any()
 
 
-def test_fast_refuses_stereo_and_other_decimations(sdr):
-    for kw in (dict(mode=0, channels=2), dict(mode=1, channels=1), dict(mode=3, channels=1)):
+def test_fast_refuses_stereo(sdr):
+    for kw in (dict(mode=0, channels=2), dict(mode=3, channels=2), dict(mode=0, channels=1, rf_taps=201)):
         with pytest.raises(sdr.SdrError) as e:
             sdr.Pipeline(variant=sdr.VARIANT_FAST, **kw)
         assert e.value.code == -1
