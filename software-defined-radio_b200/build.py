@@ -29,6 +29,8 @@ CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
               "--expt-relaxed-constexpr"]
+if os.environ.get("SDR_TC_TRACE"):   # debug build for tools/tc_trace.py (clock stamps in the tensor-core kernel)
+    NVCC_FLAGS.append("-DSDR_TC_TRACE")
 
 
 def _newer(target: str, sources: list[str]) -> bool:

@@ -1001,6 +1001,125 @@ k_audio_resample_v4(const ResampleArgs g, int batch, int rows_cap) {
   }
 }
 
+// Quad form (mono default).  profiles/r1h: the pair form spends 40 % of its time filling the
+// transposed tile (load -> shared store round trips) and its multiply-add loop is bound by
+// shared-memory wavefronts (0.78 per multiply-add).  Here
+//  * the input tile stays in its natural [capture][time] layout with an ODD row pitch, so it is
+//    filled by 4-byte asynchronous copies (no registers, no transposition) and lane c still reads
+//    bank (c*pitch + t) % 32: conflict free;
+//  * a warp computes FOUR consecutive outputs for 64 captures (two per lane): one input word
+//    feeds four accumulators, and the four outputs' taps arrive as ONE broadcast float4 from a
+//    per-phase table that the host lays out in the warp's walk order (`tq`, below): 3 wavefronts
+//    per 8 multiply-adds.
+// Every accumulator still sees its own taps in ascending order (the table only inserts zero
+// taps before/after them, and acc + 0*x == acc), so the result stays bit-identical to
+// filter.cpp:191-223; FMA=true (SDR_VARIANT_FAST only) contracts the multiply-add.
+//
+// tq[phi0][kb][o], phi0 = phase of the quad's first output, o = 0..3:
+//   tq = hp[phase_o][kb - d_o] (0 outside 0..TA-1),  d_o = top_3 - top_o,  input row = top_3 - kb.
+constexpr int RQ_J = 32;        // outputs per tile (8 warps x 4)
+struct ResampleQuadArgs {
+  AudioArgs a;
+  const float *tq;  // [U][KB][4]
+  int U, D, TA, KB;
+  int n_in;         // valid input samples of this call (rows at or past it read as zero)
+};
+
+template <bool FMA>
+__device__ __forceinline__ float rq_mac(float acc, float h, float x) {
+  return FMA ? __fmaf_rn(h, x, acc) : xmac(acc, h, x);
+}
+
+template <bool FMA, int NC>
+static __global__ void __launch_bounds__(256)
+k_audio_resample_v5(const ResampleQuadArgs g, int batch, int pitch) {
+  const AudioArgs &a = g.a;
+  constexpr int CAPS = 32 * NC;                       // captures per tile (NC per lane)
+  constexpr int PSP = RQ_J + 2;                       // padded PCM row (int16)
+  extern __shared__ __align__(16) float smem[];
+  float *tqs = smem;                                  // [8 warps][KB][4]
+  float *xs = tqs + 8 * g.KB * 4;                     // [CAPS][pitch]
+  int16_t *ps = reinterpret_cast<int16_t *>(xs + (size_t)CAPS * pitch);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = blockIdx.x * RQ_J;
+  const int jn = min(RQ_J, a.n_out - j0);
+  const int c0 = blockIdx.y * CAPS;
+  const unsigned U = (unsigned)g.U, D = (unsigned)g.D;
+  // rows [i_lo, i_hi]: from the oldest row any quad of the tile can touch (KB-1 below its newest
+  // row) to the newest row of the last quad that holds a valid output
+  const int i_lo = (int)(((unsigned)j0 * D) / U) - (g.KB - 1);
+  const int jlast = j0 + ((jn + 3) & ~3) - 1;
+  const int i_hi = (int)(((unsigned)jlast * D) / U);
+  const int rows = i_hi - i_lo + 1;
+  const int first = a.demod_off - a.delay + i_lo;     // element index of row 0 in the capture's buffer
+  const bool interior = first >= 0 && i_hi < g.n_in;  // every row of the tile is a stored sample
+  const uint32_t xs_s = (uint32_t)__cvta_generic_to_shared(xs);
+  for (int c = warp; c < CAPS; c += 8) {
+    const int ch = min(c0 + c, batch - 1);            // lanes past the batch re-read the last capture
+    const float *src = a.demod + (size_t)ch * a.demod_stride + first;
+    const uint32_t dst = xs_s + (uint32_t)(c * pitch) * 4u;
+    if (interior) {
+      for (int i = lane; i < rows; i += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(src + i) : "memory");
+    } else {
+      for (int i = lane; i < rows; i += 32)
+        xs[(size_t)c * pitch + i] = (first + i >= 0 && i_lo + i < g.n_in) ? src[i] : 0.0f;
+    }
+  }
+  const int jq = j0 + 4 * warp;
+  const bool active = jq < a.n_out;
+  if (active) {
+    const unsigned phi0 = ((unsigned)jq * D) % U;
+    const float4 *src = reinterpret_cast<const float4 *>(g.tq) + (size_t)phi0 * g.KB;
+    float4 *dst = reinterpret_cast<float4 *>(tqs) + warp * g.KB;
+    for (int i = lane; i < g.KB; i += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)),
+                   "l"(src + i) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (active) {
+    const int top3 = (int)(((unsigned)(jq + 3) * D) / U) - i_lo;
+    const float *x0 = xs + (size_t)lane * pitch + top3;
+    const float4 *t = reinterpret_cast<const float4 *>(tqs) + warp * g.KB;
+    float acc[4][NC] = {};
+    for (int kb = 0; kb < g.KB; kb += 4) {  // KB is a multiple of 4
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 h = t[kb + u];
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+          const float x = x0[(size_t)32 * cc * pitch - (kb + u)];
+          acc[0][cc] = rq_mac<FMA>(acc[0][cc], h.x, x);
+          acc[1][cc] = rq_mac<FMA>(acc[1][cc], h.y, x);
+          acc[2][cc] = rq_mac<FMA>(acc[2][cc], h.z, x);
+          acc[3][cc] = rq_mac<FMA>(acc[3][cc], h.w, x);
+        }
+      }
+    }
+    const float fu = (float)g.U;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc) {
+        const float y = xadd(acc[o][cc], xmul(acc[o][cc], fu));  // filter.cpp:213
+        const int c = lane + 32 * cc;
+        ps[c * PSP + 4 * warp + o] = pcm16(y);
+        if (a.audio_filt && c0 + c < batch && jq + o < a.n_out)
+          a.audio_filt[(size_t)(c0 + c) * a.tap_stride + jq + o] = y;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- PCM rows out: one capture per warp pass, contiguous int16 along time ----
+  for (int c = warp; c < CAPS; c += 8) {
+    const int ch = c0 + c;
+    if (ch >= batch) break;
+    int16_t *dst = a.pcm + (size_t)ch * a.pcm_stride + (size_t)j0;
+    if (lane < jn) dst[lane] = ps[c * PSP + lane];
+  }
+}
+
 // Stand-alone resampler on float in/out (no PCM), for sdr_fir_resample.
 struct ResampleOpArgs {
   const float *x;  // sample 0 at x_off, TA-1 history before it

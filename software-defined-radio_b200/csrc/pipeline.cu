@@ -108,8 +108,9 @@ struct sdr_pipeline {
   size_t cap_if, cap_audio;  // per-capture capacities of one call
   size_t demod_stride, stf_stride, nco_stride, car_stride, tap_if_stride, tap_audio_stride;
   bool rf_fast, audio_fast, bpf_fast;  // specialised kernels available for these tap counts
-  std::vector<float> h_rf, h_audio, h_pilot, h_stereo, h_poly;
-  DevBuf<float> d_h_rf, d_h_audio, d_h_pilot, d_h_stereo, d_h_poly;
+  std::vector<float> h_rf, h_audio, h_pilot, h_stereo, h_poly, h_quad;
+  DevBuf<float> d_h_rf, d_h_audio, d_h_pilot, d_h_stereo, d_h_poly, d_h_quad;
+  int quad_kb = 0;  // rows of one quad table (k_audio_resample_v5)
   // tensor-core front end (SDR_VARIANT_FAST)
   DevBuf<int8_t> tc_bmat;
   DevBuf<int32_t> tc_hq;
@@ -254,9 +255,9 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     });
     dim3 grid(segs, p->cfg.batch);
     prof_begin(p, "k_rf_demod_tc", s);
-    if (D == 10) k_rf_demod_tc<10><<<grid, TC_THREADS, TcCfg<10>::SMEM, s>>>(g);
-    else if (D == 5) k_rf_demod_tc<5><<<grid, TC_THREADS, TcCfg<5>::SMEM, s>>>(g);
-    else k_rf_demod_tc<3><<<grid, TC_THREADS, TcCfg<3>::SMEM, s>>>(g);
+    if (D == 10) k_rf_demod_tc<10><<<grid, TC_BLOCK, TcCfg<10>::SMEM, s>>>(g);
+    else if (D == 5) k_rf_demod_tc<5><<<grid, TC_BLOCK, TcCfg<5>::SMEM, s>>>(g);
+    else k_rf_demod_tc<3><<<grid, TC_BLOCK, TcCfg<3>::SMEM, s>>>(g);
     return check_launch(p, "k_rf_demod_tc");
   }
   if (p->rf_fast) {
@@ -522,6 +523,23 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     p->h_poly.resize((size_t)U * p->TA);
     for (int ph = 0; ph < U; ++ph)
       for (int k = 0; k < p->TA; ++k) p->h_poly[(size_t)ph * p->TA + k] = p->h_audio[ph + (size_t)k * U];
+    if (!p->stereo) {
+      // quad tables of k_audio_resample_v5: the taps of four consecutive outputs in the order the
+      // warp walks the input rows (newest row of the fourth output first)
+      const int D = m.audio_decim;
+      const int dmax = (U - 1 + 3 * D) / U;
+      const int KB = round_up(p->TA + dmax, 4);
+      p->quad_kb = KB;
+      p->h_quad.assign((size_t)U * KB * 4, 0.0f);
+      for (int phi0 = 0; phi0 < U; ++phi0) {
+        const int top3 = (phi0 + 3 * D) / U;
+        for (int o = 0; o < 4; ++o) {
+          const int top = (phi0 + o * D) / U, ph = (phi0 + o * D) % U, d = top3 - top;
+          for (int k = 0; k < p->TA; ++k)
+            p->h_quad[((size_t)phi0 * KB + (k + d)) * 4 + o] = p->h_poly[(size_t)ph * p->TA + k];
+        }
+      }
+    }
   }
 
   std::vector<int8_t> tc_b;
@@ -578,6 +596,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   TRY(upload(p->d_h_rf, p->h_rf));
   TRY(upload(p->d_h_audio, p->h_audio));
   if (p->resample) TRY(upload(p->d_h_poly, p->h_poly));
+  if (!p->h_quad.empty()) TRY(upload(p->d_h_quad, p->h_quad));
   if (cfg->variant == SDR_VARIANT_FAST) {
     TRY(p->tc_bmat.alloc(tc_b.size()));
     TRY(p->tc_hq.alloc(tc_h.size()));
@@ -807,7 +826,27 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   if (p->resample) {
     ResampleArgs g{aa, p->d_h_poly.p, p->m.audio_upsamp, p->m.audio_decim, p->TA};
     static const bool use_v1 = std::getenv("SDR_RESAMPLE_V1") != nullptr;
-    if (use_v1) {
+    static const bool no_quads = std::getenv("SDR_RESAMPLE_V4") != nullptr;
+    if (!p->stereo && !no_quads && !use_v1) {
+      ResampleQuadArgs q{aa, p->d_h_quad.p, p->m.audio_upsamp, p->m.audio_decim, p->TA, p->quad_kb, (int)n_if};
+      const int KB = p->quad_kb;
+      static const int nc = std::getenv("SDR_RESAMPLE_NC") ? std::atoi(std::getenv("SDR_RESAMPLE_NC")) : 2;
+      const int caps = 32 * nc;
+      int pitch = (int)(((long long)(RQ_J - 1) * p->m.audio_decim) / p->m.audio_upsamp) + KB + 2;
+      pitch |= 1;  // odd: lane c reads bank (c * pitch + t) % 32
+      const size_t smem = ((size_t)8 * KB * 4 + (size_t)caps * pitch) * sizeof(float) +
+                          (size_t)caps * (RQ_J + 2) * sizeof(int16_t);
+      if (smem > 200 * 1024) return fail(SDR_ERR_INVALID, "resampler tile does not fit in shared memory");
+      dim3 grid(((int)n_audio + RQ_J - 1) / RQ_J, (B + caps - 1) / caps);
+      using QuadKernel = void (*)(const ResampleQuadArgs, int, int);
+      const bool fma = p->cfg.variant == SDR_VARIANT_FAST;
+      QuadKernel kern = nc == 2 ? (fma ? k_audio_resample_v5<true, 2> : k_audio_resample_v5<false, 2>)
+                                : (fma ? k_audio_resample_v5<true, 1> : k_audio_resample_v5<false, 1>);
+      prof_begin(p, "k_audio_resample", s);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      kern<<<grid, 256, smem, s>>>(q, (int)B, pitch);
+      if ((rc = check_launch(p, "k_audio_resample_v5"))) return rc;
+    } else if (use_v1) {
       dim3 grid(((int)n_audio + 127) / 128, B);
       prof_begin(p, "k_audio_resample", s);
       if (p->stereo) k_audio_resample<true><<<grid, 128, 0, s>>>(g);
@@ -1145,3 +1184,10 @@ extern "C" int sdr_pipeline_process_host(sdr_pipeline *p, const uint8_t *iq, siz
   SDR_CUDA(cudaStreamSynchronize(p->s_compute));
   return SDR_OK;
 }
+
+#ifdef SDR_TC_TRACE
+extern "C" int sdr_debug_tc_trace(long long *out, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, sdr::g_tc_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? 0 : 1;
+}
+#endif

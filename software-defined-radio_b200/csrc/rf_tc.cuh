@@ -37,7 +37,8 @@
 namespace sdr {
 
 constexpr int TC_ROWS = 128;                 // A rows per tile (= TMEM lanes)
-constexpr int TC_THREADS = 2 * TC_ROWS;
+constexpr int TC_THREADS = 2 * TC_ROWS;       // worker threads (transpose + epilogue)
+constexpr int TC_BLOCK = TC_THREADS + 32;    // + one warp that only issues MMAs and bulk copies
 constexpr int TC_TILE_OUT = TC_ROWS * 16;    // 2048 outputs per tile
 constexpr int TC_TMAX = 151;                 // longest supported filter
 constexpr int TC_ND = 4;                     // signed base-256 digits per tap (31-bit fixed point)
@@ -140,9 +141,9 @@ __device__ __forceinline__ float tc_combine(const uint32_t *d, const TcScale &k)
 // fmDemod on the fast path: same formula, approximate reciprocal (the fast variant is held to
 // 100 dB / +-1 LSB against the reference, not to bit equality; I/Q already differ by ~1e-7).
 __device__ __forceinline__ float tc_demod(float i, float q, float pi, float pq) {
-  const float den = i * i + q * q;
-  if (den == 0.0f) return 0.0f;
-  return __fdividef(i * (q - pq) - q * (i - pi), den);
+  const float den = __fmaf_rn(i, i, __fmul_rn(q, q));
+  const float num = __fmaf_rn(i, __fsub_rn(q, pq), -__fmul_rn(q, __fsub_rn(i, pi)));
+  return den == 0.0f ? 0.0f : __fdividef(num, den);
 }
 
 // One transposer group: GE consecutive entries of all 2*D streams from D*GE input pairs that sit
@@ -167,8 +168,20 @@ __device__ __forceinline__ void tc_transpose_group(const uint32_t *w, uint8_t *s
   }
 }
 
+#ifdef SDR_TC_TRACE
+// Debug build only (tools/tc_trace.py): clock64 stamps of one CTA, [warp 0..8][tile 0..15][stamp 0..11].
+__device__ long long g_tc_trace[9 * 16 * 12];
+#define TC_STAMP(it, k)                                                                         \
+  do {                                                                                          \
+    if (blockIdx.x == 1 && blockIdx.y == 5 && lane == 0 && (it) < 16)                           \
+      g_tc_trace[(warp * 16 + (it)) * 12 + (k)] = clock64();                                    \
+  } while (0)
+#else
+#define TC_STAMP(it, k) do { } while (0)
+#endif
+
 template <int D>
-static __global__ void __launch_bounds__(TC_THREADS, 2)
+static __global__ void __launch_bounds__(TC_BLOCK, 2)
 k_rf_demod_tc(const RfTcArgs g) {
   using C = TcCfg<D>;
   const RfArgs &a = g.a;
@@ -176,13 +189,16 @@ k_rf_demod_tc(const RfTcArgs g) {
   uint8_t *raw = tc_smem;                                   // [C::RAW] staged input bytes
   uint8_t *streams = tc_smem + C::RAW;                      // [2D][C::STREAM]
   int8_t *bs = reinterpret_cast<int8_t *>(tc_smem + C::RAW + C::NSTREAM * C::STREAM);
-  __shared__ float last_i[2][TC_ROWS], last_q[2][TC_ROWS];  // [half][row]: I,Q of delta 7 / 15
+  // I,Q of delta 7 / 15 of every row, [tile % 3][half][row]: a set is rewritten three tiles later,
+  // i.e. after two more CTA barriers, so readers of tile t and t+1 are always done with it
+  __shared__ float last_i[3][2][TC_ROWS], last_q[3][2][TC_ROWS];
   __shared__ float carry_iq[2];
   __shared__ long long red[2][TC_THREADS / 32];
-  __shared__ __align__(8) uint64_t mma_done[2], raw_full;
+  __shared__ __align__(8) uint64_t mma_done[2], raw_full, streams_ready;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TC_STAMP(15, 10);
   const int rowi = (warp & 3) * 32 + lane;  // TMEM lane = A row served by this thread
   const int half = warp >> 2;               // which 8 of the row's 16 outputs
   const int b = blockIdx.y;
@@ -194,12 +210,15 @@ k_rf_demod_tc(const RfTcArgs g) {
   const uint8_t *hrow = a.hist + (size_t)b * 2 * a.rf_hist_len;
   const bool row_aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
 
-  for (int i = tid; i < D * C::BP / 16; i += TC_THREADS)
+  const bool issuer = warp == TC_THREADS / 32;   // warp 8: lane 0 issues MMAs and bulk copies
+  auto workers_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); };
+  for (int i = tid; i < D * C::BP / 16; i += TC_BLOCK)
     reinterpret_cast<uint4 *>(bs)[i] = __ldg(reinterpret_cast<const uint4 *>(g.bmat) + i);
   if (tid == 0) {
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
     mbar_init(&raw_full, 1);
+    mbar_init(&streams_ready, TC_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
@@ -219,8 +238,10 @@ k_rf_demod_tc(const RfTcArgs g) {
   // Epilogue of tile `tile` (accumulator set buf, completion number `use` of mma_done[buf]).
   auto epilogue = [&](int tile, int buf, int use) {
     const long long j0 = (long long)tile * TC_TILE_OUT;
+    TC_STAMP(tile - tile_begin + 1, 4);
     mbar_wait(&mma_done[buf], use & 1);
     asm volatile("tcgen05.fence::after_thread_sync;");
+    TC_STAMP(tile - tile_begin + 1, 5);
     float fi[8], fq[8];
     const uint32_t trow = tmem + buf * 2 * TC_N + 32 * half + ((uint32_t)((warp & 3) * 32) << 16);
     {
@@ -229,23 +250,30 @@ k_rf_demod_tc(const RfTcArgs g) {
       asm volatile("tcgen05.wait::ld.sync.aligned;");
 #pragma unroll
       for (int k = 0; k < 8; ++k) fi[k] = tc_combine(&v[4 * k], ks);
+      TC_STAMP(tile - tile_begin + 1, 6);
       tc_ld32(trow + TC_N, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;");
 #pragma unroll
       for (int k = 0; k < 8; ++k) fq[k] = tc_combine(&v[4 * k], ks);
     }
-    last_i[half][rowi] = fi[7];
-    last_q[half][rowi] = fq[7];
+    const int set = (tile - tile_begin) % 3, pset = (set + 2) % 3;
+    last_i[set][half][rowi] = fi[7];
+    last_q[set][half][rowi] = fq[7];
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    TC_STAMP(tile - tile_begin + 1, 7);
+    workers_sync();
+    TC_STAMP(tile - tile_begin + 1, 8);
     float pi, pq;
     if (half == 1) {            // delta 8 follows delta 7 of the same row
-      pi = last_i[0][rowi];
-      pq = last_q[0][rowi];
+      pi = last_i[set][0][rowi];
+      pq = last_q[set][0][rowi];
     } else if (rowi > 0) {      // delta 0 follows delta 15 of the previous row
-      pi = last_i[1][rowi - 1];
-      pq = last_q[1][rowi - 1];
-    } else if (tile == tile_begin && have_pred) {
+      pi = last_i[set][1][rowi - 1];
+      pq = last_q[set][1][rowi - 1];
+    } else if (tile > tile_begin) {  // ... or the last output of the previous tile
+      pi = last_i[pset][1][TC_ROWS - 1];
+      pq = last_q[pset][1][TC_ROWS - 1];
+    } else if (have_pred) {
       long long si = 0, sq = 0;
       for (int k = 0; k < TC_THREADS / 32; ++k) {
         si += red[0][k];
@@ -293,11 +321,7 @@ k_rf_demod_tc(const RfTcArgs g) {
           }
       }
     }
-    __syncthreads();  // last_* / carry reads done before they are rewritten
-    if (half == 1 && rowi == TC_ROWS - 1) {
-      carry_iq[0] = fi[7];
-      carry_iq[1] = fq[7];
-    }
+    TC_STAMP(tile - tile_begin + 1, 9);
   };
 
   if (tile_begin == 0 && tid < 2) carry_iq[tid] = a.prev_in[2 * b + tid];
@@ -313,7 +337,7 @@ k_rf_demod_tc(const RfTcArgs g) {
   auto issue_raw = [&](int tile) {
     const long long wbase = 2ll * D * tile * TC_TILE_OUT - C::BASE;
     if (tile_is_bulk(tile)) {
-      if (tid == 0) {
+      if (issuer && lane == 0) {
         constexpr uint32_t BYTES = C::RAW_BYTES;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(&raw_full)), "r"(BYTES)
                      : "memory");
@@ -325,6 +349,7 @@ k_rf_demod_tc(const RfTcArgs g) {
       }
       return;
     }
+    if (issuer) return;
     for (int q = tid; q < C::RAW_BYTES / 16; q += TC_THREADS) {
       const long long pos = wbase + 16ll * q;
       if (row_aligned && pos >= 0 && pos + 16 <= 2 * a.n_rf) {
@@ -356,11 +381,50 @@ k_rf_demod_tc(const RfTcArgs g) {
   };
   issue_raw(tile_begin);
 
+  if (issuer) {
+    // ---- issue warp: once all workers have written the streams of tile `it`, the bulk copy of
+    // the next tile into `raw` (free: every worker arrived after its last read) and the MMAs ----
+    if (lane == 0) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int it = tile - tile_begin, buf = it & 1;
+        mbar_wait(&streams_ready, it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        TC_STAMP(it, 10);
+        // the copy goes first: issuing the MMAs blocks for most of their run time (tools/tc_trace.py)
+        if (tile + 1 < tile_end) issue_raw(tile + 1);  // no-op unless the next tile is a bulk copy
+        const uint32_t s0 = tc_smem_u32(streams) + TC_FRONT, b0 = tc_smem_u32(bs);
+        const uint32_t d0 = tmem + buf * 2 * TC_N;
+#pragma unroll
+        for (int comp = 0; comp < 2; ++comp) {
+#pragma unroll
+          for (int p = 0; p < D; ++p) {
+#pragma unroll
+            for (int ksx = 0; ksx < C::KSTEPS; ++ksx) {
+              const uint64_t da = tc_desc(s0 + (2 * p + comp) * C::STREAM + 32 * ksx, 16, 128);
+              const uint64_t db = tc_desc(b0 + p * C::BP + ksx * 2 * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
+              const uint32_t acc = (p | ksx) != 0;
+              asm volatile(
+                  "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d0 + comp * TC_N),
+                  "l"(da), "l"(db), "r"(idesc), "r"(acc));
+            }
+          }
+        }
+        tc_commit(&mma_done[buf]);
+        TC_STAMP(it, 11);
+      }
+    }
+    __syncwarp();
+  } else {
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int it = tile - tile_begin, buf = it & 1;
+    const bool bulk = tile_is_bulk(tile);
+    TC_STAMP(it, 0);
     wait_raw(tile);                                                      // this tile's bytes have landed
+    TC_STAMP(it, 1);
     if (it > 0) mbar_wait(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);      // MMAs of tile it-1 have read `streams`
-    __syncthreads();                                                     // everyone's copies are visible
+    TC_STAMP(it, 2);
+    if (!bulk) workers_sync();                                           // chunked staging: everyone's copies are visible
     // ---- 1. transpose raw -> 20 phase streams (each thread: 40 input pairs per group) ----
     for (int grp = tid; grp < C::NGRP; grp += TC_THREADS) {
       uint32_t w[C::WIN / 4];
@@ -372,32 +436,15 @@ k_rf_demod_tc(const RfTcArgs g) {
       }
       tc_transpose_group<D>(w, streams, grp);
     }
+    TC_STAMP(it, 3);
+    // Every worker publishes its stream entries to the async proxy and arrives; only the issue
+    // warp waits for all 256 arrivals -- the workers go straight to the previous tile's epilogue.
     asm volatile("fence.proxy.async.shared::cta;");
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    // ---- 2. MMAs of this tile into accumulator set buf (drained by the epilogue of tile it-2) ----
-    if (tid == 0) {
-      const uint32_t s0 = tc_smem_u32(streams) + TC_FRONT, b0 = tc_smem_u32(bs);
-      const uint32_t d0 = tmem + buf * 2 * TC_N;
-#pragma unroll
-      for (int comp = 0; comp < 2; ++comp) {
-#pragma unroll
-        for (int p = 0; p < D; ++p) {
-#pragma unroll
-          for (int ksx = 0; ksx < C::KSTEPS; ++ksx) {
-            const uint64_t da = tc_desc(s0 + (2 * p + comp) * C::STREAM + 32 * ksx, 16, 128);
-            const uint64_t db = tc_desc(b0 + p * C::BP + ksx * 2 * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
-            const uint32_t acc = (p | ksx) != 0;
-            asm volatile(
-                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d0 + comp * TC_N),
-                "l"(da), "l"(db), "r"(idesc), "r"(acc));
-          }
-        }
-      }
-      tc_commit(&mma_done[buf]);
-    }
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&streams_ready)) : "memory");
+    const bool next_chunked = tile + 1 < tile_end && !tile_is_bulk(tile + 1);
+    // rare: the first tile of a later segment reads other threads' stream entries below; a
+    // chunked next tile overwrites `raw`
+    if ((tile == tile_begin && tile != 0) || next_chunked) workers_sync();
     // ---- predecessor of the segment's first output, in integers (see the single-role kernel) ----
     if (tile == tile_begin && tile != 0) {
       long long si = 0, sq = 0;
@@ -418,19 +465,19 @@ k_rf_demod_tc(const RfTcArgs g) {
       }
       have_pred = true;  // visible to everyone after the epilogue's first __syncthreads
     }
-    // ---- 3. next tile's bytes start flowing; epilogue of the previous tile meanwhile ----
-    // `raw` is free: every thread's reads precede the __syncthreads above (and that barrier's
-    // fence.proxy.async orders them before the bulk copy's async-proxy writes)
-    if (tile + 1 < tile_end) issue_raw(tile + 1);
+    // ---- 3. a chunked next tile is staged by the workers (after the barrier above) ----
+    if (next_chunked) issue_raw(tile + 1);
     if (it > 0) epilogue(tile - 1, buf ^ 1, (it - 1) >> 1);
   }
   {
     const int it = tile_end - 1 - tile_begin;
     epilogue(tile_end - 1, it & 1, it >> 1);
   }
+  }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+  TC_STAMP(15, 11);
 }
 
 
