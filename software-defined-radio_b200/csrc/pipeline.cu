@@ -111,6 +111,7 @@ struct sdr_pipeline {
   std::vector<float> h_rf, h_audio, h_pilot, h_stereo, h_poly, h_quad;
   DevBuf<float> d_h_rf, d_h_audio, d_h_pilot, d_h_stereo, d_h_poly, d_h_quad;
   int quad_kb = 0;  // rows of one quad table (k_audio_resample_v5)
+  DevBuf<int> tc_next_item;  // work counter of the persistent tensor-core front end
   // tensor-core front end (SDR_VARIANT_FAST)
   DevBuf<int8_t> tc_bmat;
   DevBuf<int32_t> tc_hq;
@@ -243,17 +244,26 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     g.hq = p->tc_hq.p;
     g.corr = p->tc_corr;
     g.scale = p->tc_scale;
+    // persistent CTAs (two per SM) take work items (capture, segment) round-robin; segments are
+    // sized so that every CTA gets at least ~12 items: the last round is then nearly full
     const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
-    const int want = std::max(1, std::min((148 * 3 * 6 + p->cfg.batch - 1) / p->cfg.batch, n_tiles));
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->cfg.device);
+    const int n_cta = 2 * n_sm;
+    static const int items_per_cta = std::getenv("SDR_TC_ITEMS") ? std::atoi(std::getenv("SDR_TC_ITEMS")) : 12;
+    const int want = std::max(1, std::min((n_cta * items_per_cta + p->cfg.batch - 1) / p->cfg.batch, n_tiles));
     g.tiles_per_seg = (n_tiles + want - 1) / want;
-    const int segs = (n_tiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
+    g.segs = (n_tiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
+    g.batch = p->cfg.batch;
     static std::once_flag once[16];
     std::call_once(once[p->cfg.device & 15], [&] {
       cudaFuncSetAttribute(k_rf_demod_tc<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<10>::SMEM);
       cudaFuncSetAttribute(k_rf_demod_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<5>::SMEM);
       cudaFuncSetAttribute(k_rf_demod_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<3>::SMEM);
     });
-    dim3 grid(segs, p->cfg.batch);
+    dim3 grid(std::min(n_cta, g.segs * g.batch));
+    g.next_item = p->tc_next_item.p;
+    if (cudaMemsetAsync(g.next_item, 0, sizeof(int), s) != cudaSuccess) return fail(SDR_ERR_CUDA, "cudaMemsetAsync");
     prof_begin(p, "k_rf_demod_tc", s);
     if (D == 10) k_rf_demod_tc<10><<<grid, TC_BLOCK, TcCfg<10>::SMEM, s>>>(g);
     else if (D == 5) k_rf_demod_tc<5><<<grid, TC_BLOCK, TcCfg<5>::SMEM, s>>>(g);
@@ -600,6 +610,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   if (cfg->variant == SDR_VARIANT_FAST) {
     TRY(p->tc_bmat.alloc(tc_b.size()));
     TRY(p->tc_hq.alloc(tc_h.size()));
+    TRY(p->tc_next_item.alloc(1));
     rc = cudaMemcpy(p->tc_bmat.p, tc_b.data(), tc_b.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
                  cudaMemcpy(p->tc_hq.p, tc_h.data(), tc_h.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess
              ? SDR_OK
@@ -1186,6 +1197,13 @@ extern "C" int sdr_pipeline_process_host(sdr_pipeline *p, const uint8_t *iq, siz
 }
 
 #ifdef SDR_TC_TRACE
+extern "C" int sdr_debug_tc_times(long long *begin, long long *end, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(begin, sdr::g_tc_begin, (size_t)n * sizeof(long long)) == cudaSuccess &&
+                 cudaMemcpyFromSymbol(end, sdr::g_tc_end, (size_t)n * sizeof(long long)) == cudaSuccess
+             ? 0
+             : 1;
+}
 extern "C" int sdr_debug_tc_trace(long long *out, int n) {
   cudaDeviceSynchronize();
   return cudaMemcpyFromSymbol(out, sdr::g_tc_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? 0 : 1;

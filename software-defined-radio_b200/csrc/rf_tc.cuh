@@ -75,7 +75,9 @@ struct RfTcArgs {
   const int32_t *hq;    // fixed-point taps, D*Q entries (zero padded)
   long long corr;       // 128 * sum(hq): offset of the unsigned samples
   float scale;          // 2^-(S+7)
-  int tiles_per_seg;
+  int tiles_per_seg;    // work item = tiles_per_seg consecutive tiles of one capture
+  int segs, batch;      // items = segs * batch
+  int *next_item;       // device counter, zeroed before the launch: further items are gridDim.x + atomicAdd
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) {
@@ -171,9 +173,10 @@ __device__ __forceinline__ void tc_transpose_group(const uint32_t *w, uint8_t *s
 #ifdef SDR_TC_TRACE
 // Debug build only (tools/tc_trace.py): clock64 stamps of one CTA, [warp 0..8][tile 0..15][stamp 0..11].
 __device__ long long g_tc_trace[9 * 16 * 12];
+__device__ long long g_tc_begin[1024], g_tc_end[1024];
 #define TC_STAMP(it, k)                                                                         \
   do {                                                                                          \
-    if (blockIdx.x == 1 && blockIdx.y == 5 && lane == 0 && (it) < 16)                           \
+    if (tc_trace_on && blockIdx.x == 7 && lane == 0 && (it) < 16)                           \
       g_tc_trace[(warp * 16 + (it)) * 12 + (k)] = clock64();                                    \
   } while (0)
 #else
@@ -190,28 +193,33 @@ k_rf_demod_tc(const RfTcArgs g) {
   uint8_t *streams = tc_smem + C::RAW;                      // [2D][C::STREAM]
   int8_t *bs = reinterpret_cast<int8_t *>(tc_smem + C::RAW + C::NSTREAM * C::STREAM);
   // I,Q of delta 7 / 15 of every row, [tile % 3][half][row]: a set is rewritten three tiles later,
-  // i.e. after two more CTA barriers, so readers of tile t and t+1 are always done with it
+  // i.e. after two more worker barriers, so readers of tile t and t+1 are always done with it
   __shared__ float last_i[3][2][TC_ROWS], last_q[3][2][TC_ROWS];
   __shared__ float carry_iq[2];
   __shared__ long long red[2][TC_THREADS / 32];
-  __shared__ __align__(8) uint64_t mma_done[2], raw_full, streams_ready;
+  __shared__ __align__(8) uint64_t mma_done[2], raw_full, streams_ready, item_ready;
+  __shared__ int item_slot[2];   // item of the CTA's k-th round at [k & 1], -1 = no more work
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  bool tc_trace_on = true;   // used by the SDR_TC_TRACE debug build only
   TC_STAMP(15, 10);
+#ifdef SDR_TC_TRACE
+  long long tc_begin_ns;
+  {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    tc_begin_ns = (long long)ns;
+  }
+#endif
   const int rowi = (warp & 3) * 32 + lane;  // TMEM lane = A row served by this thread
   const int half = warp >> 2;               // which 8 of the row's 16 outputs
-  const int b = blockIdx.y;
   const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
-  const int tile_begin = blockIdx.x * g.tiles_per_seg;
-  const int tile_end = min(tile_begin + g.tiles_per_seg, n_tiles);
-  if (tile_begin >= tile_end) return;
-  const uint8_t *row = a.iq + (size_t)b * a.iq_stride;
-  const uint8_t *hrow = a.hist + (size_t)b * 2 * a.rf_hist_len;
-  const bool row_aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
-
+  const int n_items = g.segs * g.batch;     // work item = (capture, segment of tiles_per_seg tiles)
   const bool issuer = warp == TC_THREADS / 32;   // warp 8: lane 0 issues MMAs and bulk copies
   auto workers_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); };
+
+  // ---- once per (persistent) CTA: tap digits, barriers, tensor memory ----
   for (int i = tid; i < D * C::BP / 16; i += TC_BLOCK)
     reinterpret_cast<uint4 *>(bs)[i] = __ldg(reinterpret_cast<const uint4 *>(g.bmat) + i);
   if (tid == 0) {
@@ -219,6 +227,7 @@ k_rf_demod_tc(const RfTcArgs g) {
     mbar_init(&mma_done[1], 1);
     mbar_init(&raw_full, 1);
     mbar_init(&streams_ready, TC_THREADS);
+    mbar_init(&item_ready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
@@ -232,253 +241,304 @@ k_rf_demod_tc(const RfTcArgs g) {
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                          ((uint32_t)(TC_ROWS >> 4) << 24);
-  bool have_pred = false;  // predecessor of the segment's first output comes from `red`
   const TcScale ks{g.corr, g.scale, g.scale * 8388608.0f};
 
-  // Epilogue of tile `tile` (accumulator set buf, completion number `use` of mma_done[buf]).
-  auto epilogue = [&](int tile, int buf, int use) {
-    const long long j0 = (long long)tile * TC_TILE_OUT;
-    TC_STAMP(tile - tile_begin + 1, 4);
-    mbar_wait(&mma_done[buf], use & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    TC_STAMP(tile - tile_begin + 1, 5);
-    float fi[8], fq[8];
-    const uint32_t trow = tmem + buf * 2 * TC_N + 32 * half + ((uint32_t)((warp & 3) * 32) << 16);
-    {
-      uint32_t v[32];
-      tc_ld32(trow, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;");
-#pragma unroll
-      for (int k = 0; k < 8; ++k) fi[k] = tc_combine(&v[4 * k], ks);
-      TC_STAMP(tile - tile_begin + 1, 6);
-      tc_ld32(trow + TC_N, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;");
-#pragma unroll
-      for (int k = 0; k < 8; ++k) fq[k] = tc_combine(&v[4 * k], ks);
-    }
-    const int set = (tile - tile_begin) % 3, pset = (set + 2) % 3;
-    last_i[set][half][rowi] = fi[7];
-    last_q[set][half][rowi] = fq[7];
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    TC_STAMP(tile - tile_begin + 1, 7);
-    workers_sync();
-    TC_STAMP(tile - tile_begin + 1, 8);
-    float pi, pq;
-    if (half == 1) {            // delta 8 follows delta 7 of the same row
-      pi = last_i[set][0][rowi];
-      pq = last_q[set][0][rowi];
-    } else if (rowi > 0) {      // delta 0 follows delta 15 of the previous row
-      pi = last_i[set][1][rowi - 1];
-      pq = last_q[set][1][rowi - 1];
-    } else if (tile > tile_begin) {  // ... or the last output of the previous tile
-      pi = last_i[pset][1][TC_ROWS - 1];
-      pq = last_q[pset][1][TC_ROWS - 1];
-    } else if (have_pred) {
-      long long si = 0, sq = 0;
-      for (int k = 0; k < TC_THREADS / 32; ++k) {
-        si += red[0][k];
-        sq += red[1][k];
-      }
-      pi = xmul(__ll2float_rn(si), g.scale);
-      pq = xmul(__ll2float_rn(sq), g.scale);
-    } else {
-      pi = carry_iq[0];
-      pq = carry_iq[1];
-    }
-    const long long jrow = j0 + 16 * rowi + 8 * half;
-    float dm[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      dm[k] = tc_demod(fi[k], fq[k], pi, pq);
-      pi = fi[k];
-      pq = fq[k];
-    }
-    float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
-    if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 3) == 0) {
-      *reinterpret_cast<float4 *>(drow + jrow) = make_float4(dm[0], dm[1], dm[2], dm[3]);
-      *reinterpret_cast<float4 *>(drow + jrow + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (jrow + k < a.n_if) drow[jrow + k] = dm[k];
-    }
-    if (a.i_filt) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (jrow + k < a.n_if) {
-          a.i_filt[(size_t)b * a.tap_stride + jrow + k] = fi[k];
-          a.q_filt[(size_t)b * a.tap_stride + jrow + k] = fq[k];
-        }
-    }
-    {
-      const long long last = (long long)a.n_if - 1 - jrow;
-      if (last >= 0 && last < 8) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k == last) {
-            a.prev_out[2 * b] = fi[k];
-            a.prev_out[2 * b + 1] = fq[k];
-          }
-      }
-    }
-    TC_STAMP(tile - tile_begin + 1, 9);
+  // Geometry of a work item.  A tile that lies entirely inside the capture is staged by ONE bulk
+  // asynchronous copy (TMA, completes on raw_full); tiles that touch the history in front of the
+  // capture or its end are assembled chunk by chunk by the workers.
+  struct Item {
+    int b, tile_begin, tile_end;
+    const uint8_t *row, *hrow;
+    bool row_aligned;
   };
-
-  if (tile_begin == 0 && tid < 2) carry_iq[tid] = a.prev_in[2 * b + tid];
-
-  // Stage the raw bytes of a tile: stream bytes [2*D*j0 - BASE, +RAW_BYTES).  A tile that
-  // lies entirely inside the capture is one bulk asynchronous copy (TMA, completes on raw_full);
-  // tiles that touch the history in front of the capture or its end are assembled chunk by chunk.
-  auto tile_is_bulk = [&](int tile) -> bool {
-    const long long wbase = 2ll * D * tile * TC_TILE_OUT - C::BASE;
-    return row_aligned && wbase >= 0 && wbase + C::RAW_BYTES <= 2 * a.n_rf;
+  auto get_item = [&](int item) {
+    Item w;
+    w.b = item / g.segs;
+    w.tile_begin = (item - w.b * g.segs) * g.tiles_per_seg;
+    w.tile_end = min(w.tile_begin + g.tiles_per_seg, n_tiles);
+    w.row = a.iq + (size_t)w.b * a.iq_stride;
+    w.hrow = a.hist + (size_t)w.b * 2 * a.rf_hist_len;
+    w.row_aligned = ((reinterpret_cast<uintptr_t>(w.row) & 15) == 0);
+    return w;
   };
-  uint32_t raw_phase = 0;
-  auto issue_raw = [&](int tile) {
+  auto tile_is_bulk = [&](const Item &w, int tile) -> bool {
     const long long wbase = 2ll * D * tile * TC_TILE_OUT - C::BASE;
-    if (tile_is_bulk(tile)) {
-      if (issuer && lane == 0) {
-        constexpr uint32_t BYTES = C::RAW_BYTES;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(&raw_full)), "r"(BYTES)
-                     : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                tc_smem_u32(raw)),
-            "l"(row + wbase), "r"(BYTES), "r"(tc_smem_u32(&raw_full))
-            : "memory");
-      }
-      return;
-    }
-    if (issuer) return;
+    return w.row_aligned && wbase >= 0 && wbase + C::RAW_BYTES <= 2 * a.n_rf;
+  };
+  auto issue_bulk = [&](const Item &w, int tile) {   // one thread
+    const long long wbase = 2ll * D * tile * TC_TILE_OUT - C::BASE;
+    constexpr uint32_t BYTES = C::RAW_BYTES;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(&raw_full)), "r"(BYTES)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            tc_smem_u32(raw)),
+        "l"(w.row + wbase), "r"(BYTES), "r"(tc_smem_u32(&raw_full))
+        : "memory");
+  };
+  auto stage_chunked = [&](const Item &w, int tile) {  // all workers
+    const long long wbase = 2ll * D * tile * TC_TILE_OUT - C::BASE;
     for (int q = tid; q < C::RAW_BYTES / 16; q += TC_THREADS) {
       const long long pos = wbase + 16ll * q;
-      if (row_aligned && pos >= 0 && pos + 16 <= 2 * a.n_rf) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc_smem_u32(raw + 16 * q)), "l"(row + pos)
+      if (w.row_aligned && pos >= 0 && pos + 16 <= 2 * a.n_rf) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc_smem_u32(raw + 16 * q)), "l"(w.row + pos)
                      : "memory");
+      } else if (pos >= 2 * a.n_rf) {
+        *reinterpret_cast<uint4 *>(raw + 16 * q) = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
       } else {
+        // edge chunk: 16 independent byte loads (one latency), centred zero beyond either end
+        uint32_t v[16];
+#pragma unroll
         for (int k = 0; k < 16; ++k) {
           const long long p = pos + k;
-          uint8_t val = 128;  // centred zero beyond either end
-          if (p < 0) {
-            const long long h = 2ll * a.rf_hist_len + p;
-            if (h >= 0) val = hrow[h];
-          } else if (p < 2 * a.n_rf) {
-            val = row[p];
-          }
-          raw[16 * q + k] = val;
+          const long long h = 2ll * a.rf_hist_len + p;
+          const uint8_t *src = p < 0 ? (h >= 0 ? w.hrow + h : nullptr) : (p < 2 * a.n_rf ? w.row + p : nullptr);
+          v[k] = src ? (uint32_t)__ldg(src) : 128u;
         }
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = v[4 * k] | (v[4 * k + 1] << 8) | (v[4 * k + 2] << 16) | (v[4 * k + 3] << 24);
+        *reinterpret_cast<uint4 *>(raw + 16 * q) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto wait_raw = [&](int tile) {
-    if (tile_is_bulk(tile)) {
-      mbar_wait(&raw_full, raw_phase);
-      raw_phase ^= 1;
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-  };
-  issue_raw(tile_begin);
 
   if (issuer) {
-    // ---- issue warp: once all workers have written the streams of tile `it`, the bulk copy of
-    // the next tile into `raw` (free: every worker arrived after its last read) and the MMAs ----
+    // ---- issue warp.  Per tile: wait until all workers have written its streams (which also
+    // means `raw` is free), start the bulk copy of the NEXT tile -- it goes first because issuing
+    // the MMAs blocks for most of their run time (tools/tc_trace.py) -- then the MMAs. ----
     if (lane == 0) {
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int it = tile - tile_begin, buf = it & 1;
-        mbar_wait(&streams_ready, it & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        TC_STAMP(it, 10);
-        // the copy goes first: issuing the MMAs blocks for most of their run time (tools/tc_trace.py)
-        if (tile + 1 < tile_end) issue_raw(tile + 1);  // no-op unless the next tile is a bulk copy
-        const uint32_t s0 = tc_smem_u32(streams) + TC_FRONT, b0 = tc_smem_u32(bs);
-        const uint32_t d0 = tmem + buf * 2 * TC_N;
+      uint32_t gt = 0;  // tiles issued so far by this CTA
+      for (uint32_t round = 0;; ++round) {
+        mbar_wait(&item_ready, round & 1);     // worker 0 has published this round's item
+        const int item = item_slot[round & 1];
+        if (item < 0) break;
+        const Item w = get_item(item);
+        tc_trace_on = round == 2;
+        for (int tile = w.tile_begin; tile < w.tile_end; ++tile, ++gt) {
+          const uint32_t buf = gt & 1;
+          mbar_wait(&streams_ready, gt & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          TC_STAMP(tile - w.tile_begin, 10);
+          if (tile + 1 < w.tile_end && tile_is_bulk(w, tile + 1)) issue_bulk(w, tile + 1);
+          const uint32_t s0 = tc_smem_u32(streams) + TC_FRONT, b0 = tc_smem_u32(bs);
+          const uint32_t d0 = tmem + buf * 2 * TC_N;
 #pragma unroll
-        for (int comp = 0; comp < 2; ++comp) {
+          for (int comp = 0; comp < 2; ++comp) {
 #pragma unroll
-          for (int p = 0; p < D; ++p) {
+            for (int p = 0; p < D; ++p) {
 #pragma unroll
-            for (int ksx = 0; ksx < C::KSTEPS; ++ksx) {
-              const uint64_t da = tc_desc(s0 + (2 * p + comp) * C::STREAM + 32 * ksx, 16, 128);
-              const uint64_t db = tc_desc(b0 + p * C::BP + ksx * 2 * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
-              const uint32_t acc = (p | ksx) != 0;
-              asm volatile(
-                  "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d0 + comp * TC_N),
-                  "l"(da), "l"(db), "r"(idesc), "r"(acc));
+              for (int ksx = 0; ksx < C::KSTEPS; ++ksx) {
+                const uint64_t da = tc_desc(s0 + (2 * p + comp) * C::STREAM + 32 * ksx, 16, 128);
+                const uint64_t db = tc_desc(b0 + p * C::BP + ksx * 2 * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
+                const uint32_t acc = (p | ksx) != 0;
+                asm volatile(
+                    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d0 + comp * TC_N),
+                    "l"(da), "l"(db), "r"(idesc), "r"(acc));
+              }
             }
           }
+          tc_commit(&mma_done[buf]);
+          TC_STAMP(tile - w.tile_begin, 11);
         }
-        tc_commit(&mma_done[buf]);
-        TC_STAMP(it, 11);
       }
     }
     __syncwarp();
   } else {
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
-    const int it = tile - tile_begin, buf = it & 1;
-    const bool bulk = tile_is_bulk(tile);
-    TC_STAMP(it, 0);
-    wait_raw(tile);                                                      // this tile's bytes have landed
-    TC_STAMP(it, 1);
-    if (it > 0) mbar_wait(&mma_done[buf ^ 1], ((it - 1) >> 1) & 1);      // MMAs of tile it-1 have read `streams`
-    TC_STAMP(it, 2);
-    if (!bulk) workers_sync();                                           // chunked staging: everyone's copies are visible
-    // ---- 1. transpose raw -> 20 phase streams (each thread: 40 input pairs per group) ----
-    for (int grp = tid; grp < C::NGRP; grp += TC_THREADS) {
-      uint32_t w[C::WIN / 4];
-      const uint4 *src = reinterpret_cast<const uint4 *>(raw + C::WB * grp);
+    // ---- workers: transpose tile t, then the epilogue of tile t-1 while the MMAs of t run ----
+    uint32_t gt = 0;         // tiles transposed so far by this CTA (same count as the issue warp's)
+    uint32_t raw_phase = 0;  // completions of raw_full consumed so far
+    int item = blockIdx.x;   // first item; later ones come from the device counter (dynamic balance:
+                             // CTA run times differ by +-12 %, tools/tc_trace.py)
+    for (uint32_t round = 0;; ++round) {
+      workers_sync();        // the previous item's readers of carry_iq / red / raw / item_slot are done
+      if (tid == 0) {
+        if (round > 0) item = (int)gridDim.x + atomicAdd(g.next_item, 1);
+        if (item >= n_items) item = -1;
+        item_slot[round & 1] = item;
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&item_ready)) : "memory");
+      }
+      workers_sync();
+      item = item_slot[round & 1];
+      if (item < 0) break;
+      const Item w = get_item(item);
+      tc_trace_on = true;
+      TC_STAMP(15, round < 10 ? round : 9);
+      tc_trace_on = round == 2;
+      const int b = w.b;
+      bool have_pred = false;  // predecessor of the segment's first output comes from `red`
+      if (w.tile_begin == 0 && tid < 2) carry_iq[tid] = a.prev_in[2 * b + tid];
+      if (!tile_is_bulk(w, w.tile_begin)) stage_chunked(w, w.tile_begin);
+      else if (tid == 0) issue_bulk(w, w.tile_begin);   // `raw` is free: the previous item is drained
+
+      // Epilogue of tile `tile` (global tile number t: accumulator set t & 1, its (t >> 1)-th use).
+      auto epilogue = [&](int tile, uint32_t t) {
+        const long long j0 = (long long)tile * TC_TILE_OUT;
+        const uint32_t buf = t & 1;
+        TC_STAMP(tile - w.tile_begin + 1, 4);
+        mbar_wait(&mma_done[buf], (t >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        TC_STAMP(tile - w.tile_begin + 1, 5);
+        float fi[8], fq[8];
+        const uint32_t trow = tmem + buf * 2 * TC_N + 32 * half + ((uint32_t)((warp & 3) * 32) << 16);
+        {
+          uint32_t v[32];
+          tc_ld32(trow, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;");
 #pragma unroll
-      for (int k = 0; k < C::WIN / 16; ++k) {
-        const uint4 v = src[k];
-        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-      }
-      tc_transpose_group<D>(w, streams, grp);
-    }
-    TC_STAMP(it, 3);
-    // Every worker publishes its stream entries to the async proxy and arrives; only the issue
-    // warp waits for all 256 arrivals -- the workers go straight to the previous tile's epilogue.
-    asm volatile("fence.proxy.async.shared::cta;");
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&streams_ready)) : "memory");
-    const bool next_chunked = tile + 1 < tile_end && !tile_is_bulk(tile + 1);
-    // rare: the first tile of a later segment reads other threads' stream entries below; a
-    // chunked next tile overwrites `raw`
-    if ((tile == tile_begin && tile != 0) || next_chunked) workers_sync();
-    // ---- predecessor of the segment's first output, in integers (see the single-role kernel) ----
-    if (tile == tile_begin && tile != 0) {
-      long long si = 0, sq = 0;
-      for (int n = tid; n < C::NTAPQ; n += TC_THREADS) {  // tap Dq+p meets stream entry BACK-1-q
-        const int q = n / D, p = n - q * D;
-        const long long h = g.hq[n];
-        si += h * ((int)streams[(2 * p) * C::STREAM + C::BACK - 1 - q] - 128);
-        sq += h * ((int)streams[(2 * p + 1) * C::STREAM + C::BACK - 1 - q] - 128);
-      }
+          for (int k = 0; k < 8; ++k) fi[k] = tc_combine(&v[4 * k], ks);
+          TC_STAMP(tile - w.tile_begin + 1, 6);
+          tc_ld32(trow + TC_N, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;");
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        si += __shfl_xor_sync(0xffffffffu, si, o);
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          for (int k = 0; k < 8; ++k) fq[k] = tc_combine(&v[4 * k], ks);
+        }
+        const int set = t % 3, pset = (set + 2) % 3;
+        last_i[set][half][rowi] = fi[7];
+        last_q[set][half][rowi] = fq[7];
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        TC_STAMP(tile - w.tile_begin + 1, 7);
+        workers_sync();
+        TC_STAMP(tile - w.tile_begin + 1, 8);
+        float pi, pq;
+        if (half == 1) {            // delta 8 follows delta 7 of the same row
+          pi = last_i[set][0][rowi];
+          pq = last_q[set][0][rowi];
+        } else if (rowi > 0) {      // delta 0 follows delta 15 of the previous row
+          pi = last_i[set][1][rowi - 1];
+          pq = last_q[set][1][rowi - 1];
+        } else if (tile > w.tile_begin) {  // ... or the last output of the previous tile
+          pi = last_i[pset][1][TC_ROWS - 1];
+          pq = last_q[pset][1][TC_ROWS - 1];
+        } else if (have_pred) {
+          long long si = 0, sq = 0;
+          for (int k = 0; k < TC_THREADS / 32; ++k) {
+            si += red[0][k];
+            sq += red[1][k];
+          }
+          pi = xmul(__ll2float_rn(si), g.scale);
+          pq = xmul(__ll2float_rn(sq), g.scale);
+        } else {
+          pi = carry_iq[0];
+          pq = carry_iq[1];
+        }
+        const long long jrow = j0 + 16 * rowi + 8 * half;
+        float dm[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          dm[k] = tc_demod(fi[k], fq[k], pi, pq);
+          pi = fi[k];
+          pq = fq[k];
+        }
+        float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
+        if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 3) == 0) {
+          *reinterpret_cast<float4 *>(drow + jrow) = make_float4(dm[0], dm[1], dm[2], dm[3]);
+          *reinterpret_cast<float4 *>(drow + jrow + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (jrow + k < a.n_if) drow[jrow + k] = dm[k];
+        }
+        if (a.i_filt) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (jrow + k < a.n_if) {
+              a.i_filt[(size_t)b * a.tap_stride + jrow + k] = fi[k];
+              a.q_filt[(size_t)b * a.tap_stride + jrow + k] = fq[k];
+            }
+        }
+        {
+          const long long last = (long long)a.n_if - 1 - jrow;
+          if (last >= 0 && last < 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (k == last) {
+                a.prev_out[2 * b] = fi[k];
+                a.prev_out[2 * b + 1] = fq[k];
+              }
+          }
+        }
+        TC_STAMP(tile - w.tile_begin + 1, 9);
+      };
+
+      for (int tile = w.tile_begin; tile < w.tile_end; ++tile, ++gt) {
+        const int it = tile - w.tile_begin;
+        const bool bulk = tile_is_bulk(w, tile);
+        TC_STAMP(it, 0);
+        if (bulk) {                                        // this tile's bytes have landed
+          mbar_wait(&raw_full, raw_phase & 1);
+          ++raw_phase;
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        TC_STAMP(it, 1);
+        // MMAs of the previous tile have read `streams` (the previous ITEM's were drained by its last epilogue)
+        if (it > 0) mbar_wait(&mma_done[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
+        TC_STAMP(it, 2);
+        if (!bulk) workers_sync();                         // chunked staging: everyone's copies are visible
+        // ---- 1. transpose raw -> 2 D phase streams ----
+        for (int grp = tid; grp < C::NGRP; grp += TC_THREADS) {
+          uint32_t wd[C::WIN / 4];
+          const uint4 *src = reinterpret_cast<const uint4 *>(raw + C::WB * grp);
+#pragma unroll
+          for (int k = 0; k < C::WIN / 16; ++k) {
+            const uint4 v = src[k];
+            wd[4 * k] = v.x; wd[4 * k + 1] = v.y; wd[4 * k + 2] = v.z; wd[4 * k + 3] = v.w;
+          }
+          tc_transpose_group<D>(wd, streams, grp);
+        }
+        TC_STAMP(it, 3);
+        // Every worker publishes its stream entries to the async proxy and arrives; only the
+        // issue warp waits for all 256 arrivals -- the workers go on to the previous epilogue.
+        asm volatile("fence.proxy.async.shared::cta;");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&streams_ready)) : "memory");
+        const bool next_chunked = tile + 1 < w.tile_end && !tile_is_bulk(w, tile + 1);
+        // rare: the first tile of a later segment reads other threads' stream entries below; a
+        // chunked next tile overwrites `raw`
+        if ((it == 0 && tile != 0) || next_chunked) workers_sync();
+        // ---- predecessor of the segment's first output, in integers ----
+        if (it == 0 && tile != 0) {
+          long long si = 0, sq = 0;
+          for (int n = tid; n < C::NTAPQ; n += TC_THREADS) {  // tap Dq+p meets stream entry BACK-1-q
+            const int q = n / D, p = n - q * D;
+            const long long h = g.hq[n];
+            si += h * ((int)streams[(2 * p) * C::STREAM + C::BACK - 1 - q] - 128);
+            sq += h * ((int)streams[(2 * p + 1) * C::STREAM + C::BACK - 1 - q] - 128);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            si += __shfl_xor_sync(0xffffffffu, si, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          }
+          if (lane == 0) {
+            red[0][warp] = si;
+            red[1][warp] = sq;
+          }
+          have_pred = true;  // visible to everyone after the epilogue's worker barrier
+        }
+        // ---- 2. a chunked next tile is staged by the workers (after the barrier above) ----
+        if (next_chunked) stage_chunked(w, tile + 1);
+        // ---- 3. epilogue of the previous tile while this tile's MMAs run ----
+        if (it > 0) epilogue(tile - 1, gt - 1);
       }
-      if (lane == 0) {
-        red[0][warp] = si;
-        red[1][warp] = sq;
-      }
-      have_pred = true;  // visible to everyone after the epilogue's first __syncthreads
+      epilogue(w.tile_end - 1, gt - 1);
     }
-    // ---- 3. a chunked next tile is staged by the workers (after the barrier above) ----
-    if (next_chunked) issue_raw(tile + 1);
-    if (it > 0) epilogue(tile - 1, buf ^ 1, (it - 1) >> 1);
-  }
-  {
-    const int it = tile_end - 1 - tile_begin;
-    epilogue(tile_end - 1, it & 1, it >> 1);
-  }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+  tc_trace_on = true;
   TC_STAMP(15, 11);
+#ifdef SDR_TC_TRACE
+  if (lane == 0 && warp == 0) {   // wall-clock end of every CTA (ns) and of the traced CTA's start
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_tc_end[blockIdx.x] = (long long)ns;
+    g_tc_begin[blockIdx.x] = tc_begin_ns;
+  }
+#endif
 }
-
 
 }  // namespace sdr
