@@ -115,7 +115,6 @@ struct sdr_pipeline {
   // tensor-core front end (SDR_VARIANT_FAST)
   DevBuf<int8_t> tc_bmat;
   DevBuf<int32_t> tc_hq;
-  long long tc_corr = 0;
   float tc_scale = 0.0f;
   DevBuf<uint8_t> rf_hist;
   DevBuf<float> prev, prev_new, demod, stf, car, nco, pll_state;
@@ -242,7 +241,6 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     g.a = a;
     g.bmat = p->tc_bmat.p;
     g.hq = p->tc_hq.p;
-    g.corr = p->tc_corr;
     g.scale = p->tc_scale;
     // persistent CTAs (two per SM) take work items (capture, segment) round-robin; segments are
     // sized so that every CTA gets at least ~12 items: the last round is then nearly full
@@ -565,15 +563,12 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     const int K = (16 + Q - 1 + 31) / 32 * 32;           // bytes per A row (TcCfg<D>::K)
     const int BP = TC_N * K;
     tc_h.assign((size_t)D * Q, 0);
-    long long hsum = 0;
-    for (int t = 0; t < cfg->rf_taps; ++t) {
+    for (int t = 0; t < cfg->rf_taps; ++t)
       tc_h[t] = (int32_t)std::llrint(std::ldexp((double)p->h_rf[t], S));  // round half to even
-      hsum += tc_h[t];
-    }
-    p->tc_corr = 128 * hsum;
     p->tc_scale = (float)std::ldexp(1.0, -(S + 7));
     // B tile of phase ph: column 4*delta+d carries digit_d(h[D*q+ph]) at k = delta + (Q-1) - q
-    tc_b.assign((size_t)D * BP, 0);
+    tc_b.assign((size_t)D * BP + TC_CORR_BYTES, 0);
+    long long digit_sum[TC_ND] = {};
     auto put = [&](int ph, int col, int k, int8_t val) {  // canonical no-swizzle K-major order
       const size_t off = (size_t)ph * BP + ((size_t)(k / 16) * (TC_N / 8) + col / 8) * 128 + (col % 8) * 16 + (k % 16);
       tc_b[off] = val;
@@ -584,7 +579,26 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
       for (int d = 0; d < TC_ND; ++d) {
         const int digit = (int)(((v + 128) & 255) - 128);
         v = (v - digit) >> 8;
+        digit_sum[d] += digit;
         for (int delta = 0; delta < 16; ++delta) put(ph, TC_ND * delta + d, delta + (Q - 1) - q, (int8_t)digit);
+      }
+    }
+    // Offset tile (64 columns x 32): multiplied by an A operand of all 128 it starts every
+    // accumulator at -128 * sum_t digit_d(h[t]), i.e. the unsigned samples act as (x - 128).
+    // Column (delta, d) holds -digit_sum[d] spread over its 32 entries.
+    for (int d = 0; d < TC_ND; ++d) {
+      const long long e = -digit_sum[d];
+      if (std::llabs(e) > 32 * 127) {
+        sdr_pipeline_destroy(p);
+        return fail(SDR_ERR_INVALID, "rf taps not representable by the tensor-core front end");
+      }
+      const int q0 = (int)(e / 32), r = (int)(e - 32 * (long long)q0);
+      for (int k = 0; k < 32; ++k) {
+        const int val = q0 + (k < std::abs(r) ? (r > 0 ? 1 : -1) : 0);
+        for (int delta = 0; delta < 16; ++delta) {
+          const int col = TC_ND * delta + d;
+          tc_b[(size_t)D * BP + ((size_t)(k / 16) * (TC_N / 8) + col / 8) * 128 + (col % 8) * 16 + (k % 16)] = (int8_t)val;
+        }
       }
     }
   }

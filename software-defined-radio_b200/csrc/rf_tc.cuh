@@ -43,6 +43,7 @@ constexpr int TC_TILE_OUT = TC_ROWS * 16;    // 2048 outputs per tile
 constexpr int TC_TMAX = 151;                 // longest supported filter
 constexpr int TC_ND = 4;                     // signed base-256 digits per tap (31-bit fixed point)
 constexpr int TC_N = 16 * TC_ND;             // 64 accumulator columns per component
+constexpr int TC_CORR_BYTES = TC_N * 32;      // one 64 x 32 B tile that removes the +128 offset (below)
 constexpr int TC_FRONT = 16;                 // spare stream entries in front of row 0's window
 
 template <int D>
@@ -65,15 +66,15 @@ struct TcCfg {
   static constexpr int BP = TC_N * K;                          // bytes of one phase's B tile
   static constexpr int HIST = (BASE + 1) / 2;                  // raw history pairs the first tile reaches back
   static constexpr int NTAPQ = D * Q;                          // fixed-point tap table length
-  static constexpr size_t SMEM = (size_t)RAW + (size_t)NSTREAM * STREAM + (size_t)D * BP;
+  static constexpr size_t SMEM = (size_t)RAW + (size_t)NSTREAM * STREAM + (size_t)D * BP + TC_CORR_BYTES + 128;
   static_assert(STREAM % GE == 0 && WB % 16 == 0 && BASE % 16 == 0, "tile geometry");
 };
 
 struct RfTcArgs {
   RfArgs a;
-  const int8_t *bmat;   // [D phases][64 x K] in canonical no-swizzle K-major core-matrix order
+  const int8_t *bmat;   // [D phases][64 x K] in canonical no-swizzle K-major core-matrix order, then
+                        // the 64 x 32 offset tile
   const int32_t *hq;    // fixed-point taps, D*Q entries (zero padded)
-  long long corr;       // 128 * sum(hq): offset of the unsigned samples
   float scale;          // 2^-(S+7)
   int tiles_per_seg;    // work item = tiles_per_seg consecutive tiles of one capture
   int segs, batch;      // items = segs * batch
@@ -118,34 +119,29 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 
-// Recombine the four base-256 digit sums into the fixed-point FIR output and round once.
-// v = d0 + 2^8 d1 + 2^16 d2 + 2^24 d3 - corr is an integer below 2^47.  It is cut into
-// H = v >> 23 (|H| < 2^24) and L = v & (2^23-1): both are exactly representable floats, so
-// fma(H, 2^23 * sc, L * sc) performs the ONLY rounding, and it is the round-to-nearest of v * sc
-// (sc is a power of two).  No 64-bit conversion and no FP64 pipe (profiles/r1d, r1f: I2F.S64 was
-// the most stalled instruction of the first version; a double-precision form throttled the
-// FP64 pipe).
+// Recombine the four base-256 digit sums (already centred: the offset tile subtracted
+// 128 * sum(digit) inside the tensor core, so each |d_k| < 2^22) into the fixed-point FIR output
+// v = d0 + 2^8 d1 + 2^16 d2 + 2^24 d3 and scale it.  lo = d0 + 2^8 d1 and hi = d2 + 2^8 d3 are
+// exact 31-bit integers; each is rounded to float once and fma(hi, 2^16 sc, lo sc) rounds a
+// third time: at most one ulp from the exactly rounded v * sc, and exactly 0 for v = 0
+// (profiles/r1h: the exactly rounded form was a quarter of the kernel's instructions).
 struct TcScale {
-  long long corr;
   float sc;     // 2^-(S+7)
-  float sc23;   // 2^23 * sc
+  float sc16;   // 2^16 * sc
 };
 __device__ __forceinline__ float tc_combine(const uint32_t *d, const TcScale &k) {
   const int lo = (int32_t)d[0] + 256 * (int32_t)d[1];
   const int hi = (int32_t)d[2] + 256 * (int32_t)d[3];
-  const long long v = (long long)hi * 65536 + lo - k.corr;
-  const int H = (int)(v >> 23);
-  const uint32_t L = (uint32_t)v & 0x7fffffu;
-  // float(L) without a convert: L sits in the mantissa of 2^23
-  const float Lf = __fsub_rn(__uint_as_float(0x4B000000u | L), 8388608.0f);
-  return __fmaf_rn(__int2float_rn(H), k.sc23, __fmul_rn(Lf, k.sc));
+  return __fmaf_rn(__int2float_rn(hi), k.sc16, __fmul_rn(__int2float_rn(lo), k.sc));
 }
 // fmDemod on the fast path: same formula, approximate reciprocal (the fast variant is held to
 // 100 dB / +-1 LSB against the reference, not to bit equality; I/Q already differ by ~1e-7).
 __device__ __forceinline__ float tc_demod(float i, float q, float pi, float pq) {
   const float den = __fmaf_rn(i, i, __fmul_rn(q, q));
   const float num = __fmaf_rn(i, __fsub_rn(q, pq), -__fmul_rn(q, __fsub_rn(i, pi)));
-  return den == 0.0f ? 0.0f : __fdividef(num, den);
+  float r;   // I, Q are multiples of 2^-(S+7): den is 0 or far above the subnormal range
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  return den == 0.0f ? 0.0f : __fmul_rn(num, r);
 }
 
 // One transposer group: GE consecutive entries of all 2*D streams from D*GE input pairs that sit
@@ -192,12 +188,14 @@ k_rf_demod_tc(const RfTcArgs g) {
   uint8_t *raw = tc_smem;                                   // [C::RAW] staged input bytes
   uint8_t *streams = tc_smem + C::RAW;                      // [2D][C::STREAM]
   int8_t *bs = reinterpret_cast<int8_t *>(tc_smem + C::RAW + C::NSTREAM * C::STREAM);
+  int8_t *corr_b = bs + D * C::BP;                          // [64 x 32] offset tile (B operand)
+  uint8_t *corr_a = reinterpret_cast<uint8_t *>(corr_b) + TC_CORR_BYTES;   // one core matrix of 128s (A operand)
   // I,Q of delta 7 / 15 of every row, [tile % 3][half][row]: a set is rewritten three tiles later,
   // i.e. after two more worker barriers, so readers of tile t and t+1 are always done with it
   __shared__ float last_i[3][2][TC_ROWS], last_q[3][2][TC_ROWS];
-  __shared__ float carry_iq[2];
-  __shared__ long long red[2][TC_THREADS / 32];
-  __shared__ __align__(8) uint64_t mma_done[2], raw_full, streams_ready, item_ready;
+  __shared__ float carry_iq[2][2];                      // [round parity][I,Q]
+  __shared__ int red[2][2][TC_ND][TC_THREADS / 32];     // [round parity][I,Q][digit][warp]
+  __shared__ __align__(8) uint64_t mma_done[2], raw_full, streams_ready, item_full, item_empty;
   __shared__ int item_slot[2];   // item of the CTA's k-th round at [k & 1], -1 = no more work
   __shared__ uint32_t tmem_slot;
 
@@ -220,14 +218,16 @@ k_rf_demod_tc(const RfTcArgs g) {
   auto workers_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); };
 
   // ---- once per (persistent) CTA: tap digits, barriers, tensor memory ----
-  for (int i = tid; i < D * C::BP / 16; i += TC_BLOCK)
+  for (int i = tid; i < (D * C::BP + TC_CORR_BYTES) / 16; i += TC_BLOCK)
     reinterpret_cast<uint4 *>(bs)[i] = __ldg(reinterpret_cast<const uint4 *>(g.bmat) + i);
+  if (tid < 32) reinterpret_cast<uint32_t *>(corr_a)[tid] = 0x80808080u;
   if (tid == 0) {
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
     mbar_init(&raw_full, 1);
     mbar_init(&streams_ready, TC_THREADS);
-    mbar_init(&item_ready, 1);
+    mbar_init(&item_full, 1);
+    mbar_init(&item_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
@@ -241,7 +241,7 @@ k_rf_demod_tc(const RfTcArgs g) {
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                          ((uint32_t)(TC_ROWS >> 4) << 24);
-  const TcScale ks{g.corr, g.scale, g.scale * 8388608.0f};
+  const TcScale ks{g.scale, g.scale * 65536.0f};
 
   // Geometry of a work item.  A tile that lies entirely inside the capture is staged by ONE bulk
   // asynchronous copy (TMA, completes on raw_full); tiles that touch the history in front of the
@@ -304,35 +304,61 @@ k_rf_demod_tc(const RfTcArgs g) {
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
+  // Work items.  Round r of a CTA processes item(r): item(0) = blockIdx.x, item(r + 1) is taken
+  // from the device counter by worker 0 at the START of round r (dynamic balance: CTA run times
+  // differ by +-12 %, tools/tc_trace.py) and published in item_slot[(r + 1) & 1]: phase r of
+  // item_full.  The issue warp acknowledges on item_empty so that phases never alias.
+  // Tiles of consecutive items are pipelined like tiles of one item: the first tile of
+  // item(r + 1) is staged and transposed before the last epilogue of item(r).
   if (issuer) {
     // ---- issue warp.  Per tile: wait until all workers have written its streams (which also
     // means `raw` is free), start the bulk copy of the NEXT tile -- it goes first because issuing
     // the MMAs blocks for most of their run time (tools/tc_trace.py) -- then the MMAs. ----
     if (lane == 0) {
       uint32_t gt = 0;  // tiles issued so far by this CTA
+      Item w = get_item(blockIdx.x);
       for (uint32_t round = 0;; ++round) {
-        mbar_wait(&item_ready, round & 1);     // worker 0 has published this round's item
-        const int item = item_slot[round & 1];
-        if (item < 0) break;
-        const Item w = get_item(item);
         tc_trace_on = round == 2;
+        int next_item = -1;
+        Item nw = w;
         for (int tile = w.tile_begin; tile < w.tile_end; ++tile, ++gt) {
           const uint32_t buf = gt & 1;
           mbar_wait(&streams_ready, gt & 1);
           asm volatile("tcgen05.fence::after_thread_sync;");
           TC_STAMP(tile - w.tile_begin, 10);
-          if (tile + 1 < w.tile_end && tile_is_bulk(w, tile + 1)) issue_bulk(w, tile + 1);
+          if (tile + 1 < w.tile_end) {
+            if (tile_is_bulk(w, tile + 1)) issue_bulk(w, tile + 1);
+          } else {
+            mbar_wait(&item_full, round & 1);
+            next_item = item_slot[(round + 1) & 1];
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&item_empty)) : "memory");
+            if (next_item >= 0) {
+              nw = get_item(next_item);
+              if (tile_is_bulk(nw, nw.tile_begin)) issue_bulk(nw, nw.tile_begin);
+            }
+          }
           const uint32_t s0 = tc_smem_u32(streams) + TC_FRONT, b0 = tc_smem_u32(bs);
           const uint32_t d0 = tmem + buf * 2 * TC_N;
 #pragma unroll
           for (int comp = 0; comp < 2; ++comp) {
+            {
+              // offset tile first (overwrites the accumulators): every A row is the same 32 bytes
+              // of 128 (both strides 0), column (delta, d) of B sums to -sum_t digit_d(h[t]), so the
+              // accumulators start at -128 * sum_t digit_d(h[t]) and end as sums over (x - 128)
+              const uint64_t da = tc_desc(tc_smem_u32(corr_a), 0, 0);
+              const uint64_t db = tc_desc(tc_smem_u32(corr_b), (TC_N / 8) * 128, 128);
+              asm volatile(
+                  "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d0 + comp * TC_N),
+                  "l"(da), "l"(db), "r"(idesc), "r"(0u));
+            }
 #pragma unroll
             for (int p = 0; p < D; ++p) {
 #pragma unroll
               for (int ksx = 0; ksx < C::KSTEPS; ++ksx) {
                 const uint64_t da = tc_desc(s0 + (2 * p + comp) * C::STREAM + 32 * ksx, 16, 128);
                 const uint64_t db = tc_desc(b0 + p * C::BP + ksx * 2 * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
-                const uint32_t acc = (p | ksx) != 0;
+                const uint32_t acc = 1u;
                 asm volatile(
                     "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d0 + comp * TC_N),
@@ -343,188 +369,223 @@ k_rf_demod_tc(const RfTcArgs g) {
           tc_commit(&mma_done[buf]);
           TC_STAMP(tile - w.tile_begin, 11);
         }
+        if (next_item < 0) break;
+        w = nw;
       }
     }
     __syncwarp();
   } else {
     // ---- workers: transpose tile t, then the epilogue of tile t-1 while the MMAs of t run ----
-    uint32_t gt = 0;         // tiles transposed so far by this CTA (same count as the issue warp's)
-    uint32_t raw_phase = 0;  // completions of raw_full consumed so far
-    int item = blockIdx.x;   // first item; later ones come from the device counter (dynamic balance:
-                             // CTA run times differ by +-12 %, tools/tc_trace.py)
-    for (uint32_t round = 0;; ++round) {
-      workers_sync();        // the previous item's readers of carry_iq / red / raw / item_slot are done
-      if (tid == 0) {
-        if (round > 0) item = (int)gridDim.x + atomicAdd(g.next_item, 1);
-        if (item >= n_items) item = -1;
-        item_slot[round & 1] = item;
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&item_ready)) : "memory");
+    // Epilogue of tile `tile` of capture b (segment starting at tile_begin; global tile number t:
+    // accumulator set t & 1, its (t >> 1)-th use; rp = parity of the item's round).
+    auto epilogue = [&](int b, int tile_begin, int tile, uint32_t t, uint32_t rp) {
+      const long long j0 = (long long)tile * TC_TILE_OUT;
+      const uint32_t buf = t & 1;
+      TC_STAMP(tile - tile_begin + 1, 4);
+      mbar_wait(&mma_done[buf], (t >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      TC_STAMP(tile - tile_begin + 1, 5);
+      float fi[8], fq[8];
+      const uint32_t trow = tmem + buf * 2 * TC_N + 32 * half + ((uint32_t)((warp & 3) * 32) << 16);
+      {
+        uint32_t v[32];
+        tc_ld32(trow, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fi[k] = tc_combine(&v[4 * k], ks);
+        TC_STAMP(tile - tile_begin + 1, 6);
+        tc_ld32(trow + TC_N, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;");
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fq[k] = tc_combine(&v[4 * k], ks);
       }
+      const int set = t % 3, pset = (set + 2) % 3;
+      last_i[set][half][rowi] = fi[7];
+      last_q[set][half][rowi] = fq[7];
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      TC_STAMP(tile - tile_begin + 1, 7);
       workers_sync();
-      item = item_slot[round & 1];
-      if (item < 0) break;
-      const Item w = get_item(item);
-      tc_trace_on = true;
-      TC_STAMP(15, round < 10 ? round : 9);
-      tc_trace_on = round == 2;
-      const int b = w.b;
-      bool have_pred = false;  // predecessor of the segment's first output comes from `red`
-      if (w.tile_begin == 0 && tid < 2) carry_iq[tid] = a.prev_in[2 * b + tid];
-      if (!tile_is_bulk(w, w.tile_begin)) stage_chunked(w, w.tile_begin);
-      else if (tid == 0) issue_bulk(w, w.tile_begin);   // `raw` is free: the previous item is drained
-
-      // Epilogue of tile `tile` (global tile number t: accumulator set t & 1, its (t >> 1)-th use).
-      auto epilogue = [&](int tile, uint32_t t) {
-        const long long j0 = (long long)tile * TC_TILE_OUT;
-        const uint32_t buf = t & 1;
-        TC_STAMP(tile - w.tile_begin + 1, 4);
-        mbar_wait(&mma_done[buf], (t >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        TC_STAMP(tile - w.tile_begin + 1, 5);
-        float fi[8], fq[8];
-        const uint32_t trow = tmem + buf * 2 * TC_N + 32 * half + ((uint32_t)((warp & 3) * 32) << 16);
-        {
-          uint32_t v[32];
-          tc_ld32(trow, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;");
+      TC_STAMP(tile - tile_begin + 1, 8);
+      float pi, pq;
+      if (half == 1) {            // delta 8 follows delta 7 of the same row
+        pi = last_i[set][0][rowi];
+        pq = last_q[set][0][rowi];
+      } else if (rowi > 0) {      // delta 0 follows delta 15 of the previous row
+        pi = last_i[set][1][rowi - 1];
+        pq = last_q[set][1][rowi - 1];
+      } else if (tile > tile_begin) {  // ... or the last output of the segment's previous tile
+        pi = last_i[pset][1][TC_ROWS - 1];
+        pq = last_q[pset][1][TC_ROWS - 1];
+      } else if (tile != 0) {     // first output of a later segment: recomputed in integers
+        uint32_t di[TC_ND], dq[TC_ND];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) fi[k] = tc_combine(&v[4 * k], ks);
-          TC_STAMP(tile - w.tile_begin + 1, 6);
-          tc_ld32(trow + TC_N, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;");
-#pragma unroll
-          for (int k = 0; k < 8; ++k) fq[k] = tc_combine(&v[4 * k], ks);
-        }
-        const int set = t % 3, pset = (set + 2) % 3;
-        last_i[set][half][rowi] = fi[7];
-        last_q[set][half][rowi] = fq[7];
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        TC_STAMP(tile - w.tile_begin + 1, 7);
-        workers_sync();
-        TC_STAMP(tile - w.tile_begin + 1, 8);
-        float pi, pq;
-        if (half == 1) {            // delta 8 follows delta 7 of the same row
-          pi = last_i[set][0][rowi];
-          pq = last_q[set][0][rowi];
-        } else if (rowi > 0) {      // delta 0 follows delta 15 of the previous row
-          pi = last_i[set][1][rowi - 1];
-          pq = last_q[set][1][rowi - 1];
-        } else if (tile > w.tile_begin) {  // ... or the last output of the previous tile
-          pi = last_i[pset][1][TC_ROWS - 1];
-          pq = last_q[pset][1][TC_ROWS - 1];
-        } else if (have_pred) {
-          long long si = 0, sq = 0;
+        for (int d = 0; d < TC_ND; ++d) {
+          int si = 0, sq = 0;
           for (int k = 0; k < TC_THREADS / 32; ++k) {
-            si += red[0][k];
-            sq += red[1][k];
+            si += red[rp][0][d][k];
+            sq += red[rp][1][d][k];
           }
-          pi = xmul(__ll2float_rn(si), g.scale);
-          pq = xmul(__ll2float_rn(sq), g.scale);
-        } else {
-          pi = carry_iq[0];
-          pq = carry_iq[1];
+          di[d] = (uint32_t)si;
+          dq[d] = (uint32_t)sq;
         }
-        const long long jrow = j0 + 16 * rowi + 8 * half;
-        float dm[8];
+        pi = tc_combine(di, ks);   // the same function of the same digit sums as the tile that owns it
+        pq = tc_combine(dq, ks);
+      } else {                    // first output of the call: the carried state
+        pi = carry_iq[rp][0];
+        pq = carry_iq[rp][1];
+      }
+      const long long jrow = j0 + 16 * rowi + 8 * half;
+      float dm[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          dm[k] = tc_demod(fi[k], fq[k], pi, pq);
-          pi = fi[k];
-          pq = fq[k];
-        }
-        float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
-        if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 3) == 0) {
-          *reinterpret_cast<float4 *>(drow + jrow) = make_float4(dm[0], dm[1], dm[2], dm[3]);
-          *reinterpret_cast<float4 *>(drow + jrow + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
-        } else {
+      for (int k = 0; k < 8; ++k) {
+        dm[k] = tc_demod(fi[k], fq[k], pi, pq);
+        pi = fi[k];
+        pq = fq[k];
+      }
+      float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
+      if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 3) == 0) {
+        *reinterpret_cast<float4 *>(drow + jrow) = make_float4(dm[0], dm[1], dm[2], dm[3]);
+        *reinterpret_cast<float4 *>(drow + jrow + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (jrow + k < a.n_if) drow[jrow + k] = dm[k];
+      }
+      if (a.i_filt) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (jrow + k < a.n_if) {
+            a.i_filt[(size_t)b * a.tap_stride + jrow + k] = fi[k];
+            a.q_filt[(size_t)b * a.tap_stride + jrow + k] = fq[k];
+          }
+      }
+      {
+        const long long last = (long long)a.n_if - 1 - jrow;
+        if (last >= 0 && last < 8) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            if (jrow + k < a.n_if) drow[jrow + k] = dm[k];
-        }
-        if (a.i_filt) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (jrow + k < a.n_if) {
-              a.i_filt[(size_t)b * a.tap_stride + jrow + k] = fi[k];
-              a.q_filt[(size_t)b * a.tap_stride + jrow + k] = fq[k];
+            if (k == last) {
+              a.prev_out[2 * b] = fi[k];
+              a.prev_out[2 * b + 1] = fq[k];
             }
         }
-        {
-          const long long last = (long long)a.n_if - 1 - jrow;
-          if (last >= 0 && last < 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (k == last) {
-                a.prev_out[2 * b] = fi[k];
-                a.prev_out[2 * b + 1] = fq[k];
-              }
-          }
-        }
-        TC_STAMP(tile - w.tile_begin + 1, 9);
-      };
+      }
+      TC_STAMP(tile - tile_begin + 1, 9);
+    };
 
-      for (int tile = w.tile_begin; tile < w.tile_end; ++tile, ++gt) {
-        const int it = tile - w.tile_begin;
-        const bool bulk = tile_is_bulk(w, tile);
-        TC_STAMP(it, 0);
-        if (bulk) {                                        // this tile's bytes have landed
-          mbar_wait(&raw_full, raw_phase & 1);
-          ++raw_phase;
-        } else {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
+    uint32_t gt = 0;         // tiles transposed so far by this CTA (same count as the issue warp's)
+    uint32_t raw_phase = 0;  // completions of raw_full consumed so far
+    uint32_t round = 0;
+    Item w = get_item(blockIdx.x);
+    int tile = w.tile_begin;
+    int p_b = 0, p_begin = 0, p_tile = -1;   // previous tile (p_tile < 0: none yet)
+    uint32_t p_rp = 0;
+    if (!tile_is_bulk(w, tile)) stage_chunked(w, tile);
+    else if (tid == 0) issue_bulk(w, tile);
+    for (;;) {
+      const int it = tile - w.tile_begin;
+      if (it == 0) {   // start of a round
+        tc_trace_on = true;
+        TC_STAMP(15, round < 10 ? round : 9);
+        tc_trace_on = round == 2;
+        if (tid == 0) {
+          if (round > 0) mbar_wait(&item_empty, (round - 1) & 1);   // the issue warp has read item(round)
+          int nxt = (int)gridDim.x + atomicAdd(g.next_item, 1);
+          if (nxt >= n_items) nxt = -1;
+          item_slot[(round + 1) & 1] = nxt;
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&item_full)) : "memory");
         }
-        TC_STAMP(it, 1);
-        // MMAs of the previous tile have read `streams` (the previous ITEM's were drained by its last epilogue)
-        if (it > 0) mbar_wait(&mma_done[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
-        TC_STAMP(it, 2);
-        if (!bulk) workers_sync();                         // chunked staging: everyone's copies are visible
-        // ---- 1. transpose raw -> 2 D phase streams ----
-        for (int grp = tid; grp < C::NGRP; grp += TC_THREADS) {
-          uint32_t wd[C::WIN / 4];
-          const uint4 *src = reinterpret_cast<const uint4 *>(raw + C::WB * grp);
+        if (w.tile_begin == 0 && tid < 2) carry_iq[round & 1][tid] = a.prev_in[2 * w.b + tid];
+      }
+      const bool bulk = tile_is_bulk(w, tile);
+      TC_STAMP(it, 0);
+      if (bulk) {                                        // this tile's bytes have landed
+        mbar_wait(&raw_full, raw_phase & 1);
+        ++raw_phase;
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      TC_STAMP(it, 1);
+      if (gt > 0) mbar_wait(&mma_done[(gt - 1) & 1], ((gt - 1) >> 1) & 1);   // MMAs of the previous tile have read `streams`
+      TC_STAMP(it, 2);
+      if (!bulk) workers_sync();                         // chunked staging: everyone's copies are visible
+      // ---- 1. transpose raw -> 2 D phase streams ----
+      for (int grp = tid; grp < C::NGRP; grp += TC_THREADS) {
+        uint32_t wd[C::WIN / 4];
+        const uint4 *src = reinterpret_cast<const uint4 *>(raw + C::WB * grp);
 #pragma unroll
-          for (int k = 0; k < C::WIN / 16; ++k) {
-            const uint4 v = src[k];
-            wd[4 * k] = v.x; wd[4 * k + 1] = v.y; wd[4 * k + 2] = v.z; wd[4 * k + 3] = v.w;
-          }
-          tc_transpose_group<D>(wd, streams, grp);
+        for (int k = 0; k < C::WIN / 16; ++k) {
+          const uint4 v = src[k];
+          wd[4 * k] = v.x; wd[4 * k + 1] = v.y; wd[4 * k + 2] = v.z; wd[4 * k + 3] = v.w;
         }
-        TC_STAMP(it, 3);
-        // Every worker publishes its stream entries to the async proxy and arrives; only the
-        // issue warp waits for all 256 arrivals -- the workers go on to the previous epilogue.
-        asm volatile("fence.proxy.async.shared::cta;");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&streams_ready)) : "memory");
-        const bool next_chunked = tile + 1 < w.tile_end && !tile_is_bulk(w, tile + 1);
-        // rare: the first tile of a later segment reads other threads' stream entries below; a
-        // chunked next tile overwrites `raw`
-        if ((it == 0 && tile != 0) || next_chunked) workers_sync();
-        // ---- predecessor of the segment's first output, in integers ----
-        if (it == 0 && tile != 0) {
-          long long si = 0, sq = 0;
-          for (int n = tid; n < C::NTAPQ; n += TC_THREADS) {  // tap Dq+p meets stream entry BACK-1-q
-            const int q = n / D, p = n - q * D;
-            const long long h = g.hq[n];
-            si += h * ((int)streams[(2 * p) * C::STREAM + C::BACK - 1 - q] - 128);
-            sq += h * ((int)streams[(2 * p + 1) * C::STREAM + C::BACK - 1 - q] - 128);
+        tc_transpose_group<D>(wd, streams, grp);
+      }
+      TC_STAMP(it, 3);
+      // Every worker publishes its stream entries to the async proxy and arrives; only the
+      // issue warp waits for all 256 arrivals -- the workers go on to the previous epilogue.
+      asm volatile("fence.proxy.async.shared::cta;");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&streams_ready)) : "memory");
+      // ---- 2. which tile comes next (possibly the first tile of the next item) ----
+      Item nw = w;
+      int ntile = tile + 1;
+      bool have_next = true;
+      if (ntile == w.tile_end) {
+        mbar_wait(&item_full, round & 1);
+        const int nxt = item_slot[(round + 1) & 1];
+        have_next = nxt >= 0;
+        if (have_next) {
+          nw = get_item(nxt);
+          ntile = nw.tile_begin;
+        }
+      }
+      const bool next_chunked = have_next && !tile_is_bulk(nw, ntile);
+      const bool need_red = it == 0 && tile != 0;
+      // rare: the first tile of a later segment reads other threads' stream entries below; a
+      // chunked next tile overwrites `raw`
+      if (need_red || next_chunked) workers_sync();
+      if (need_red) {   // predecessor of the segment's first output: its centred digit sums, in integers
+        int si[TC_ND] = {}, sq[TC_ND] = {};
+        for (int n = tid; n < C::NTAPQ; n += TC_THREADS) {  // tap Dq+p meets stream entry BACK-1-q
+          const int q = n / D, p = n - q * D;
+          const int xi = (int)streams[(2 * p) * C::STREAM + C::BACK - 1 - q] - 128;
+          const int xq = (int)streams[(2 * p + 1) * C::STREAM + C::BACK - 1 - q] - 128;
+          int v = g.hq[n];
+#pragma unroll
+          for (int d = 0; d < TC_ND; ++d) {
+            const int digit = ((v + 128) & 255) - 128;   // balanced base-256 digit, as in the B tiles
+            v = (v - digit) >> 8;
+            si[d] += digit * xi;
+            sq[d] += digit * xq;
           }
+        }
+#pragma unroll
+        for (int d = 0; d < TC_ND; ++d) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
-            si += __shfl_xor_sync(0xffffffffu, si, o);
-            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            si[d] += __shfl_xor_sync(0xffffffffu, si[d], o);
+            sq[d] += __shfl_xor_sync(0xffffffffu, sq[d], o);
           }
-          if (lane == 0) {
-            red[0][warp] = si;
-            red[1][warp] = sq;
+          if (lane == 0) {   // read after the worker barrier of this tile's epilogue
+            red[round & 1][0][d][warp] = si[d];
+            red[round & 1][1][d][warp] = sq[d];
           }
-          have_pred = true;  // visible to everyone after the epilogue's worker barrier
         }
-        // ---- 2. a chunked next tile is staged by the workers (after the barrier above) ----
-        if (next_chunked) stage_chunked(w, tile + 1);
-        // ---- 3. epilogue of the previous tile while this tile's MMAs run ----
-        if (it > 0) epilogue(tile - 1, gt - 1);
       }
-      epilogue(w.tile_end - 1, gt - 1);
+      if (next_chunked) stage_chunked(nw, ntile);   // a bulk next tile is issued by the issue warp
+      // ---- 3. epilogue of the previous tile while this tile's MMAs run ----
+      if (p_tile >= 0) epilogue(p_b, p_begin, p_tile, gt - 1, p_rp);
+      else workers_sync();   // every iteration has one barrier after the item_full read above
+      p_b = w.b;
+      p_begin = w.tile_begin;
+      p_tile = tile;
+      p_rp = round & 1;
+      ++gt;
+      if (!have_next) break;
+      if (ntile == nw.tile_begin && tile + 1 == w.tile_end) ++round;
+      w = nw;
+      tile = ntile;
     }
+    epilogue(p_b, p_begin, p_tile, gt - 1, p_rp);
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
