@@ -52,7 +52,8 @@ constexpr int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) 
 // Offset (in floats) of sample `e` relative to the first sample of a thread's own group.
 constexpr int fir_off(int e, int G) { return e + fir_pad(G) * floordiv(e, G); }
 
-template <int T, int D, int R, int HALO>
+// FMA = true contracts each multiply-add (SDR_VARIANT_FAST only: no longer bit-identical).
+template <int T, int D, int R, int HALO, bool FMA = false>
 __device__ __forceinline__ void fir_window(const float *__restrict__ w,
                                            const TapArray<taps_window(T)> &taps, float (&acc)[R]) {
   // `w` points at the sample of the thread's FIRST output (e = 0).
@@ -72,7 +73,7 @@ __device__ __forceinline__ void fir_window(const float *__restrict__ w,
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int n = r * D - e;
-        if (n >= 0 && n < T) acc[r] = xmac(acc[r], taps.h[n], xv);
+        if (n >= 0 && n < T) acc[r] = FMA ? __fmaf_rn(taps.h[n], xv, acc[r]) : xmac(acc[r], taps.h[n], xv);
       }
     }
   }
@@ -498,7 +499,7 @@ struct AudioCfg {
   static constexpr int ROW = round_up(Geom::FLOATS, 4);
 };
 
-template <int T, int D, int R, int NT, bool STEREO>
+template <int T, int D, int R, int NT, bool STEREO, bool FMA = false>
 __global__ void __launch_bounds__(NT)
 k_audio_fir(const AudioArgs a, const __grid_constant__ TapArray<taps_window(T)> taps) {
   using Cfg = AudioCfg<T, D, R, NT>;
@@ -530,8 +531,8 @@ k_audio_fir(const AudioArgs a, const __grid_constant__ TapArray<taps_window(T)> 
     float am[R], as[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) am[r] = as[r] = 0.0f;
-    fir_window<T, D, R, HALO>(xm + Geom::thread_base(t), taps, am);
-    if (STEREO) fir_window<T, D, R, HALO>(xs + Geom::thread_base(t), taps, as);
+    fir_window<T, D, R, HALO, FMA>(xm + Geom::thread_base(t), taps, am);
+    if (STEREO) fir_window<T, D, R, HALO, FMA>(xs + Geom::thread_base(t), taps, as);
     const int o = o0 + t * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {

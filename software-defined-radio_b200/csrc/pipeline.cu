@@ -314,11 +314,10 @@ static int launch_audio(sdr_pipeline *p, AudioArgs a, cudaStream_t s) {
   constexpr int NT = 128;
   using Cfg = AudioCfg<T, D, R, NT>;
   constexpr size_t SMEM = (size_t)Cfg::ROW * (STEREO ? 2 : 1) * sizeof(float);
-  auto kern = k_audio_fir<T, D, R, NT, STEREO>;
-  static std::once_flag once[16];
-  std::call_once(once[p->cfg.device & 15], [&] {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-  });
+  // the fast variant (mono only) contracts the multiply-adds
+  const bool fma = !STEREO && p->cfg.variant == SDR_VARIANT_FAST;
+  auto kern = fma ? k_audio_fir<T, D, R, NT, STEREO, !STEREO> : k_audio_fir<T, D, R, NT, STEREO, false>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
   int segs = pick_segments(a.n_out, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
   prof_begin(p, "k_audio_fir", s);
@@ -489,7 +488,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   if (cfg->variant == SDR_VARIANT_FAST)
     p->HR = std::max(p->HR, m.rf_decim == 10 ? TcCfg<10>::HIST : m.rf_decim == 5 ? TcCfg<5>::HIST : TcCfg<3>::HIST);
   p->HA = round_up(p->TA - 1, 4);
-  p->HD = round_up(std::max(p->stereo ? cfg->stereo_taps - 1 : 0, p->TA - 1 + p->delay), 4);
+  p->HD = round_up(std::max(p->stereo ? cfg->stereo_taps - 1 : 0, p->TA - 1 + p->delay), 8);  // 32-byte aligned sample 0
   sdr_mode_info mi;
   sdr_mode_lookup(cfg->mode, cfg->channels, &mi);
   p->granule_bytes = mi.granule_bytes;
@@ -562,25 +561,27 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     const int Q = (TC_TMAX + D - 1) / D;                 // taps per phase (TcCfg<D>::Q)
     const int K = (16 + Q - 1 + 31) / 32 * 32;           // bytes per A row (TcCfg<D>::K)
     const int BP = TC_N * K;
+    const int SHIFT = D == 10 ? 1 : D == 5 ? 2 : 0;       // TcCfg<D>::SHIFT: tap t sits at n = t + SHIFT = D q + ph
+    const int BACK = D == 10 ? 32 : TC_FRONT + Q - 1;     // TcCfg<D>::BACK
     tc_h.assign((size_t)D * Q, 0);
     for (int t = 0; t < cfg->rf_taps; ++t)
-      tc_h[t] = (int32_t)std::llrint(std::ldexp((double)p->h_rf[t], S));  // round half to even
+      tc_h[t + SHIFT] = (int32_t)std::llrint(std::ldexp((double)p->h_rf[t], S));  // round half to even
     p->tc_scale = (float)std::ldexp(1.0, -(S + 7));
-    // B tile of phase ph: column 4*delta+d carries digit_d(h[D*q+ph]) at k = delta + (Q-1) - q
+    // B tile of phase ph: column 4*delta+d carries digit_d(tap n = D*q+ph) at k = delta + (BACK-FRONT) - q
     tc_b.assign((size_t)D * BP + TC_CORR_BYTES, 0);
     long long digit_sum[TC_ND] = {};
     auto put = [&](int ph, int col, int k, int8_t val) {  // canonical no-swizzle K-major order
       const size_t off = (size_t)ph * BP + ((size_t)(k / 16) * (TC_N / 8) + col / 8) * 128 + (col % 8) * 16 + (k % 16);
       tc_b[off] = val;
     };
-    for (int t = 0; t < cfg->rf_taps; ++t) {
-      const int q = t / D, ph = t % D;
-      long long v = tc_h[t];
+    for (int n = 0; n < D * Q; ++n) {
+      const int q = n / D, ph = n % D;
+      long long v = tc_h[n];
       for (int d = 0; d < TC_ND; ++d) {
         const int digit = (int)(((v + 128) & 255) - 128);
         v = (v - digit) >> 8;
         digit_sum[d] += digit;
-        for (int delta = 0; delta < 16; ++delta) put(ph, TC_ND * delta + d, delta + (Q - 1) - q, (int8_t)digit);
+        for (int delta = 0; delta < 16; ++delta) put(ph, TC_ND * delta + d, delta + (BACK - TC_FRONT) - q, (int8_t)digit);
       }
     }
     // Offset tile (64 columns x 32): multiplied by an A operand of all 128 it starts every
@@ -603,7 +604,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     }
   }
   const size_t B = (size_t)cfg->batch;
-  p->demod_stride = round_up((int)(p->HD + p->cap_if + 8), 4);
+  p->demod_stride = round_up((int)(p->HD + p->cap_if + 8), 8);
   p->stf_stride = round_up((int)(p->HA + p->cap_if + 8), 4);
   p->nco_stride = p->stf_stride;
   p->car_stride = round_up((int)p->cap_if + 4, 4);

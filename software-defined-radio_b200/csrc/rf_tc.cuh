@@ -51,13 +51,19 @@ struct TcCfg {
   static constexpr int Q = (TC_TMAX + D - 1) / D;              // taps per phase: 16 / 31 / 51
   static constexpr int K = (16 + Q - 1 + 31) / 32 * 32;        // bytes per A row: 32 / 64 / 96
   static constexpr int KSTEPS = K / 32;
-  static constexpr int BACK = TC_FRONT + Q - 1;                // stream entry s' holds xp[p][j0 - BACK + s']
+  // Two free choices make every transposer group's input window start on a 16-byte boundary
+  // (one LDS.128 less per group): the phase split is shifted by SHIFT taps (stream p holds
+  // x[D i - p + SHIFT], so tap t sits at n = t + SHIFT = D q + p), and stream entry s' holds
+  // xp[p][j0 - BACK + s'] with any BACK in [FRONT + Q - 1, FRONT + K - 16].
+  static constexpr int SHIFT = D == 10 ? 1 : D == 5 ? 2 : 0;
+  static constexpr int BACK = D == 10 ? 32 : TC_FRONT + Q - 1;
+  static_assert(BACK >= TC_FRONT + Q - 1 && BACK <= TC_FRONT + K - 16 && TC_TMAX - 1 + SHIFT <= D * Q - 1, "stream geometry");
   static constexpr int STREAM = TC_FRONT + 16 * (TC_ROWS - 1) + K;
   static constexpr int NSTREAM = 2 * D;
   static constexpr int GE = (D % 2 == 0) ? 4 : 8;              // stream entries built per transposer group
   static constexpr int NGRP = STREAM / GE;
   static constexpr int WB = 2 * D * GE;                        // input bytes consumed per group
-  static constexpr int CONST0 = 2 * D * BACK + 2 * (D - 1);    // 2*c_lo of group 0 = 2*D*j0 - CONST0
+  static constexpr int CONST0 = 2 * D * BACK + 2 * (D - 1) - 2 * SHIFT;    // 2*c_lo of group 0 = 2*D*j0 - CONST0
   static constexpr int OFF = (16 - CONST0 % 16) % 16;          // bytes from the aligned window start
   static constexpr int WIN = (WB + OFF + 15) / 16 * 16;        // aligned window read per group
   static constexpr int BASE = CONST0 + OFF;                    // window of group 0 starts at 2*D*j0 - BASE
@@ -443,7 +449,13 @@ k_rf_demod_tc(const RfTcArgs g) {
         pq = fq[k];
       }
       float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
-      if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 3) == 0) {
+      if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 7) == 0) {
+        // one 256-bit store per thread: half the store wavefronts of two float4 (the L1 data pipe
+        // is the busiest unit of this kernel, profiles/r1k)
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(drow + jrow), "f"(dm[0]), "f"(dm[1]),
+                     "f"(dm[2]), "f"(dm[3]), "f"(dm[4]), "f"(dm[5]), "f"(dm[6]), "f"(dm[7])
+                     : "memory");
+      } else if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 3) == 0) {
         *reinterpret_cast<float4 *>(drow + jrow) = make_float4(dm[0], dm[1], dm[2], dm[3]);
         *reinterpret_cast<float4 *>(drow + jrow + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
       } else {
