@@ -1031,37 +1031,47 @@ __device__ __forceinline__ float rq_mac(float acc, float h, float x) {
   return FMA ? __fmaf_rn(h, x, acc) : xmac(acc, h, x);
 }
 
+// Tile rows are 16-byte aligned in shared AND global memory (the tile starts at a multiple of
+// four samples of the capture's buffer), so they are filled by 16-byte asynchronous copies and a
+// lane reads FOUR consecutive input samples with one LDS.128; pitch/4 is odd, which keeps a
+// quarter-warp's LDS.128 on eight distinct 16-byte bank groups.  A quad whose newest row is not
+// the last of an aligned group walks `r` rows earlier; its tap table is staged r rows lower
+// (rows are float4, so the shift keeps the copies aligned) with zero rows around it.
 template <bool FMA, int NC>
 static __global__ void __launch_bounds__(256)
 k_audio_resample_v5(const ResampleQuadArgs g, int batch, int pitch) {
   const AudioArgs &a = g.a;
   constexpr int CAPS = 32 * NC;                       // captures per tile (NC per lane)
   constexpr int PSP = RQ_J + 2;                       // padded PCM row (int16)
+  const int KBP = g.KB + 4;                           // table rows incl. the alignment shift
   extern __shared__ __align__(16) float smem[];
-  float *tqs = smem;                                  // [8 warps][KB][4]
-  float *xs = tqs + 8 * g.KB * 4;                     // [CAPS][pitch]
+  float *tqs = smem;                                  // [8 warps][KBP][4]
+  float *xs = tqs + 8 * KBP * 4;                      // [CAPS][pitch]
   int16_t *ps = reinterpret_cast<int16_t *>(xs + (size_t)CAPS * pitch);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j0 = blockIdx.x * RQ_J;
   const int jn = min(RQ_J, a.n_out - j0);
   const int c0 = blockIdx.y * CAPS;
   const unsigned U = (unsigned)g.U, D = (unsigned)g.D;
-  // rows [i_lo, i_hi]: from the oldest row any quad of the tile can touch (KB-1 below its newest
-  // row) to the newest row of the last quad that holds a valid output
-  const int i_lo = (int)(((unsigned)j0 * D) / U) - (g.KB - 1);
+  // rows [i_lo, i_hi]: from the oldest row any quad of the tile can touch (KBP-1 below its
+  // aligned newest row), moved down to a multiple of four samples of the buffer, to the end of
+  // the aligned group holding the newest row of the last quad with a valid output
+  const int off = a.demod_off - a.delay;              // buffer index of input sample 0
+  int i_lo = (int)(((unsigned)j0 * D) / U) - (KBP - 1);
+  i_lo -= (((off + i_lo) % 4) + 4) % 4;
   const int jlast = j0 + ((jn + 3) & ~3) - 1;
-  const int i_hi = (int)(((unsigned)jlast * D) / U);
-  const int rows = i_hi - i_lo + 1;
-  const int first = a.demod_off - a.delay + i_lo;     // element index of row 0 in the capture's buffer
-  const bool interior = first >= 0 && i_hi < g.n_in;  // every row of the tile is a stored sample
+  const int i_hi = ((int)(((unsigned)jlast * D) / U) - i_lo) | 3;   // relative to i_lo, end of its group
+  const int rows = i_hi + 1;                          // multiple of 4
+  const int first = off + i_lo;                       // buffer index of tile row 0 (multiple of 4)
+  const bool interior = first >= 0 && i_lo + i_hi < g.n_in && (a.demod_stride & 3) == 0;
   const uint32_t xs_s = (uint32_t)__cvta_generic_to_shared(xs);
   for (int c = warp; c < CAPS; c += 8) {
     const int ch = min(c0 + c, batch - 1);            // lanes past the batch re-read the last capture
     const float *src = a.demod + (size_t)ch * a.demod_stride + first;
     const uint32_t dst = xs_s + (uint32_t)(c * pitch) * 4u;
     if (interior) {
-      for (int i = lane; i < rows; i += 32)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(src + i) : "memory");
+      for (int i = 4 * lane; i < rows; i += 128)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 4u * i), "l"(src + i) : "memory");
     } else {
       for (int i = lane; i < rows; i += 32)
         xs[(size_t)c * pitch + i] = (first + i >= 0 && i_lo + i < g.n_in) ? src[i] : 0.0f;
@@ -1069,28 +1079,40 @@ k_audio_resample_v5(const ResampleQuadArgs g, int batch, int pitch) {
   }
   const int jq = j0 + 4 * warp;
   const bool active = jq < a.n_out;
+  int gtop = 0;
   if (active) {
+    const int top3 = (int)(((unsigned)(jq + 3) * D) / U) - i_lo;
+    gtop = top3 | 3;                                  // newest row of the aligned group
+    const int r = gtop - top3;                        // rows walked before the quad's own newest row
     const unsigned phi0 = ((unsigned)jq * D) % U;
     const float4 *src = reinterpret_cast<const float4 *>(g.tq) + (size_t)phi0 * g.KB;
-    float4 *dst = reinterpret_cast<float4 *>(tqs) + warp * g.KB;
-    for (int i = lane; i < g.KB; i += 32)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)),
-                   "l"(src + i) : "memory");
+    float4 *dst = reinterpret_cast<float4 *>(tqs) + warp * KBP;
+    for (int i = lane; i < KBP; i += 32) {
+      const int k = i - r;
+      if (k >= 0 && k < g.KB)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)),
+                     "l"(src + k) : "memory");
+      else
+        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (active) {
-    const int top3 = (int)(((unsigned)(jq + 3) * D) / U) - i_lo;
-    const float *x0 = xs + (size_t)lane * pitch + top3;
-    const float4 *t = reinterpret_cast<const float4 *>(tqs) + warp * g.KB;
+    const float *x0 = xs + (size_t)lane * pitch + gtop - 3;   // aligned group holding the newest row
+    const float4 *t = reinterpret_cast<const float4 *>(tqs) + warp * KBP;
     float acc[4][NC] = {};
-    for (int kb = 0; kb < g.KB; kb += 4) {  // KB is a multiple of 4
+#pragma unroll 2
+    for (int kb = 0; kb < KBP; kb += 4) {
+      float4 xv[NC];
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc) xv[cc] = *reinterpret_cast<const float4 *>(x0 + (size_t)32 * cc * pitch - kb);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float4 h = t[kb + u];
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc) {
-          const float x = x0[(size_t)32 * cc * pitch - (kb + u)];
+          const float x = u == 0 ? xv[cc].w : u == 1 ? xv[cc].z : u == 2 ? xv[cc].y : xv[cc].x;
           acc[0][cc] = rq_mac<FMA>(acc[0][cc], h.x, x);
           acc[1][cc] = rq_mac<FMA>(acc[1][cc], h.y, x);
           acc[2][cc] = rq_mac<FMA>(acc[2][cc], h.z, x);
@@ -1112,12 +1134,22 @@ k_audio_resample_v5(const ResampleQuadArgs g, int batch, int pitch) {
     }
   }
   __syncthreads();
-  // ---- PCM rows out: one capture per warp pass, contiguous int16 along time ----
-  for (int c = warp; c < CAPS; c += 8) {
-    const int ch = c0 + c;
-    if (ch >= batch) break;
-    int16_t *dst = a.pcm + (size_t)ch * a.pcm_stride + (size_t)j0;
-    if (lane < jn) dst[lane] = ps[c * PSP + lane];
+  // ---- PCM rows out: two captures per warp pass, 32-bit words along time ----
+  const bool words = jn == RQ_J && (a.pcm_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(a.pcm) & 3) == 0;
+  if (words) {
+    for (int c = 2 * warp + (lane >> 4); c < CAPS; c += 16) {
+      const int ch = c0 + c;
+      if (ch >= batch) continue;
+      uint32_t *dst = reinterpret_cast<uint32_t *>(a.pcm + (size_t)ch * a.pcm_stride + (size_t)j0);
+      dst[lane & 15] = *reinterpret_cast<const uint32_t *>(ps + c * PSP + 2 * (lane & 15));
+    }
+  } else {
+    for (int c = warp; c < CAPS; c += 8) {
+      const int ch = c0 + c;
+      if (ch >= batch) break;
+      int16_t *dst = a.pcm + (size_t)ch * a.pcm_stride + (size_t)j0;
+      if (lane < jn) dst[lane] = ps[c * PSP + lane];
+    }
   }
 }
 

@@ -858,9 +858,10 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
       const int KB = p->quad_kb;
       static const int nc = std::getenv("SDR_RESAMPLE_NC") ? std::atoi(std::getenv("SDR_RESAMPLE_NC")) : 2;
       const int caps = 32 * nc;
-      int pitch = (int)(((long long)(RQ_J - 1) * p->m.audio_decim) / p->m.audio_upsamp) + KB + 2;
-      pitch |= 1;  // odd: lane c reads bank (c * pitch + t) % 32
-      const size_t smem = ((size_t)8 * KB * 4 + (size_t)caps * pitch) * sizeof(float) +
+      // rows of a tile: inputs spanned by RQ_J outputs + the table (KB + 4 rows) + alignment slack
+      int pitch = round_up((int)(((long long)(RQ_J - 1) * p->m.audio_decim) / p->m.audio_upsamp) + KB + 4 + 8, 4);
+      if ((pitch / 4) % 2 == 0) pitch += 4;  // pitch/4 odd: conflict-free LDS.128 across lanes
+      const size_t smem = ((size_t)8 * (KB + 4) * 4 + (size_t)caps * pitch) * sizeof(float) +
                           (size_t)caps * (RQ_J + 2) * sizeof(int16_t);
       if (smem > 200 * 1024) return fail(SDR_ERR_INVALID, "resampler tile does not fit in shared memory");
       dim3 grid(((int)n_audio + RQ_J - 1) / RQ_J, (B + caps - 1) / caps);
