@@ -44,9 +44,10 @@ extern "C" {
 /* Arithmetic variants of the batched pipeline. */
 #define SDR_VARIANT_EXACT 0 /* CUDA-core path, bit-identical to the reference */
 /* Tensor-core RF front end (tcgen05 kind::i8 over the raw byte stream), mono only, all four
- * modes (rf_decim 10, 5, 3), rf_taps <= 151.  I/Q are the exactly rounded fixed-point FIR
- * outputs (tap quantisation 2^-34) instead of the reference's sequential float sums:
- * float intermediates agree to >= 100 dB SNR and PCM to +-1 LSB, not bit for bit.
+ * modes (rf_decim 10, 5, 3), rf_taps <= 151.  I/Q are fixed-point FIR outputs (tap
+ * quantisation 2^-34, exact integer sums, <= 1 ulp recombination) instead of the reference's
+ * sequential float sums, and the audio filter contracts its multiply-adds: float
+ * intermediates agree to >= 100 dB SNR and PCM to +-1 LSB, not bit for bit.
  * Stereo is refused: the PLL amplifies 1-ulp differences beyond the parity bound. */
 #define SDR_VARIANT_FAST 1
 

@@ -6,30 +6,37 @@
 // exactly that situation.
 //
 // How (polyphase Hankel GEMM on tcgen05, kind::i8), for a T-tap filter decimating by D:
-//   y[j] = sum_n h[n] x[D j - n] = sum_p sum_q h[D q + p] * xp[p][j - q],   xp[p][i] = x[D i - p]
+//   y[j] = sum_n h[n] x[D j - n] = sum_p sum_q h[D q + p - c] * xp[p][j - q],   xp[p][i] = x[D i - p + c]
+// (c = TcCfg::SHIFT, a free re-indexing that aligns the transposer's windows)
 // 1. A CUDA-core pass transposes the raw interleaved bytes into 2 D byte streams (D phases x
 //    {I,Q}) in shared memory -- no conversion, the bytes stay unsigned 8-bit (PRMT only).
 // 2. For each stream, row m of the MMA's A operand is the K bytes starting 16 bytes after row
 //    m-1: a matrix descriptor with leading-byte-offset 16 and stride-byte-offset 128 turns the
 //    stream into that overlapping-row (Hankel) matrix in place (tools/umma_hankel_test.cu), so
-//    row m sees xp[p][j0+16m-(Q-1) ..] and produces the 16 outputs j0+16m+delta.
-// 3. The B operand of phase p holds the taps h[Dq+p], scaled to 31-bit fixed point and split
-//    into four signed base-256 digits: column 4*delta+d has digit_d at k = delta+(Q-1)-q.
+//    row m sees xp[p][j0+16m-(BACK-FRONT) ..] and produces the 16 outputs j0+16m+delta.
+// 3. The B operand of phase p holds that phase's taps, scaled to 31-bit fixed point and split
+//    into four signed base-256 digits: column 4*delta+d has digit_d at k = delta+(BACK-FRONT)-q.
 //    (Three digits are enough for 130 dB on I/Q in steady state, but not while the filter fills
 //    at the start of a capture, where the outputs are ~1e-6 and fmDemod divides by them.)
-//    D*K/32 MMAs per component accumulate sum_t digit_d(h[t]) * u8[...] exactly in int32.
-// 4. The epilogue recombines the digits in integers, removes the 128 offset of the unsigned
-//    samples and rounds ONCE to float: the exactly rounded fixed-point FIR output (tap
-//    quantisation 2^-34, far below the reference's own float rounding).  It differs from the
-//    reference's sequential float sum only by that rounding (~1e-7 relative; tests: >= 100 dB
-//    SNR, PCM +-1 LSB) and is bit-identical to an integer model of itself (tests).
+//    D*K/32 MMAs per component accumulate sum_t digit_d(h[t]) * u8[...] exactly in int32; one
+//    more MMA with a constant A operand starts the accumulators at -128 * sum_t digit_d(h[t]),
+//    so they end as the digit sums over the CENTRED samples (x - 128), each below 2^22.
+// 4. The epilogue recombines the four digit sums (tc_combine): exact in integers up to two
+//    31-bit halves, then two int->float conversions and one FMA -- at most one ulp from the
+//    exactly rounded fixed-point FIR output (tap quantisation 2^-34, far below the reference's
+//    own float rounding), and exactly zero when that output is zero.  It differs from the
+//    reference's sequential float sum by ~1e-7 relative (tests: >= 100 dB SNR, PCM +-1 LSB;
+//    against an integer model of the kernel: <= 1 ulp).
 //    fmDemod follows in the same kernel; the one-sample state crosses rows via shared memory.
 //
-// Schedule (8 warps, two CTAs per SM): the raw bytes of the NEXT tile arrive by one TMA bulk
-// copy while the current tile is processed; all warps transpose; accumulators are double
-// buffered so the MMAs of tile i run under the epilogue of tile i-1; a TMEM lane quarter is
-// readable by warps w and w+4, which split a row's 16 outputs.  History of the design with the
-// measured time of each step: DESIGN.md section 4 and profiles/.
+// Schedule: persistent CTAs, two per SM, 8 worker warps + 1 issue warp.  Work items (capture,
+// segment of tiles) come from a device counter.  Per tile the workers transpose the staged bytes
+// into the streams, arrive on an mbarrier and go on to the epilogue of the PREVIOUS tile
+// (accumulators are double buffered; a TMEM lane quarter is readable by warps w and w+4, which
+// split a row's 16 outputs); lane 0 of the issue warp waits for the 256 arrivals, starts the TMA
+// bulk copy of the next tile into the (now free) staging buffer and then issues the MMAs.
+// History of the design with the measured time of each step: DESIGN.md section 4, profiles/,
+// tools/tc_trace.py.
 #pragma once
 
 #include "kernels.cuh"
