@@ -1359,12 +1359,14 @@ struct CarryArgs {
   long long n_rf;
   float *prev_dst;
   const float *prev_src;
+  int *work_counter;   // optional: work-item counter of the tensor-core front end, re-armed for the next call
 };
 
 static __global__ void k_carry(const CarryArgs c) {
   extern __shared__ unsigned char stage[];
   const int b = blockIdx.x;
   const int t = threadIdx.x;
+  if (c.work_counter && b == 0 && t == 0) *c.work_counter = 0;
   // 1. float tails.  Source and destination ranges may overlap when the call was
   //    shorter than the history, so go through shared memory.
   float *fstage = reinterpret_cast<float *>(stage);

@@ -112,6 +112,7 @@ struct sdr_pipeline {
   DevBuf<float> d_h_rf, d_h_audio, d_h_pilot, d_h_stereo, d_h_poly, d_h_quad;
   int quad_kb = 0;  // rows of one quad table (k_audio_resample_v5)
   DevBuf<int> tc_next_item;  // work counter of the persistent tensor-core front end
+  bool tc_counter_armed = false;  // zeroed since its last use (k_carry does it at the end of a call)
   // tensor-core front end (SDR_VARIANT_FAST)
   DevBuf<int8_t> tc_bmat;
   DevBuf<int32_t> tc_hq;
@@ -261,7 +262,10 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     });
     dim3 grid(std::min(n_cta, g.segs * g.batch));
     g.next_item = p->tc_next_item.p;
-    if (cudaMemsetAsync(g.next_item, 0, sizeof(int), s) != cudaSuccess) return fail(SDR_ERR_CUDA, "cudaMemsetAsync");
+    if (!p->tc_counter_armed &&   // first call, or the previous call failed before its k_carry
+        cudaMemsetAsync(g.next_item, 0, sizeof(int), s) != cudaSuccess)
+      return fail(SDR_ERR_CUDA, "cudaMemsetAsync");
+    p->tc_counter_armed = false;
     prof_begin(p, "k_rf_demod_tc", s);
     if (D == 10) k_rf_demod_tc<10><<<grid, TC_BLOCK, TcCfg<10>::SMEM, s>>>(g);
     else if (D == 5) k_rf_demod_tc<5><<<grid, TC_BLOCK, TcCfg<5>::SMEM, s>>>(g);
@@ -625,7 +629,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   if (cfg->variant == SDR_VARIANT_FAST) {
     TRY(p->tc_bmat.alloc(tc_b.size()));
     TRY(p->tc_hq.alloc(tc_h.size()));
-    TRY(p->tc_next_item.alloc(1));
+    TRY(p->tc_next_item.alloc(1));   // zeroed before first use; k_carry re-arms it at the end of every call
     rc = cudaMemcpy(p->tc_bmat.p, tc_b.data(), tc_b.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
                  cudaMemcpy(p->tc_hq.p, tc_h.data(), tc_h.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess
              ? SDR_OK
@@ -982,9 +986,11 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   // When taps are kept the carry would overwrite what sdr_pipeline_tap reads
   // (history-prefixed rows), so the tap accessor accounts for it via last_n_if.
   size_t sh = std::max<size_t>((size_t)std::max(p->HD, p->HA + 1) * sizeof(float), (size_t)2 * p->HR);
+  ca.work_counter = p->tc_next_item.p;   // nullptr unless the fast variant allocated it
   prof_begin(p, "k_carry", s);
   k_carry<<<B, 128, sh, s>>>(ca);
   if ((rc = check_launch(p, "k_carry"))) return rc;
+  p->tc_counter_armed = true;
   p->last_n_if = n_if;
   p->last_n_audio = n_audio;
   return SDR_OK;
