@@ -243,16 +243,26 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     g.bmat = p->tc_bmat.p;
     g.hq = p->tc_hq.p;
     g.scale = p->tc_scale;
-    // persistent CTAs (two per SM) take work items (capture, segment) round-robin; segments are
-    // sized so that every CTA gets at least ~12 items: the last round is then nearly full
+    // Persistent CTAs (two per SM) take work items (segment of a capture) from a device counter.
+    // Long segments first (a segment start costs an extra barrier and the integer predecessor),
+    // a few short ones at the end of every capture so that the last items handed out are small.
     const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->cfg.device);
     const int n_cta = 2 * n_sm;
-    static const int items_per_cta = std::getenv("SDR_TC_ITEMS") ? std::atoi(std::getenv("SDR_TC_ITEMS")) : 12;
-    const int want = std::max(1, std::min((n_cta * items_per_cta + p->cfg.batch - 1) / p->cfg.batch, n_tiles));
-    g.tiles_per_seg = (n_tiles + want - 1) / want;
-    g.segs = (n_tiles + g.tiles_per_seg - 1) / g.tiles_per_seg;
+    static const int items_per_cta = std::getenv("SDR_TC_ITEMS") ? std::atoi(std::getenv("SDR_TC_ITEMS")) : 6;
+    static const int tail_tiles = std::getenv("SDR_TC_TAIL") ? std::atoi(std::getenv("SDR_TC_TAIL")) : 8;
+    static const int small_tiles = std::getenv("SDR_TC_SMALL") ? std::atoi(std::getenv("SDR_TC_SMALL")) : 4;
+    const int tail = n_tiles >= 4 * tail_tiles ? tail_tiles : 0;          // tiles covered by short segments
+    const int n_small = tail ? (tail + small_tiles - 1) / small_tiles : 0;
+    const int head = n_tiles - tail;
+    const int want = std::max(1, std::min({(n_cta * items_per_cta + p->cfg.batch - 1) / p->cfg.batch, head,
+                                           TC_MAX_SEGS - n_small}));
+    const int per = (head + want - 1) / want;
+    g.segs = 0;
+    for (int t = 0; t < head; t += per) g.seg_begin[g.segs++] = t;
+    for (int t = head; t < n_tiles; t += small_tiles) g.seg_begin[g.segs++] = t;
+    g.seg_begin[g.segs] = n_tiles;
     g.batch = p->cfg.batch;
     static std::once_flag once[16];
     std::call_once(once[p->cfg.device & 15], [&] {

@@ -51,6 +51,7 @@ constexpr int TC_TMAX = 151;                 // longest supported filter
 constexpr int TC_ND = 4;                     // signed base-256 digits per tap (31-bit fixed point)
 constexpr int TC_N = 16 * TC_ND;             // 64 accumulator columns per component
 constexpr int TC_CORR_BYTES = TC_N * 32;      // one 64 x 32 B tile that removes the +128 offset (below)
+constexpr int TC_MAX_SEGS = 15;              // segments per capture (work items per capture)
 constexpr int TC_FRONT = 16;                 // spare stream entries in front of row 0's window
 
 template <int D>
@@ -89,7 +90,10 @@ struct RfTcArgs {
                         // the 64 x 32 offset tile
   const int32_t *hq;    // fixed-point taps, D*Q entries (zero padded)
   float scale;          // 2^-(S+7)
-  int tiles_per_seg;    // work item = tiles_per_seg consecutive tiles of one capture
+  // work item = one segment (consecutive tiles [seg_begin[s], seg_begin[s+1])) of one capture;
+  // items are numbered segment-major, so the short segments at the end of a capture are the last
+  // items handed out and the kernel's tail (CTAs waiting for the slowest) stays short
+  int seg_begin[TC_MAX_SEGS + 1];
   int segs, batch;      // items = segs * batch
   int *next_item;       // device counter, zeroed before the launch: further items are gridDim.x + atomicAdd
 };
@@ -226,7 +230,7 @@ k_rf_demod_tc(const RfTcArgs g) {
   const int rowi = (warp & 3) * 32 + lane;  // TMEM lane = A row served by this thread
   const int half = warp >> 2;               // which 8 of the row's 16 outputs
   const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
-  const int n_items = g.segs * g.batch;     // work item = (capture, segment of tiles_per_seg tiles)
+  const int n_items = g.segs * g.batch;     // work item = (segment, capture)
   const bool issuer = warp == TC_THREADS / 32;   // warp 8: lane 0 issues MMAs and bulk copies
   auto workers_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); };
 
@@ -266,9 +270,10 @@ k_rf_demod_tc(const RfTcArgs g) {
   };
   auto get_item = [&](int item) {
     Item w;
-    w.b = item / g.segs;
-    w.tile_begin = (item - w.b * g.segs) * g.tiles_per_seg;
-    w.tile_end = min(w.tile_begin + g.tiles_per_seg, n_tiles);
+    const int sg = item / g.batch;
+    w.b = item - sg * g.batch;
+    w.tile_begin = g.seg_begin[sg];
+    w.tile_end = g.seg_begin[sg + 1];
     w.row = a.iq + (size_t)w.b * a.iq_stride;
     w.hrow = a.hist + (size_t)w.b * 2 * a.rf_hist_len;
     w.row_aligned = ((reinterpret_cast<uintptr_t>(w.row) & 15) == 0);
