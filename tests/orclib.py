@@ -154,3 +154,142 @@ def REF() -> RefLib | None:
             return None
         _ref = RefLib(path)
     return _ref
+
+
+# ---------------------------------------------------------------------------
+# RDS oracle (oracle/rds_oracle.c: restatement of model/fmRDS.py + fmSupportLib.py)
+# ---------------------------------------------------------------------------
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+RDS_TAP_NAMES = ["channel_filt", "carrier_filt", "pll_i", "pll_q", "mixer_i", "mixer_q",
+                 "resampler_i", "resampler_q", "rrc_i", "rrc_q"]
+RDS_PARAMS = {0: dict(U=247, D=960, sps=26, block_if=9600),
+              2: dict(U=817, D=1920, sps=43, block_if=1536000)}
+
+
+class RdsOracle:
+    """ctypes view of the rdo_* functions; lives in the same library as the FM oracle."""
+
+    def __init__(self):
+        L = ORC().lib
+        self.lib = L
+        L.rdo_bandpass.restype = None
+        L.rdo_bandpass.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, f64p]
+        L.rdo_lowpass.restype = None
+        L.rdo_lowpass.argtypes = [C.c_int, C.c_double, C.c_double, f64p]
+        L.rdo_rrc.restype = None
+        L.rdo_rrc.argtypes = [C.c_double, C.c_int, f64p]
+        L.rdo_fir.restype = None
+        L.rdo_fir.argtypes = [f64p, C.c_size_t, f64p, C.c_int, f64p, f64p]
+        L.rdo_allpass.restype = None
+        L.rdo_allpass.argtypes = [f64p, C.c_size_t, f64p, C.c_int, f64p]
+        L.rdo_pll.restype = None
+        L.rdo_pll.argtypes = [f64p, C.c_size_t, C.c_double, C.c_double, f64p, C.c_double,
+                              C.c_double, C.c_double, f64p, f64p]
+        L.rdo_resample.restype = None
+        L.rdo_resample.argtypes = [f64p, C.c_size_t, f64p, C.c_int, f64p, C.c_int, C.c_int, f64p]
+        L.rdo_cdr.restype = C.c_int
+        L.rdo_cdr.argtypes = [f64p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.rdo_diff_decode.restype = None
+        L.rdo_diff_decode.argtypes = [u8p, C.c_int, u8p]
+        L.rdo_syndrome.restype = None
+        L.rdo_syndrome.argtypes = [u8p, u8p]
+        L.rdo_framesync.restype = C.c_char
+        L.rdo_framesync.argtypes = [u8p, C.c_int, C.POINTER(C.c_int)]
+        L.rdo_chain_create.restype = C.c_void_p
+        L.rdo_chain_create.argtypes = [C.c_int, C.c_int]
+        L.rdo_chain_destroy.restype = None
+        L.rdo_chain_destroy.argtypes = [C.c_void_p]
+        L.rdo_chain_block.restype = None
+        L.rdo_chain_block.argtypes = [C.c_void_p, f64p]
+        L.rdo_chain_tap.restype = C.POINTER(C.c_double)
+        L.rdo_chain_tap.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+        L.rdo_chain_bits.restype = C.c_int
+        L.rdo_chain_bits.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint8)),
+                                     C.POINTER(C.POINTER(C.c_uint8))]
+        L.rdo_chain_offset.restype = C.c_char
+        L.rdo_chain_offset.argtypes = [C.c_void_p]
+
+    # -- design ------------------------------------------------------------
+    def bandpass(self, ntaps, Fs, Fb, Fe):
+        h = np.empty(ntaps, np.float64)
+        self.lib.rdo_bandpass(ntaps, Fs, Fb, Fe, h)
+        return h
+
+    def lowpass(self, ntaps, Fs, Fc):
+        h = np.empty(ntaps, np.float64)
+        self.lib.rdo_lowpass(ntaps, Fs, Fc, h)
+        return h
+
+    def rrc(self, Fs, ntaps):
+        h = np.empty(ntaps, np.float64)
+        self.lib.rdo_rrc(Fs, ntaps, h)
+        return h
+
+    # -- bit layer -----------------------------------------------------------
+    def cdr(self, x, sps, block_count):
+        x = np.ascontiguousarray(x, np.float64)
+        bits = np.zeros(x.size // sps + 4, np.uint8)
+        n = self.lib.rdo_cdr(x, x.size, sps, block_count, bits, bits.size)
+        return bits[:n].copy()
+
+    def diff_decode(self, bits):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        out = np.zeros_like(bits)
+        self.lib.rdo_diff_decode(bits, bits.size, out)
+        return out
+
+    def syndrome(self, d26):
+        d = np.ascontiguousarray(d26, np.uint8)
+        s = np.zeros(10, np.uint8)
+        self.lib.rdo_syndrome(d, s)
+        return s
+
+    def framesync(self, bits):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        idx = C.c_int(0)
+        o = self.lib.rdo_framesync(bits if bits.size else np.zeros(1, np.uint8), bits.size,
+                                   C.byref(idx))
+        return o.decode(), idx.value
+
+    # -- chain -----------------------------------------------------------------
+    def run_chain(self, fm_demod, mode, block_if=None, keep=("rrc_i", "rrc_q")):
+        """fm_demod: float array, a whole number of blocks.  Returns a dict with the kept
+        stages concatenated over blocks, 'cdr_bits' / 'diff_bits' (lists per block) and
+        'offsets' (one character per block)."""
+        block_if = block_if or RDS_PARAMS[mode]["block_if"]
+        x = np.ascontiguousarray(fm_demod, np.float64)
+        assert x.size % block_if == 0
+        h = self.lib.rdo_chain_create(mode, block_if)
+        if not h:
+            raise ValueError("RDS is defined for modes 0 and 2 only")
+        out = {k: [] for k in keep}
+        out.update(cdr_bits=[], diff_bits=[], offsets="")
+        try:
+            for b in range(x.size // block_if):
+                self.lib.rdo_chain_block(h, x[b * block_if:(b + 1) * block_if])
+                for k in keep:
+                    cnt = C.c_size_t(0)
+                    ptr = self.lib.rdo_chain_tap(h, RDS_TAP_NAMES.index(k), C.byref(cnt))
+                    out[k].append(np.ctypeslib.as_array(ptr, shape=(cnt.value,)).copy())
+                p1 = C.POINTER(C.c_uint8)()
+                p2 = C.POINTER(C.c_uint8)()
+                n = self.lib.rdo_chain_bits(h, C.byref(p1), C.byref(p2))
+                out["cdr_bits"].append(np.ctypeslib.as_array(p1, shape=(max(n, 1),))[:n].copy())
+                out["diff_bits"].append(np.ctypeslib.as_array(p2, shape=(max(n, 1),))[:n].copy())
+                out["offsets"] += self.lib.rdo_chain_offset(h).decode()
+        finally:
+            self.lib.rdo_chain_destroy(h)
+        for k in keep:
+            out[k] = np.concatenate(out[k])
+        return out
+
+
+_rds = None
+
+
+def RDS() -> RdsOracle:
+    global _rds
+    if _rds is None:
+        _rds = RdsOracle()
+    return _rds
