@@ -188,6 +188,74 @@ int sdr_pipeline_profile(sdr_pipeline *p, int enable);
 int sdr_pipeline_kernel_times(sdr_pipeline *p, int index, char *name, size_t name_cap,
                               double *total_ms, uint64_t *count, int reset);
 
+/* ------------------------------------------------------------------------ */
+/* RDS receiver chain (modes 0 and 2), attached to a batched pipeline.       */
+/* The reference has no C++ RDS path: these entry points replace the block    */
+/* loop of its Python model, model/fmRDS.py:222-276 (functions in             */
+/* model/fmSupportLib.py), which works in double precision -- and so do the   */
+/* device kernels (csrc/rds.cu).  Input is the pipeline's fm_demod.           */
+/* Once created, the chain runs at the end of every sdr_pipeline_process_*    */
+/* call of its pipeline (same stream); the pipeline's granule becomes one     */
+/* RDS block (sdr_rds_info.block_bytes).  sdr_pipeline_reset resets it too.   */
+/* Destroy the sdr_rds handle before its pipeline.                            */
+/* ------------------------------------------------------------------------ */
+typedef struct sdr_rds sdr_rds;
+
+typedef struct {
+  int block_if;           /* IF samples per RDS block = the CDR window; 0 = the model's
+                             (fmRDS.py:149-152: 9600 in mode 0, 1536000 in mode 2); a multiple of 9600 */
+  int max_pending_blocks; /* blocks whose bits may wait for sdr_rds_read; 0 = default */
+  int keep_nco;           /* keep the PLL's NCO outputs for sdr_rds_tap (SDR_RDS_TAP_PLL_*) */
+} sdr_rds_config;
+
+typedef struct {
+  int upsamp, decim;        /* fmRDS.py:57-58 / :69-70 */
+  int samples_per_symbol;   /* fmRDS.py:60 / :72 */
+  int block_if, block_out;  /* IF samples in / symbol-rate samples out per block */
+  int block_bytes;          /* raw I/Q bytes per block */
+  int max_pending_blocks, max_bits_per_block;
+} sdr_rds_info_t;
+
+/* Stages that sdr_rds_tap returns (last process call; names are fmRDS.py's variables). */
+#define SDR_RDS_TAP_CHANNEL 0     /* fmRDS.py:223 rds_channel_filt */
+#define SDR_RDS_TAP_CARRIER 1     /* fmRDS.py:233 rds_carrier_filt */
+#define SDR_RDS_TAP_PLL_I 2       /* fmRDS.py:236 rds_PLL (n+1 values; needs keep_nco) */
+#define SDR_RDS_TAP_PLL_Q 3       /* fmRDS.py:236 rds_PLL_Q */
+#define SDR_RDS_TAP_MIXER_I 4     /* fmRDS.py:241 rds_mixer */
+#define SDR_RDS_TAP_MIXER_Q 5     /* fmRDS.py:251 rds_mixer2 */
+#define SDR_RDS_TAP_RESAMPLER_I 6 /* fmRDS.py:244 rds_resampler_out */
+#define SDR_RDS_TAP_RESAMPLER_Q 7 /* fmRDS.py:252 rds_resampler_out2 */
+#define SDR_RDS_TAP_RRC_I 8       /* fmRDS.py:248 rds_RRC_out */
+#define SDR_RDS_TAP_RRC_Q 9       /* fmRDS.py:254 rds_RRC_out2 */
+
+#define SDR_RDS_FILTER_CHANNEL 0   /* bandPass(151, if_fs, 54e3, 60e3)         fmRDS.py:122 */
+#define SDR_RDS_FILTER_CARRIER 1   /* bandPass(151, if_fs, 113.5e3, 114.5e3)   fmRDS.py:123 */
+#define SDR_RDS_FILTER_RESAMPLER 2 /* impResponse(101*U, if_fs*U, 3e3)         fmRDS.py:124 */
+#define SDR_RDS_FILTER_RRC 3       /* impulseResponseRootRaisedCosine(2375*SPS, 101) fmRDS.py:125 */
+
+/* The model's coefficient sets (host, double): fmSupportLib.py:358-385, :251-287. */
+int sdr_rds_design(int which, int mode, double *h, size_t cap, size_t *n);
+
+int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rds **out);
+int sdr_rds_destroy(sdr_rds *r);
+int sdr_rds_info(const sdr_rds *r, sdr_rds_info_t *out);
+/* Blocks processed since the last sdr_rds_discard. */
+int sdr_rds_pending(sdr_rds *r, size_t *n_blocks);
+/* Bit layer of capture `channel` for the pending blocks, in order:
+ *   cdr_bits   CDR + Manchester decoding output      fmRDS.py:268 (fmSupportLib.py:103-222)
+ *   diff_bits  differentially decoded bits           fmRDS.py:271 (fmSupportLib.py:241-249)
+ *   bit_counts bits per block
+ *   offsets    the frame synchroniser's result after each block: ' ', 'A', 'B', 'C',
+ *              'c' (C') or 'D'                       fmRDS.py:272-276 (fmSupportLib.py:30-100)
+ * Any output pointer may be NULL; *n_bits / *n_blocks always receive the totals. */
+int sdr_rds_read(sdr_rds *r, int channel, uint8_t *cdr_bits, uint8_t *diff_bits, size_t bits_cap,
+                 size_t *n_bits, int *bit_counts, char *offsets, size_t blocks_cap,
+                 size_t *n_blocks);
+/* Forget the pending blocks (the frame synchroniser keeps its carried bits). */
+int sdr_rds_discard(sdr_rds *r);
+/* Double-precision intermediate `stage` of capture `channel` from the last process call. */
+int sdr_rds_tap(sdr_rds *r, int stage, int channel, double *dst, size_t cap, size_t *n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,20 @@ class ModeInfo(C.Structure):
                 ("block_bytes", C.c_int), ("granule_bytes", C.c_int), ("pcm_per_granule", C.c_int)]
 
 
+class RdsConfig(C.Structure):
+    _fields_ = [("block_if", C.c_int), ("max_pending_blocks", C.c_int), ("keep_nco", C.c_int)]
+
+
+class RdsInfo(C.Structure):
+    _fields_ = [("upsamp", C.c_int), ("decim", C.c_int), ("samples_per_symbol", C.c_int),
+                ("block_if", C.c_int), ("block_out", C.c_int), ("block_bytes", C.c_int),
+                ("max_pending_blocks", C.c_int), ("max_bits_per_block", C.c_int)]
+
+
+RDS_TAP_NAMES = ["channel_filt", "carrier_filt", "pll_i", "pll_q", "mixer_i", "mixer_q",
+                 "resampler_i", "resampler_q", "rrc_i", "rrc_q"]
+RDS_FILTER_NAMES = ["channel", "carrier", "resampler", "rrc"]
+
 _f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _vp = C.c_void_p
 
@@ -81,6 +95,15 @@ ABI = {
     "sdr_pipeline_profile": (C.c_int, [_vp, C.c_int]),
     "sdr_pipeline_kernel_times": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_size_t,
                                             C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
+    "sdr_rds_design": (C.c_int, [C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sdr_rds_create": (C.c_int, [_vp, C.POINTER(RdsConfig), C.POINTER(_vp)]),
+    "sdr_rds_destroy": (C.c_int, [_vp]),
+    "sdr_rds_info": (C.c_int, [_vp, C.POINTER(RdsInfo)]),
+    "sdr_rds_pending": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
+    "sdr_rds_read": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t), _vp, _vp,
+                               C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sdr_rds_discard": (C.c_int, [_vp]),
+    "sdr_rds_tap": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
 }
 
 _lib = None
@@ -299,4 +322,77 @@ class Pipeline:
         _check(lib().sdr_pipeline_tap(self._h, stage, channel, None, 0, C.byref(n)))
         out = np.zeros(n.value, np.float32)
         _check(lib().sdr_pipeline_tap(self._h, stage, channel, out.ctypes.data, out.size, C.byref(n)))
+        return out
+
+
+# ---- RDS chain (model/fmRDS.py:222-276) ----------------------------------------------------------
+def rds_design(which: str, mode: int) -> np.ndarray:
+    """The model's coefficient sets: 'channel', 'carrier', 'resampler', 'rrc' (float64)."""
+    w = RDS_FILTER_NAMES.index(which)
+    n = C.c_size_t(0)
+    _check(lib().sdr_rds_design(w, mode, None, 0, C.byref(n)))
+    h = np.zeros(n.value, np.float64)
+    _check(lib().sdr_rds_design(w, mode, h.ctypes.data, h.size, C.byref(n)))
+    return h
+
+
+class Rds:
+    """RDS receiver attached to a :class:`Pipeline` (modes 0 and 2): it runs at the end of every
+    process call of that pipeline, on the same stream."""
+
+    def __init__(self, pipeline: Pipeline, block_if=0, max_pending_blocks=0, keep_nco=False):
+        self.pipeline = pipeline
+        self._h = _vp()
+        cfg = RdsConfig(block_if, max_pending_blocks, 1 if keep_nco else 0)
+        _check(lib().sdr_rds_create(pipeline._h, C.byref(cfg), C.byref(self._h)))
+        self.info = RdsInfo()
+        _check(lib().sdr_rds_info(self._h, C.byref(self.info)))
+
+    def close(self):
+        if self._h:
+            lib().sdr_rds_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def pending(self) -> int:
+        n = C.c_size_t(0)
+        _check(lib().sdr_rds_pending(self._h, C.byref(n)))
+        return n.value
+
+    def read(self, channel: int = 0) -> dict:
+        """Bit layer of the pending blocks of one capture: cdr_bits, diff_bits (uint8 arrays),
+        bit_counts (per block) and offsets (one character per block)."""
+        nbits, nblk = C.c_size_t(0), C.c_size_t(0)
+        _check(lib().sdr_rds_read(self._h, channel, None, None, 0, C.byref(nbits), None, None, 0,
+                                  C.byref(nblk)))
+        cdr = np.zeros(max(nbits.value, 1), np.uint8)
+        diff = np.zeros(max(nbits.value, 1), np.uint8)
+        counts = np.zeros(max(nblk.value, 1), np.int32)
+        offs = C.create_string_buffer(max(nblk.value, 1))
+        _check(lib().sdr_rds_read(self._h, channel, cdr.ctypes.data, diff.ctypes.data, cdr.size,
+                                  C.byref(nbits), counts.ctypes.data, offs, counts.size,
+                                  C.byref(nblk)))
+        return dict(cdr_bits=cdr[:nbits.value], diff_bits=diff[:nbits.value],
+                    bit_counts=counts[:nblk.value], offsets=offs.raw[:nblk.value].decode())
+
+    def discard(self):
+        _check(lib().sdr_rds_discard(self._h))
+
+    def tap(self, name: str, channel: int = 0) -> np.ndarray:
+        stage = RDS_TAP_NAMES.index(name)
+        n = C.c_size_t(0)
+        _check(lib().sdr_rds_tap(self._h, stage, channel, None, 0, C.byref(n)))
+        out = np.zeros(n.value, np.float64)
+        _check(lib().sdr_rds_tap(self._h, stage, channel, out.ctypes.data, out.size, C.byref(n)))
         return out

@@ -18,6 +18,7 @@
 #include "../../include/sdr_b200.h"
 #include "design.h"
 #include "kernels.cuh"
+#include "pipeline_view.h"
 #include "rf_tc.cuh"
 
 namespace sdr {
@@ -32,7 +33,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   if (e == cudaErrorMemoryAllocation) return SDR_ERR_NOMEM;
   return SDR_ERR_CUDA;
 }
-static int fail(int code, const std::string &msg) {
+int fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
 }
@@ -124,6 +125,9 @@ struct sdr_pipeline {
   bool keep_taps = false;
   size_t last_n_if = 0, last_n_audio = 0;
   uint64_t launches = 0;
+  // optional follower stage (RDS, rds.cu): runs at the end of every process call
+  sdr::PipelineHook hook = nullptr;
+  void *hook_ctx = nullptr;
   // optional per-kernel timing (CUDA events on the launching stream)
   bool profiling = false;
   struct Site {
@@ -186,6 +190,9 @@ static int check_launch(sdr_pipeline *p, const char *name) {
   if (p) p->launches++;
   return SDR_OK;
 }
+
+void sdr_prof_begin(sdr_pipeline *p, const char *name, cudaStream_t s) { prof_begin(p, name, s); }
+int sdr_check_launch(sdr_pipeline *p, const char *name) { return check_launch(p, name); }
 
 static int pick_segments(int n_out, int tile_out, int batch, int *outs_per_seg) {
   const int n_tiles = (n_out + tile_out - 1) / tile_out;
@@ -447,6 +454,38 @@ extern "C" int sdr_pipeline_reset(sdr_pipeline *p) {
   }
   p->last_n_if = p->last_n_audio = 0;
   SDR_CUDA(cudaDeviceSynchronize());
+  if (p->hook && (rc = p->hook(p->hook_ctx, 1, 0, nullptr))) return rc;
+  return SDR_OK;
+}
+
+int sdr::pipeline_view(sdr_pipeline *p, DemodView *v) {
+  if (!p || !v) return fail(SDR_ERR_INVALID, "null argument");
+  v->demod = p->demod.p;
+  v->stride = p->demod_stride;
+  v->off = p->HD;
+  v->batch = p->cfg.batch;
+  v->device = p->cfg.device;
+  v->mode = p->cfg.mode;
+  v->if_Fs = p->m.if_Fs;
+  v->rf_decim = p->m.rf_decim;
+  v->cap_if = p->cap_if;
+  return SDR_OK;
+}
+
+int sdr::pipeline_set_hook(sdr_pipeline *p, PipelineHook fn, void *ctx, int granule_bytes) {
+  if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
+  if (fn && p->hook && p->hook_ctx != ctx) return fail(SDR_ERR_INVALID, "pipeline already has a follower stage");
+  if (fn && granule_bytes > 0) {
+    long long a = p->granule_bytes, b = granule_bytes;
+    while (b) { const long long t = a % b; a = b; b = t; }
+    const long long l = (long long)p->granule_bytes / a * granule_bytes;
+    const int factor = (int)(l / p->granule_bytes);
+    p->granule_bytes = (int)l;
+    p->if_per_granule *= factor;
+    p->pcm_per_granule *= factor;
+  }
+  p->hook = fn;
+  p->hook_ctx = ctx;
   return SDR_OK;
 }
 
@@ -783,6 +822,8 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   const int B = p->cfg.batch;
   const bool taps = p->keep_taps;
   int rc;
+  // the follower stage refuses the call before anything is enqueued
+  if (p->hook && (rc = p->hook(p->hook_ctx, 2, n_if, s))) return rc;
 
   // ---- K1 ----
   RfArgs ra{};
@@ -969,6 +1010,9 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
                                    p->tap_if_stride, (int)n_if);
     if ((rc = check_launch(p, "k_copy_rows"))) return rc;
   }
+
+  // ---- follower stage (RDS): reads this call's fm_demod before the carry moves on ----
+  if (p->hook && (rc = p->hook(p->hook_ctx, 0, n_if, s))) return rc;
 
   // ---- carry ----
   CarryArgs ca{};

@@ -1,0 +1,959 @@
+// rds.cu -- the RDS receiver chain on the device, attached to a batched pipeline.
+//
+// The reference has no C++ RDS path; what it has is the Python model
+// model/fmRDS.py:222-276 on model/fmSupportLib.py, which
+// works in double precision.  This file follows that model, stage for stage, in double
+// precision, from the pipeline's fm_demod (float, bit-identical to the C++ reference):
+//
+//   R1  k_rds_fir<151, float in>     channel band-pass 54-60 kHz            fmRDS.py:223
+//   R2  k_rds_fir<151, squared in>   x^2, carrier band-pass 113.5-114.5 kHz fmRDS.py:230-233
+//   R3  k_rds_pll                    PLL at 114 kHz, NCO I and Q (scale 0.5, 3pi/8),
+//                                    all-pass delay (75) and both mixers   fmRDS.py:227,236-241,251
+//   R4  k_rds_resample               rational resampler U/D, 101 taps per phase, gain U
+//                                                                           fmRDS.py:244,252
+//   R5  k_rds_fir<101>               root-raised-cosine filter, I and Q     fmRDS.py:248,254
+//   R6  k_rds_cdr                    clock/data recovery + Manchester decoding, one thread
+//                                    per (capture, block)                   fmRDS.py:257-268
+//   R7  k_rds_carry                  history prefixes for the next call
+//   host: differential decoding and the frame synchroniser (fmRDS.py:271-276) on the few
+//   bits per block that come back.
+//
+// Every row keeps the tail of the previous call in front of the current samples (the same
+// "history prefix" layout as the audio path), so a call may cover any whole number of RDS
+// blocks and the result does not depend on how a capture is cut into calls -- except for the
+// CDR, whose window is the block, as in the model (its state is re-created per block,
+// fmRDS.py:257-260).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sdr_b200.h"
+#include "common.cuh"
+#include "pipeline_view.h"
+
+using namespace sdr;
+
+namespace sdr {
+
+constexpr int RDS_T = 151;   // fmRDS.py:100 rds_taps
+constexpr int RDS_TP = 101;  // taps per resampler phase (fmRDS.py:59,71) and RRC taps (:61,73)
+constexpr int RDS_HC = 152;  // channel_filt history prefix: >= 150 (carrier FIR), >= 75 (all-pass)
+constexpr int RDS_HM = 104;  // mixer history prefix: the resampler reaches 100 samples back
+constexpr int RDS_HS = 104;  // resampler-output history prefix: the RRC reaches 100 back
+constexpr int RDS_DELAY = (RDS_T - 1) / 2;  // fmRDS.py:178 state_rds_allpass
+constexpr int RDS_CDR_START = 158;          // fmRDS.py:259 start_init
+constexpr int RDS_POLY_PITCH = 104;
+
+template <int T>
+struct DTaps {
+  double h[T];
+};
+
+// ---------------------------------------------------------------------------
+// R1/R2/R5: double-precision FIR, y[n] = sum_k h[k] f(x[n-k]).
+// One thread produces R consecutive outputs from a shared-memory window; the window is
+// stored in groups of R with one padding slot so the per-thread stride (R+1 doubles) keeps
+// the 64-bit loads of a half-warp on distinct bank pairs.  Taps are a __grid_constant__
+// parameter: after unrolling each one is a constant-bank operand of its DFMA.
+// ---------------------------------------------------------------------------
+struct RdsFirArgs {
+  const void *src[2];  // [B][src_stride]; z = 0/1 selects the row set (I / Q)
+  size_t src_stride;
+  int src_off;         // element of a row that holds sample 0 of this call (history before it)
+  const float *hist32; // INMODE 0 only: [B][hist_len] samples that precede sample 0
+  int hist_len;
+  double *dst[2];
+  size_t dst_stride;
+  int dst_off;
+  int n;
+  int outs_per_seg;
+};
+
+// INMODE 0: float input with a separate history; 1: double input, squared; 2: double input
+template <int T, int R, int NT, int INMODE>
+__global__ void __launch_bounds__(NT)
+k_rds_fir(const RdsFirArgs a, const __grid_constant__ DTaps<T> taps) {
+  constexpr int HALO = ((T - 1 + R - 1) / R) * R;
+  constexpr int TILE = NT * R;
+  constexpr int WIN = HALO + TILE;
+  __shared__ double xs[WIN + WIN / R + 1];
+  const int t = threadIdx.x;
+  const int b = blockIdx.y;
+  const int z = blockIdx.z;
+  const int o_begin = blockIdx.x * a.outs_per_seg;
+  const int o_end = min(o_begin + a.outs_per_seg, a.n);
+  const float *s32 = reinterpret_cast<const float *>(z ? a.src[1] : a.src[0]) + (size_t)b * a.src_stride + a.src_off;
+  const double *s64 = reinterpret_cast<const double *>(z ? a.src[1] : a.src[0]) + (size_t)b * a.src_stride + a.src_off;
+  const float *hist = INMODE == 0 ? a.hist32 + (size_t)b * a.hist_len : nullptr;
+  double *drow = (z ? a.dst[1] : a.dst[0]) + (size_t)b * a.dst_stride + a.dst_off;
+  for (int o0 = o_begin; o0 < o_end; o0 += TILE) {
+    __syncthreads();
+    for (int q = t; q < WIN; q += NT) {
+      const int i = o0 - HALO + q;
+      double v = 0.0;
+      if (i < a.n) {
+        if (INMODE == 0) {
+          if (i >= 0) v = (double)s32[i];
+          else if (i >= -a.hist_len) v = (double)hist[a.hist_len + i];
+        } else if (i >= -a.src_off) {
+          v = s64[i];
+          if (INMODE == 1) v = __dmul_rn(v, v);  // fmRDS.py:230
+        }
+      }
+      xs[q + q / R] = v;
+    }
+    __syncthreads();
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    const double *w = xs + (t * R + HALO) + (t * R + HALO) / R;
+#pragma unroll
+    for (int c = R - 1; c >= -(T - 1); --c) {
+      // window slot of sample (output 0 of this thread) + c, with the group padding
+      const int off = c + (c >= 0 ? c / R : -((-c + R - 1) / R));
+      const double v = w[off];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int k = r - c;
+        if (k >= 0 && k < T) acc[r] = fma(taps.h[k], v, acc[r]);
+      }
+    }
+    const int o = o0 + t * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (o + r < o_end) drow[o + r] = acc[r];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// R3: PLL + NCO (fmSupportLib.py:297-354) with the all-pass delay and the two mixers
+// (fmRDS.py:227,241,251) as its output stage.  Sequential per capture: one lane per capture.
+// ncoOut[0] of a call is the last NCO value of the previous call (state[4] / state[6]); the
+// mixers use ncoOut[0..N), i.e. the NCO delayed by one sample.
+// ---------------------------------------------------------------------------
+struct RdsPllArgs {
+  const double *carr;  // [B][carr_stride]
+  size_t carr_stride;
+  const double *chan;  // [B][chan_stride], sample 0 at chan_off
+  size_t chan_stride;
+  int chan_off;
+  double *mixI, *mixQ;  // [B][mix_stride], sample 0 at mix_off
+  size_t mix_stride;
+  int mix_off;
+  double *ncoI, *ncoQ;  // optional [B][nco_stride]: ncoOut[0..N] for the parity taps
+  size_t nco_stride;
+  double *state;  // [B][8]
+  int n, batch;
+  double freq, Fs, ncoScale, phaseAdjust, normBandwidth;
+};
+
+static __global__ void k_rds_pll(const RdsPllArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.batch) return;
+  // fmSupportLib.py:303-309
+  const double Kp = __dmul_rn(a.normBandwidth, 2.666);
+  const double Ki = __dmul_rn(__dmul_rn(a.normBandwidth, a.normBandwidth), 3.555);
+  double *st = a.state + (size_t)b * 8;
+  double integrator = st[0], phaseEst = st[1], fbI = st[2], fbQ = st[3];
+  double outI = st[4], trigOffset = st[5], outQ = st[6];
+  const double *in = a.carr + (size_t)b * a.carr_stride;
+  const double *ap = a.chan + (size_t)b * a.chan_stride + a.chan_off - RDS_DELAY;
+  double *mI = a.mixI + (size_t)b * a.mix_stride + a.mix_off;
+  double *mQ = a.mixQ + (size_t)b * a.mix_stride + a.mix_off;
+  double *nI = a.ncoI ? a.ncoI + (size_t)b * a.nco_stride : nullptr;
+  double *nQ = a.ncoQ ? a.ncoQ + (size_t)b * a.nco_stride : nullptr;
+  // fmSupportLib.py:340: 2*pi*(freq/Fs), left to right
+  const double w = __dmul_rn(__dmul_rn(2.0, 3.141592653589793), __ddiv_rn(a.freq, a.Fs));
+  // each lane walks its own rows, so every load is its own line: fetch ahead of the recurrence
+  double xq[4], aq[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xq[i] = i < a.n ? in[i] : 0.0;
+    aq[i] = i < a.n ? ap[i] : 0.0;
+  }
+  if (nI) nI[0] = outI;
+  if (nQ) nQ[0] = outQ;
+  for (int k = 0; k < a.n; ++k) {
+    const double x = xq[0], d = aq[0];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      xq[i] = xq[i + 1];
+      aq[i] = aq[i + 1];
+    }
+    xq[3] = (k + 4 < a.n) ? in[k + 4] : 0.0;
+    aq[3] = (k + 4 < a.n) ? ap[k + 4] : 0.0;
+    // mixers: rds_PLL[:-1] * rds_allpass * 2 (fmRDS.py:241,251)
+    mI[k] = __dmul_rn(__dmul_rn(outI, d), 2.0);
+    mQ[k] = __dmul_rn(__dmul_rn(outQ, d), 2.0);
+    // fmSupportLib.py:324-348
+    const double errorI = __dmul_rn(x, fbI);
+    const double errorQ = __dmul_rn(x, -fbQ);
+    const double errorD = atan2(errorQ, errorI);
+    integrator = __dadd_rn(integrator, __dmul_rn(Ki, errorD));
+    phaseEst = __dadd_rn(__dadd_rn(phaseEst, __dmul_rn(Kp, errorD)), integrator);
+    trigOffset = __dadd_rn(trigOffset, 1.0);
+    const double trigArg = __dadd_rn(__dmul_rn(w, trigOffset), phaseEst);
+    sincos(trigArg, &fbQ, &fbI);
+    sincos(__dadd_rn(__dmul_rn(trigArg, a.ncoScale), a.phaseAdjust), &outQ, &outI);
+    if (nI) nI[k + 1] = outI;
+    if (nQ) nQ[k + 1] = outQ;
+  }
+  st[0] = integrator;
+  st[1] = phaseEst;
+  st[2] = fbI;
+  st[3] = fbQ;
+  st[4] = outI;
+  st[5] = trigOffset;
+  st[6] = outQ;
+}
+
+// ---------------------------------------------------------------------------
+// R4: rational resampler (fmSupportLib.py:388-407): output j takes phase (jD mod U) of the
+// 101*U-tap low-pass and the 101 inputs ending at floor(jD/U); gain U.  poly is the filter
+// regrouped by phase, [U][RDS_POLY_PITCH].  One thread per output, I and Q together.
+// ---------------------------------------------------------------------------
+struct RdsResampleArgs {
+  const double *mixI, *mixQ;
+  size_t mix_stride;
+  int mix_off;
+  double *rsI, *rsQ;
+  size_t rs_stride;
+  int rs_off;
+  const double *poly;
+  int U, D, n_out;
+};
+
+static __global__ void __launch_bounds__(128) k_rds_resample(const RdsResampleArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (j >= a.n_out) return;
+  const long long m = (long long)j * a.D;
+  const int phase = (int)(m % a.U);
+  const long long base = m / a.U;
+  const double *h = a.poly + (size_t)phase * RDS_POLY_PITCH;
+  const double *xi = a.mixI + (size_t)b * a.mix_stride + a.mix_off + base;
+  const double *xq = a.mixQ + (size_t)b * a.mix_stride + a.mix_off + base;
+  double accI = 0.0, accQ = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < RDS_TP; ++k) {
+    const double hk = __ldg(h + k);
+    accI = fma(hk, xi[-k], accI);
+    accQ = fma(hk, xq[-k], accQ);
+  }
+  a.rsI[(size_t)b * a.rs_stride + a.rs_off + j] = __dmul_rn(accI, (double)a.U);
+  a.rsQ[(size_t)b * a.rs_stride + a.rs_off + j] = __dmul_rn(accQ, (double)a.U);
+}
+
+// ---------------------------------------------------------------------------
+// R6: clock and data recovery + Manchester decoding (fmSupportLib.py:103-222), driven as in
+// fmRDS.py:257-268: per block, pair = (0,0), start = 158, prev_size = 0 (which makes the
+// model's "pair with the previous block" branch, :117-125, dead).  One thread per
+// (capture, block).  The model builds the whole array of sampling points, then walks the
+// pairs; a pair of equal signs that cannot be repaired by inverting a small sample moves
+// the start by one symbol and starts over.  Pair decisions only depend on the two samples of
+// the pair, so one pass can decide and emit bits while it samples; a restart rewinds the
+// output to the bits the restarts themselves produced.
+// Where the model would never leave its loop (a whole pass without a single pair of opposite
+// signs, e.g. fewer than two sampling points left), the pass is accepted as it stands.
+// ---------------------------------------------------------------------------
+struct RdsCdrArgs {
+  const double *rrc;  // [B][rrc_stride]
+  size_t rrc_stride;
+  int block_out;      // samples per block
+  int n_blocks;       // blocks in this call
+  int sps;
+  long long first_block;  // index of this call's first block since reset (block_count, :157)
+  uint8_t *bits;      // [B][blocks_cap][bits_cap]
+  int *counts;        // [B][blocks_cap]
+  int blocks_cap, bits_cap, cursor;
+  int batch;
+};
+
+static __global__ void k_rds_cdr(const RdsCdrArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.batch * a.n_blocks) return;
+  const int b = idx / a.n_blocks, blk = idx % a.n_blocks;
+  const double *x = a.rrc + (size_t)b * a.rrc_stride + (size_t)blk * a.block_out;
+  const int n = a.block_out, sps = a.sps;
+  uint8_t *out = a.bits + ((size_t)b * a.blocks_cap + a.cursor + blk) * a.bits_cap;
+  const bool first_ever = (a.first_block + blk) == 0;
+  const double limit = 0.3;
+  int start = RDS_CDR_START;
+  int n_prefix = 0;
+  double pair0 = 0.0;
+  int nb = 0;
+  for (;;) {
+    double p1 = 0.0, p2 = 0.0;  // the two previous sampling points (before pair repairs)
+    double first = 0.0, s0 = 0.0;
+    bool restart = false;
+    nb = n_prefix;
+    int k = 0;
+    for (int i = start; i < n; i += sps, ++k) {
+      const double xi = x[i];
+      double s = xi;
+      // :128-136 a third consecutive high (or low) is inverted
+      if (k >= 2 && ((p2 > 0 && p1 > 0 && xi > 0) || (p2 < 0 && p1 < 0 && xi < 0))) s = -xi;
+      p2 = p1;
+      p1 = s;
+      if ((k & 1) == 0) {
+        first = s;
+        if (k == 0) s0 = s;
+        continue;
+      }
+      double u = first, v = s;
+      if ((u < 0 && v < 0) || (u > 0 && v > 0)) {  // :147
+        if (fabs(u) < limit) u = -u;                // :151-153
+        else if (fabs(v) < limit) v = -v;           // :154-156
+        else {                                      // :158-172
+          restart = true;
+          break;
+        }
+      }
+      if (k == 1) s0 = u;  // samples[0] as the model sees it at a later restart
+      // manchestering, :203-222
+      uint8_t bit = 0;
+      if (u > 0 && v < 0) bit = 1;
+      if (nb < a.bits_cap) out[nb] = bit;
+      ++nb;
+    }
+    if (!restart) break;
+    start += sps;
+    if (!first_ever) {  // :160-167: symbolToBit looks at pair[0] only (:228-236)
+      const uint8_t bit = pair0 > 0 ? 1 : 0;
+      if (n_prefix < a.bits_cap) out[n_prefix] = bit;
+      ++n_prefix;
+      pair0 = s0;
+    }
+  }
+  a.counts[(size_t)b * a.blocks_cap + a.cursor + blk] = min(nb, a.bits_cap);
+}
+
+// ---------------------------------------------------------------------------
+// R7: move the tails into the history prefixes; keep the last demod samples.
+// ---------------------------------------------------------------------------
+struct RdsCarryArgs {
+  double *rows[5];
+  size_t strides[5];
+  int src_off[5];  // first element to copy
+  int len[5];
+  const float *demod;  // this call's fm_demod, sample 0 at demod_off
+  size_t demod_stride;
+  int demod_off;
+  int n_if;
+  float *hist32;  // [B][hist_len]
+  int hist_len;
+};
+
+static __global__ void k_rds_carry(const RdsCarryArgs c) {
+  __shared__ double stage[RDS_HC + 8];
+  const int b = blockIdx.x, t = threadIdx.x;
+  for (int r = 0; r < 5; ++r) {
+    if (!c.rows[r]) continue;
+    double *row = c.rows[r] + (size_t)b * c.strides[r];
+    for (int i = t; i < c.len[r]; i += blockDim.x) stage[i] = row[c.src_off[r] + i];
+    __syncthreads();
+    for (int i = t; i < c.len[r]; i += blockDim.x) row[i] = stage[i];
+    __syncthreads();
+  }
+  // last hist_len samples of (old history ++ this call's fm_demod)
+  float *fs = reinterpret_cast<float *>(stage);
+  float *h = c.hist32 + (size_t)b * c.hist_len;
+  const float *d = c.demod + (size_t)b * c.demod_stride + c.demod_off;
+  for (int i = t; i < c.hist_len; i += blockDim.x) {
+    const int j = c.n_if - c.hist_len + i;
+    fs[i] = j >= 0 ? d[j] : h[c.hist_len + j];
+  }
+  __syncthreads();
+  for (int i = t; i < c.hist_len; i += blockDim.x) h[i] = fs[i];
+}
+
+// ---------------------------------------------------------------------------
+// host: filter design in double, like the model
+// ---------------------------------------------------------------------------
+// fmSupportLib.py:358-372
+static std::vector<double> rds_band_pass(int ntaps, double Fs, double Fb, double Fe) {
+  std::vector<double> h((size_t)ntaps);
+  const double center = ((Fe + Fb) / 2) / (Fs / 2);
+  const double pass = (Fe - Fb) / (Fs / 2);
+  const double mid = (double)(ntaps - 1) / 2;
+  for (int i = 0; i < ntaps; ++i) {
+    double v = pass;
+    if ((double)i != mid) {
+      const double arg = M_PI * pass / 2 * ((double)i - mid);
+      v = pass * (std::sin(arg) / arg);
+    }
+    v = v * std::cos((double)i * M_PI * center);
+    const double win = std::sin((double)i * M_PI / (double)ntaps);
+    h[(size_t)i] = v * (win * win);
+  }
+  return h;
+}
+
+// fmSupportLib.py:376-385
+static std::vector<double> rds_low_pass(int ntaps, double Fs, double Fc) {
+  std::vector<double> h((size_t)ntaps);
+  const double norm = Fc / (Fs / 2);
+  const double mid = (double)(ntaps - 1) / 2;
+  for (int i = 0; i < ntaps; ++i) {
+    double v = norm;
+    if ((double)i != mid) {
+      const double arg = M_PI * norm * ((double)i - mid);
+      v = norm * (std::sin(arg) / arg);
+    }
+    const double win = std::sin((double)i * M_PI / (double)ntaps);
+    h[(size_t)i] = v * (win * win);
+  }
+  return h;
+}
+
+// fmSupportLib.py:251-287
+static std::vector<double> rds_rrc(double Fs, int ntaps) {
+  std::vector<double> h((size_t)ntaps);
+  const double Ts = 1 / 2375.0, beta = 0.90;
+  for (int k = 0; k < ntaps; ++k) {
+    const double t = ((double)k - (double)ntaps / 2) / Fs;
+    double v;
+    if (t == 0.0) {
+      v = 1.0 + beta * ((4 / M_PI) - 1);
+    } else if (t == -Ts / (4 * beta) || t == Ts / (4 * beta)) {
+      v = (beta / std::sqrt(2.0)) * (((1 + 2 / M_PI) * std::sin(M_PI / (4 * beta))) +
+                                     ((1 - 2 / M_PI) * std::cos(M_PI / (4 * beta))));
+    } else {
+      const double q = 4 * beta * t / Ts;
+      v = (std::sin(M_PI * t * (1 - beta) / Ts) + 4 * beta * (t / Ts) * std::cos(M_PI * t * (1 + beta) / Ts)) /
+          (M_PI * t * (1 - q * q) / Ts);
+    }
+    h[(size_t)k] = v;
+  }
+  return h;
+}
+
+template <typename T>
+struct RBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (!count) return SDR_OK;
+    SDR_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    SDR_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    return SDR_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~RBuf() { release(); }
+};
+
+}  // namespace sdr
+
+struct sdr_rds {
+  sdr_pipeline *pipe = nullptr;
+  DemodView view{};
+  int mode = 0, U = 0, D = 0, sps = 0;
+  int block_if = 0, block_out = 0, block_bytes = 0;
+  int blocks_cap = 0, bits_cap = 0;
+  size_t cap_if = 0, cap_out = 0;
+  size_t chan_stride = 0, carr_stride = 0, mix_stride = 0, rs_stride = 0, rrc_stride = 0, nco_stride = 0;
+  DTaps<RDS_T> h_chan{}, h_carr{};
+  DTaps<RDS_TP> h_rrc{};
+  RBuf<double> poly, chan, carr, mixI, mixQ, rsI, rsQ, rrcI, rrcQ, ncoI, ncoQ, pll;
+  RBuf<float> hist32;
+  RBuf<uint8_t> bits;
+  RBuf<int> counts;
+  bool keep_nco = false;
+  int cursor = 0;             // blocks waiting in bits/counts
+  long long blocks_done = 0;  // since reset
+  size_t last_n_if = 0;
+  cudaStream_t last_stream = nullptr;
+  // host mirror of the pending results + the frame synchroniser's carried bits per capture
+  bool mirrored = true;
+  std::vector<uint8_t> h_bits;
+  std::vector<int> h_counts;
+  std::vector<std::vector<uint8_t>> decoded;  // fmRDS.py:272-276 decoded_data
+  std::vector<std::string> offsets;           // per capture, one letter per pending block
+  std::vector<std::vector<uint8_t>> diff;     // per capture, differential bits of pending blocks
+};
+
+static int rds_reset_device(sdr_rds *r) {
+  SDR_CUDA(cudaSetDevice(r->view.device));
+  const size_t B = (size_t)r->view.batch;
+  double *rows[] = {r->chan.p, r->carr.p, r->mixI.p, r->mixQ.p, r->rsI.p, r->rsQ.p, r->rrcI.p, r->rrcQ.p};
+  size_t sizes[] = {r->chan.n, r->carr.n, r->mixI.n, r->mixQ.n, r->rsI.n, r->rsQ.n, r->rrcI.n, r->rrcQ.n};
+  for (int i = 0; i < 8; ++i)
+    if (rows[i]) SDR_CUDA(cudaMemset(rows[i], 0, sizes[i] * sizeof(double)));
+  SDR_CUDA(cudaMemset(r->hist32.p, 0, r->hist32.n * sizeof(float)));
+  // fmRDS.py:175 state_rds_pll = [0, 0, 1, 0, 1, 0, 1]
+  std::vector<double> st(B * 8, 0.0);
+  for (size_t b = 0; b < B; ++b) st[b * 8 + 2] = st[b * 8 + 4] = st[b * 8 + 6] = 1.0;
+  SDR_CUDA(cudaMemcpy(r->pll.p, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+  r->cursor = 0;
+  r->blocks_done = 0;
+  r->last_n_if = 0;
+  r->mirrored = true;
+  for (auto &d : r->decoded) d.clear();
+  for (auto &o : r->offsets) o.clear();
+  for (auto &d : r->diff) d.clear();
+  std::fill(r->h_counts.begin(), r->h_counts.end(), 0);
+  return SDR_OK;
+}
+
+static int segs_for(int n, int tile, int batch, int z, int *outs_per_seg) {
+  const int n_tiles = (n + tile - 1) / tile;
+  int want = (1184 + batch * z - 1) / (batch * z);  // ~ 148 SMs x 8 CTAs
+  want = std::max(1, std::min(want, n_tiles));
+  const int per = (n_tiles + want - 1) / want;
+  *outs_per_seg = per * tile;
+  return (n_tiles + per - 1) / per;
+}
+
+static int rds_validate(const sdr_rds *r, size_t n_if) {
+  if (n_if % (size_t)r->block_if) return fail(SDR_ERR_INVALID, "RDS: the call is not a whole number of RDS blocks");
+  if (n_if > r->cap_if) return fail(SDR_ERR_CAPACITY, "RDS: call exceeds the capacity fixed at create time");
+  if (r->cursor + (int)(n_if / (size_t)r->block_if) > r->blocks_cap)
+    return fail(SDR_ERR_CAPACITY, "RDS: result buffer full; call sdr_rds_read, then sdr_rds_discard");
+  return SDR_OK;
+}
+
+static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
+  if (n_if == 0) return SDR_OK;
+  int rc = rds_validate(r, n_if);
+  if (rc) return rc;
+  const int n_blocks = (int)(n_if / (size_t)r->block_if);
+  const int B = r->view.batch;
+  const int n = (int)n_if;
+  const int n_out = (int)((long long)n_if * r->U / r->D);
+  sdr_pipeline *p = r->pipe;
+  int ops;
+  constexpr int R = 8, NT = 128, TILE = R * NT;
+
+  {  // R1
+    RdsFirArgs a{};
+    a.src[0] = r->view.demod;
+    a.src_stride = r->view.stride;
+    a.src_off = r->view.off;
+    a.hist32 = r->hist32.p;
+    a.hist_len = RDS_T - 1;
+    a.dst[0] = r->chan.p;
+    a.dst_stride = r->chan_stride;
+    a.dst_off = RDS_HC;
+    a.n = n;
+    dim3 grid(segs_for(n, TILE, B, 1, &ops), B, 1);
+    a.outs_per_seg = ops;
+    sdr_prof_begin(p, "k_rds_fir_channel", s);
+    k_rds_fir<RDS_T, R, NT, 0><<<grid, NT, 0, s>>>(a, r->h_chan);
+    if ((rc = sdr_check_launch(p, "k_rds_fir_channel"))) return rc;
+  }
+  {  // R2
+    RdsFirArgs a{};
+    a.src[0] = r->chan.p;
+    a.src_stride = r->chan_stride;
+    a.src_off = RDS_HC;
+    a.dst[0] = r->carr.p;
+    a.dst_stride = r->carr_stride;
+    a.dst_off = 0;
+    a.n = n;
+    dim3 grid(segs_for(n, TILE, B, 1, &ops), B, 1);
+    a.outs_per_seg = ops;
+    sdr_prof_begin(p, "k_rds_fir_carrier", s);
+    k_rds_fir<RDS_T, R, NT, 1><<<grid, NT, 0, s>>>(a, r->h_carr);
+    if ((rc = sdr_check_launch(p, "k_rds_fir_carrier"))) return rc;
+  }
+  {  // R3
+    RdsPllArgs a{};
+    a.carr = r->carr.p;
+    a.carr_stride = r->carr_stride;
+    a.chan = r->chan.p;
+    a.chan_stride = r->chan_stride;
+    a.chan_off = RDS_HC;
+    a.mixI = r->mixI.p;
+    a.mixQ = r->mixQ.p;
+    a.mix_stride = r->mix_stride;
+    a.mix_off = RDS_HM;
+    a.ncoI = r->keep_nco ? r->ncoI.p : nullptr;
+    a.ncoQ = r->keep_nco ? r->ncoQ.p : nullptr;
+    a.nco_stride = r->nco_stride;
+    a.state = r->pll.p;
+    a.n = n;
+    a.batch = B;
+    // fmRDS.py:236-237
+    a.freq = 114e3;
+    a.Fs = (double)r->view.if_Fs;
+    a.ncoScale = 0.5;
+    a.phaseAdjust = 3 * M_PI / 8;
+    a.normBandwidth = 0.002;
+    sdr_prof_begin(p, "k_rds_pll", s);
+    k_rds_pll<<<(B + 31) / 32, 32, 0, s>>>(a);
+    if ((rc = sdr_check_launch(p, "k_rds_pll"))) return rc;
+  }
+  {  // R4
+    RdsResampleArgs a{};
+    a.mixI = r->mixI.p;
+    a.mixQ = r->mixQ.p;
+    a.mix_stride = r->mix_stride;
+    a.mix_off = RDS_HM;
+    a.rsI = r->rsI.p;
+    a.rsQ = r->rsQ.p;
+    a.rs_stride = r->rs_stride;
+    a.rs_off = RDS_HS;
+    a.poly = r->poly.p;
+    a.U = r->U;
+    a.D = r->D;
+    a.n_out = n_out;
+    dim3 grid((n_out + 127) / 128, B);
+    sdr_prof_begin(p, "k_rds_resample", s);
+    k_rds_resample<<<grid, 128, 0, s>>>(a);
+    if ((rc = sdr_check_launch(p, "k_rds_resample"))) return rc;
+  }
+  {  // R5
+    RdsFirArgs a{};
+    a.src[0] = r->rsI.p;
+    a.src[1] = r->rsQ.p;
+    a.src_stride = r->rs_stride;
+    a.src_off = RDS_HS;
+    a.dst[0] = r->rrcI.p;
+    a.dst[1] = r->rrcQ.p;
+    a.dst_stride = r->rrc_stride;
+    a.dst_off = 0;
+    a.n = n_out;
+    dim3 grid(segs_for(n_out, TILE, B, 2, &ops), B, 2);
+    a.outs_per_seg = ops;
+    sdr_prof_begin(p, "k_rds_fir_rrc", s);
+    k_rds_fir<RDS_TP, R, NT, 2><<<grid, NT, 0, s>>>(a, r->h_rrc);
+    if ((rc = sdr_check_launch(p, "k_rds_fir_rrc"))) return rc;
+  }
+  {  // R6
+    RdsCdrArgs a{};
+    a.rrc = r->rrcI.p;
+    a.rrc_stride = r->rrc_stride;
+    a.block_out = r->block_out;
+    a.n_blocks = n_blocks;
+    a.sps = r->sps;
+    a.first_block = r->blocks_done;
+    a.bits = r->bits.p;
+    a.counts = r->counts.p;
+    a.blocks_cap = r->blocks_cap;
+    a.bits_cap = r->bits_cap;
+    a.cursor = r->cursor;
+    a.batch = B;
+    const int total = B * n_blocks;
+    sdr_prof_begin(p, "k_rds_cdr", s);
+    k_rds_cdr<<<(total + 63) / 64, 64, 0, s>>>(a);
+    if ((rc = sdr_check_launch(p, "k_rds_cdr"))) return rc;
+  }
+  {  // R7
+    RdsCarryArgs c{};
+    double *rows[5] = {r->chan.p, r->mixI.p, r->mixQ.p, r->rsI.p, r->rsQ.p};
+    const size_t strides[5] = {r->chan_stride, r->mix_stride, r->mix_stride, r->rs_stride, r->rs_stride};
+    const int lens[5] = {RDS_HC, RDS_HM, RDS_HM, RDS_HS, RDS_HS};
+    const int srcs[5] = {n, n, n, n_out, n_out};
+    for (int i = 0; i < 5; ++i) {
+      c.rows[i] = rows[i];
+      c.strides[i] = strides[i];
+      c.len[i] = lens[i];
+      c.src_off[i] = srcs[i];
+    }
+    c.demod = r->view.demod;
+    c.demod_stride = r->view.stride;
+    c.demod_off = r->view.off;
+    c.n_if = n;
+    c.hist32 = r->hist32.p;
+    c.hist_len = RDS_T - 1;
+    sdr_prof_begin(p, "k_rds_carry", s);
+    k_rds_carry<<<B, 128, 0, s>>>(c);
+    if ((rc = sdr_check_launch(p, "k_rds_carry"))) return rc;
+  }
+  r->cursor += n_blocks;
+  r->blocks_done += n_blocks;
+  r->last_n_if = n_if;
+  r->last_stream = s;
+  r->mirrored = false;
+  return SDR_OK;
+}
+
+static int rds_hook(void *ctx, int event, size_t n_if, cudaStream_t s) {
+  sdr_rds *r = static_cast<sdr_rds *>(ctx);
+  if (event == 1) return rds_reset_device(r);
+  if (event == 2) return rds_validate(r, n_if);
+  return rds_process(r, n_if, s);
+}
+
+// ---------------------------------------------------------------------------
+// host bit layer: differential decoding and the frame synchroniser
+// ---------------------------------------------------------------------------
+// fmSupportLib.py:32-57, one 10-bit mask per row (bit 9 = first column)
+static const uint16_t kParityRows[26] = {
+    0x200, 0x100, 0x080, 0x040, 0x020, 0x010, 0x008, 0x004, 0x002, 0x001, 0x2DC, 0x16E, 0x0B7,
+    0x287, 0x39F, 0x313, 0x355, 0x376, 0x1BB, 0x201, 0x3DC, 0x1EE, 0x0F7, 0x2A7, 0x38F, 0x31B};
+
+// fmSupportLib.py:14-27 and :62-91
+static char rds_offset_of(const uint8_t *d) {
+  uint16_t s = 0;
+  for (int i = 0; i < 26; ++i)
+    if (d[i] == 1) s ^= kParityRows[i];
+  switch (s) {
+    case 0x3D8: return 'A';  // 1111011000
+    case 0x3D4: return 'B';  // 1111010100
+    case 0x25C: return 'C';  // 1001011100
+    case 0x3CC: return 'c';  // 1111001100 (C')
+    case 0x258: return 'D';  // 1001011000
+  }
+  return ' ';
+}
+
+// fmSupportLib.py:30-100
+static char rds_framesync(const std::vector<uint8_t> &d, size_t *consumed) {
+  const long n = (long)d.size();
+  long pos = 0;
+  char type = ' ';
+  while (pos < n - 26) {
+    const char o = rds_offset_of(d.data() + pos);
+    if (o != ' ') {
+      type = o;
+      if (n - (pos + 26) < 26) break;
+      pos += 26;
+    } else {
+      pos += 1;
+    }
+  }
+  const long idx = type == ' ' ? pos : pos + 26;
+  *consumed = (size_t)std::min(std::max(idx, 0L), n);
+  return type;
+}
+
+// Bring the pending blocks to the host and run the bit layer for the ones not seen yet.
+static int rds_mirror(sdr_rds *r) {
+  if (r->mirrored) return SDR_OK;
+  SDR_CUDA(cudaSetDevice(r->view.device));
+  SDR_CUDA(cudaStreamSynchronize(r->last_stream));
+  SDR_CUDA(cudaMemcpy(r->h_bits.data(), r->bits.p, r->h_bits.size(), cudaMemcpyDeviceToHost));
+  SDR_CUDA(cudaMemcpy(r->h_counts.data(), r->counts.p, r->h_counts.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  const int B = r->view.batch;
+  for (int b = 0; b < B; ++b) {
+    std::string &offs = r->offsets[(size_t)b];
+    for (int blk = (int)offs.size(); blk < r->cursor; ++blk) {
+      const int cnt = r->h_counts[(size_t)b * r->blocks_cap + blk];
+      const uint8_t *bits = r->h_bits.data() + ((size_t)b * r->blocks_cap + blk) * r->bits_cap;
+      std::vector<uint8_t> &dec = r->decoded[(size_t)b];
+      std::vector<uint8_t> &df = r->diff[(size_t)b];
+      // fmSupportLib.py:241-249: the first bit of a block is taken as it is
+      for (int i = 0; i < cnt; ++i) {
+        const uint8_t v = i == 0 ? bits[0] : (uint8_t)(bits[i] != bits[i - 1]);
+        dec.push_back(v);
+        df.push_back(v);
+      }
+      size_t used = 0;
+      offs.push_back(rds_framesync(dec, &used));  // fmRDS.py:275
+      dec.erase(dec.begin(), dec.begin() + (long)used);  // fmRDS.py:276
+    }
+  }
+  r->mirrored = true;
+  return SDR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rds **out) {
+  if (!p || !out) return fail(SDR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  sdr_rds *r = new (std::nothrow) sdr_rds();
+  if (!r) return fail(SDR_ERR_NOMEM, "out of host memory");
+  int rc = pipeline_view(p, &r->view);
+  if (rc) { delete r; return rc; }
+  r->pipe = p;
+  r->mode = r->view.mode;
+  // fmRDS.py:55-75: RDS is defined for modes 0 and 2 only
+  if (r->mode == 0) { r->U = 247; r->D = 960; r->sps = 26; }
+  else if (r->mode == 2) { r->U = 817; r->D = 1920; r->sps = 43; }
+  else { delete r; return fail(SDR_ERR_INVALID, "RDS is defined for modes 0 and 2 only (fmRDS.py:55-75)"); }
+  // fmRDS.py:149-152: block = 2*10*5*960*2 bytes (mode 0) / 10*800*1920*2 bytes (mode 2)
+  const int model_block_if = r->mode == 0 ? 9600 : 1536000;
+  r->block_if = (cfg && cfg->block_if > 0) ? cfg->block_if : model_block_if;
+  // whole resampler outputs and whole audio granules per block
+  if (r->block_if % 9600) { delete r; return fail(SDR_ERR_INVALID, "RDS block must be a multiple of 9600 IF samples"); }
+  r->block_out = (int)((long long)r->block_if * r->U / r->D);
+  r->block_bytes = r->block_if * r->view.rf_decim * 2;
+  if ((size_t)r->block_if > r->view.cap_if) {
+    delete r;
+    return fail(SDR_ERR_CAPACITY, "pipeline max_bytes_per_channel is smaller than one RDS block");
+  }
+  if (r->block_out <= RDS_CDR_START) { delete r; return fail(SDR_ERR_INVALID, "RDS block too short for the CDR"); }
+  SDR_CUDA(cudaSetDevice(r->view.device));
+  const size_t B = (size_t)r->view.batch;
+  r->cap_if = r->view.cap_if / (size_t)r->block_if * (size_t)r->block_if;
+  r->cap_out = r->cap_if * (size_t)r->U / (size_t)r->D;
+  const int blocks_per_call = (int)(r->cap_if / (size_t)r->block_if);
+  r->blocks_cap = (cfg && cfg->max_pending_blocks > 0) ? cfg->max_pending_blocks : std::max(16, 2 * blocks_per_call);
+  r->blocks_cap = std::max(r->blocks_cap, blocks_per_call);
+  r->bits_cap = r->block_out / r->sps + 4;
+  r->keep_nco = cfg && cfg->keep_nco;
+  auto up = [](size_t v) { return (v + 3) / 4 * 4; };
+  r->chan_stride = up(RDS_HC + r->cap_if);
+  r->carr_stride = up(r->cap_if);
+  r->mix_stride = up(RDS_HM + r->cap_if);
+  r->rs_stride = up(RDS_HS + r->cap_out);
+  r->rrc_stride = up(r->cap_out);
+  r->nco_stride = up(r->cap_if + 1);
+  // filters (fmRDS.py:122-125)
+  const double if_Fs = (double)r->view.if_Fs;
+  std::vector<double> hc = rds_band_pass(RDS_T, if_Fs, 54e3, 60e3);
+  std::vector<double> hk = rds_band_pass(RDS_T, if_Fs, 113.5e3, 114.5e3);
+  std::vector<double> hr = rds_low_pass(RDS_TP * r->U, if_Fs * r->U, 3e3);
+  std::vector<double> hq = rds_rrc(2375.0 * r->sps, RDS_TP);
+  std::memcpy(r->h_chan.h, hc.data(), sizeof(r->h_chan.h));
+  std::memcpy(r->h_carr.h, hk.data(), sizeof(r->h_carr.h));
+  std::memcpy(r->h_rrc.h, hq.data(), sizeof(r->h_rrc.h));
+  std::vector<double> poly((size_t)r->U * RDS_POLY_PITCH, 0.0);
+  for (int ph = 0; ph < r->U; ++ph)
+    for (int k = 0; k < RDS_TP; ++k) poly[(size_t)ph * RDS_POLY_PITCH + k] = hr[(size_t)ph + (size_t)k * r->U];
+  bool ok = !r->poly.alloc(poly.size()) && !r->chan.alloc(B * r->chan_stride) &&
+            !r->carr.alloc(B * r->carr_stride) && !r->mixI.alloc(B * r->mix_stride) &&
+            !r->mixQ.alloc(B * r->mix_stride) && !r->rsI.alloc(B * r->rs_stride) &&
+            !r->rsQ.alloc(B * r->rs_stride) && !r->rrcI.alloc(B * r->rrc_stride) &&
+            !r->rrcQ.alloc(B * r->rrc_stride) && !r->pll.alloc(B * 8) &&
+            !r->hist32.alloc(B * (RDS_T - 1)) &&
+            !r->bits.alloc(B * (size_t)r->blocks_cap * (size_t)r->bits_cap) &&
+            !r->counts.alloc(B * (size_t)r->blocks_cap);
+  if (ok && r->keep_nco) ok = !r->ncoI.alloc(B * r->nco_stride) && !r->ncoQ.alloc(B * r->nco_stride);
+  if (!ok) { delete r; return SDR_ERR_NOMEM; }
+  if (cudaMemcpy(r->poly.p, poly.data(), poly.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete r;
+    return fail(SDR_ERR_CUDA, "RDS: uploading the polyphase table failed");
+  }
+  r->h_bits.assign(B * (size_t)r->blocks_cap * (size_t)r->bits_cap, 0);
+  r->h_counts.assign(B * (size_t)r->blocks_cap, 0);
+  r->decoded.assign(B, {});
+  r->offsets.assign(B, {});
+  r->diff.assign(B, {});
+  if ((rc = rds_reset_device(r)) || (rc = pipeline_set_hook(p, rds_hook, r, r->block_bytes))) {
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return SDR_OK;
+}
+
+extern "C" int sdr_rds_destroy(sdr_rds *r) {
+  if (!r) return SDR_OK;
+  cudaSetDevice(r->view.device);
+  cudaDeviceSynchronize();
+  pipeline_set_hook(r->pipe, nullptr, nullptr, 0);
+  delete r;
+  return SDR_OK;
+}
+
+extern "C" int sdr_rds_info(const sdr_rds *r, sdr_rds_info_t *out) {
+  if (!r || !out) return fail(SDR_ERR_INVALID, "null argument");
+  out->upsamp = r->U;
+  out->decim = r->D;
+  out->samples_per_symbol = r->sps;
+  out->block_if = r->block_if;
+  out->block_out = r->block_out;
+  out->block_bytes = r->block_bytes;
+  out->max_pending_blocks = r->blocks_cap;
+  out->max_bits_per_block = r->bits_cap;
+  return SDR_OK;
+}
+
+extern "C" int sdr_rds_pending(sdr_rds *r, size_t *n_blocks) {
+  if (!r || !n_blocks) return fail(SDR_ERR_INVALID, "null argument");
+  *n_blocks = (size_t)r->cursor;
+  return SDR_OK;
+}
+
+extern "C" int sdr_rds_read(sdr_rds *r, int channel, uint8_t *cdr_bits, uint8_t *diff_bits, size_t bits_cap,
+                            size_t *n_bits, int *bit_counts, char *offsets, size_t blocks_cap,
+                            size_t *n_blocks) {
+  if (!r) return fail(SDR_ERR_INVALID, "null argument");
+  if (channel < 0 || channel >= r->view.batch) return fail(SDR_ERR_INVALID, "channel out of range");
+  int rc = rds_mirror(r);
+  if (rc) return rc;
+  const size_t nb = (size_t)r->cursor;
+  size_t total = 0;
+  for (size_t blk = 0; blk < nb; ++blk) total += (size_t)r->h_counts[(size_t)channel * r->blocks_cap + blk];
+  if (n_bits) *n_bits = total;
+  if (n_blocks) *n_blocks = nb;
+  if ((cdr_bits || diff_bits) && bits_cap < total) return fail(SDR_ERR_CAPACITY, "bit buffer too small");
+  if ((bit_counts || offsets) && blocks_cap < nb) return fail(SDR_ERR_CAPACITY, "block buffer too small");
+  size_t w = 0;
+  for (size_t blk = 0; blk < nb; ++blk) {
+    const int cnt = r->h_counts[(size_t)channel * r->blocks_cap + blk];
+    if (cdr_bits)
+      std::memcpy(cdr_bits + w, r->h_bits.data() + ((size_t)channel * r->blocks_cap + blk) * r->bits_cap, (size_t)cnt);
+    if (bit_counts) bit_counts[blk] = cnt;
+    w += (size_t)cnt;
+  }
+  if (diff_bits && total) std::memcpy(diff_bits, r->diff[(size_t)channel].data(), total);
+  if (offsets && nb) std::memcpy(offsets, r->offsets[(size_t)channel].data(), nb);
+  return SDR_OK;
+}
+
+extern "C" int sdr_rds_discard(sdr_rds *r) {
+  if (!r) return fail(SDR_ERR_INVALID, "null argument");
+  int rc = rds_mirror(r);  // the frame synchroniser still has to see every block
+  if (rc) return rc;
+  r->cursor = 0;
+  for (auto &o : r->offsets) o.clear();
+  for (auto &d : r->diff) d.clear();
+  return SDR_OK;
+}
+
+extern "C" int sdr_rds_tap(sdr_rds *r, int stage, int channel, double *dst, size_t cap, size_t *n) {
+  if (!r || !n) return fail(SDR_ERR_INVALID, "null argument");
+  if (channel < 0 || channel >= r->view.batch) return fail(SDR_ERR_INVALID, "channel out of range");
+  const size_t n_if = r->last_n_if;
+  const size_t n_out = n_if * (size_t)r->U / (size_t)r->D;
+  const double *src = nullptr;
+  size_t cnt = 0;
+  // The carry has already moved the tails into the prefixes; samples 0.. of the last call are
+  // still in place behind them.
+  switch (stage) {
+    case SDR_RDS_TAP_CHANNEL: src = r->chan.p + (size_t)channel * r->chan_stride + RDS_HC; cnt = n_if; break;
+    case SDR_RDS_TAP_CARRIER: src = r->carr.p + (size_t)channel * r->carr_stride; cnt = n_if; break;
+    case SDR_RDS_TAP_PLL_I: src = r->ncoI.p ? r->ncoI.p + (size_t)channel * r->nco_stride : nullptr; cnt = n_if + 1; break;
+    case SDR_RDS_TAP_PLL_Q: src = r->ncoQ.p ? r->ncoQ.p + (size_t)channel * r->nco_stride : nullptr; cnt = n_if + 1; break;
+    case SDR_RDS_TAP_MIXER_I: src = r->mixI.p + (size_t)channel * r->mix_stride + RDS_HM; cnt = n_if; break;
+    case SDR_RDS_TAP_MIXER_Q: src = r->mixQ.p + (size_t)channel * r->mix_stride + RDS_HM; cnt = n_if; break;
+    case SDR_RDS_TAP_RESAMPLER_I: src = r->rsI.p + (size_t)channel * r->rs_stride + RDS_HS; cnt = n_out; break;
+    case SDR_RDS_TAP_RESAMPLER_Q: src = r->rsQ.p + (size_t)channel * r->rs_stride + RDS_HS; cnt = n_out; break;
+    case SDR_RDS_TAP_RRC_I: src = r->rrcI.p + (size_t)channel * r->rrc_stride; cnt = n_out; break;
+    case SDR_RDS_TAP_RRC_Q: src = r->rrcQ.p + (size_t)channel * r->rrc_stride; cnt = n_out; break;
+    default: return fail(SDR_ERR_INVALID, "unknown RDS stage");
+  }
+  if (!src) return fail(SDR_ERR_INVALID, "NCO outputs are kept only when sdr_rds_config.keep_nco is set");
+  if (n_if == 0) cnt = 0;
+  *n = cnt;
+  if (!dst) return SDR_OK;
+  if (cap < cnt) return fail(SDR_ERR_CAPACITY, "destination too small");
+  SDR_CUDA(cudaSetDevice(r->view.device));
+  SDR_CUDA(cudaStreamSynchronize(r->last_stream));
+  if (cnt) SDR_CUDA(cudaMemcpy(dst, src, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+  return SDR_OK;
+}
+
+extern "C" int sdr_rds_design(int which, int mode, double *h, size_t cap, size_t *n) {
+  if (!n) return fail(SDR_ERR_INVALID, "null argument");
+  if (mode != 0 && mode != 2) return fail(SDR_ERR_INVALID, "RDS is defined for modes 0 and 2 only");
+  const int U = mode == 0 ? 247 : 817, sps = mode == 0 ? 26 : 43;
+  std::vector<double> v;
+  switch (which) {
+    case SDR_RDS_FILTER_CHANNEL: v = rds_band_pass(RDS_T, 240000.0, 54e3, 60e3); break;
+    case SDR_RDS_FILTER_CARRIER: v = rds_band_pass(RDS_T, 240000.0, 113.5e3, 114.5e3); break;
+    case SDR_RDS_FILTER_RESAMPLER: v = rds_low_pass(RDS_TP * U, 240000.0 * U, 3e3); break;
+    case SDR_RDS_FILTER_RRC: v = rds_rrc(2375.0 * sps, RDS_TP); break;
+    default: return fail(SDR_ERR_INVALID, "unknown RDS filter");
+  }
+  *n = v.size();
+  if (!h) return SDR_OK;
+  if (cap < v.size()) return fail(SDR_ERR_CAPACITY, "destination too small");
+  std::memcpy(h, v.data(), v.size() * sizeof(double));
+  return SDR_OK;
+}

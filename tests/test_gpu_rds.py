@@ -1,0 +1,190 @@
+"""GPU parity tests of the RDS chain (C ABI: sdr_rds_*, csrc/rds.cu) against the CPU oracle
+(oracle/rds_oracle.c, pinned to the reference's Python model) and against the golden vectors
+generated from that model (tests/golden/rds_*.npz, tests/golden/make_golden_rds.py).
+
+Tolerances (double precision on both sides; the device sums with fused multiply-adds and in
+its own order, and calls CUDA's atan2/sincos where the model calls glibc's):
+  FIR stages                        1e-12 of full scale
+  NCO outputs, mixers and later     1e-9  (the PLL turns rounding noise, relative to the small
+                                    carrier band-pass output, into phase: ~1e-11 rad)
+  CDR / differential bits, offsets  exact
+"""
+import os
+
+import numpy as np
+import pytest
+
+import orclib
+from sdr_b200 import siggen
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STAGES = list(orclib.RDS_TAP_NAMES)
+TOL = {k: (1e-12 if k in ("channel_filt", "carrier_filt") else 1e-9) for k in STAGES}
+
+
+def close(got, want, tol, what=""):
+    assert got.shape == want.shape, what
+    scale = max(1.0, float(np.abs(want).max()))
+    err = float(np.abs(got - want).max()) if got.size else 0.0
+    assert err <= tol * scale, f"{what}: {err:.3e} > {tol * scale:.3e}"
+
+
+def run_gpu(sdr, iq, mode, block_if, n_calls=1, channels=1, variant=0):
+    """iq [B, nbytes] -> ({stage: [B] arrays}, [B] read() dicts)."""
+    B, nbytes = iq.shape
+    with sdr.Pipeline(mode=mode, channels=channels, batch=B, variant=variant,
+                      max_bytes_per_channel=nbytes) as p:
+        with sdr.Rds(p, block_if=block_if, keep_nco=True, max_pending_blocks=64) as r:
+            bb = r.info.block_bytes
+            assert nbytes % bb == 0
+            blocks = nbytes // bb
+            per_call = max(1, blocks // n_calls) * bb
+            parts = {}
+            off = 0
+            while off < nbytes:
+                ln = per_call if nbytes - off - per_call >= bb else nbytes - off
+                p.process_host(np.ascontiguousarray(iq[:, off:off + ln]))
+                for name in STAGES:
+                    for c in range(B):
+                        t = r.tap(name, c)
+                        # the NCO rows have n+1 entries per call; the last one opens the next call
+                        parts.setdefault((name, c), []).append(t)
+                off += ln
+            assert r.pending() == blocks
+            reads = [r.read(c) for c in range(B)]
+            assert p.launch_count() > 0
+    return parts, reads
+
+
+def oracle_chain(orc_rds, orc, iq_row, mode, block_if):
+    """fm_demod from the FM oracle (which wants whole reference blocks: pad, the chain is
+    causal), then the RDS oracle on the part that belongs to the capture."""
+    ref_block = siggen.MODES[mode]["block_bytes"]
+    pad = (-iq_row.size) % ref_block
+    padded = np.concatenate((iq_row, np.full(pad, 128, np.uint8)))
+    _, taps = orc.run_chain(padded, mode, 1)
+    n_if = iq_row.size // (2 * siggen.MODES[mode]["rf_decim"])
+    fm = taps["demod"][:n_if].astype(np.float64)
+    return orc_rds.run_chain(fm, mode, block_if, keep=tuple(STAGES))
+
+
+def compare(parts, reads, want, c, n_blocks, block_if):
+    for name in STAGES:
+        chunks = parts[(name, c)]
+        if name.startswith("pll"):
+            # oracle keeps n+1 values per block; per call the device keeps n+1: compare the
+            # first n of every call against the oracle's blocks, and the closing value
+            w = want[name].reshape(n_blocks, block_if + 1)
+            got = np.concatenate([ch[:-1] for ch in chunks])
+            close(got, w[:, :-1].reshape(-1), TOL[name], name)
+            close(chunks[-1][-1:], w[-1, -1:], TOL[name], name + " (last)")
+        else:
+            close(np.concatenate(chunks), want[name], TOL[name], name)
+    rd = reads[c]
+    assert list(rd["bit_counts"]) == [b.size for b in want["cdr_bits"]]
+    assert np.array_equal(rd["cdr_bits"], np.concatenate(want["cdr_bits"]))
+    assert np.array_equal(rd["diff_bits"], np.concatenate(want["diff_bits"]))
+    assert rd["offsets"] == want["offsets"]
+
+
+@pytest.mark.parametrize("mode,n_ref,block_if,n_blocks,n_calls", [
+    (0, 15, 9600, 8, 1),     # the model's own block (fmRDS.py:149)
+    (0, 15, 9600, 8, 3),     # same capture cut into three calls: carried state
+    (0, 15, 19200, 4, 2),    # a longer CDR window
+    (2, 12, 19200, 2, 1),    # mode 2 (U/D = 817/1920, 43 samples per symbol)
+    (2, 24, 9600, 14, 4),
+])
+def test_rds_matches_oracle(sdr, orc, mode, n_ref, block_if, n_blocks, n_calls):
+    R = orclib.RDS()
+    nbytes = n_blocks * block_if * 20
+    iq = np.stack([siggen.make_capture(200 + c, mode, n_ref, "rds")[:nbytes] for c in range(3)])
+    parts, reads = run_gpu(sdr, iq, mode, block_if, n_calls)
+    for c in range(3):
+        want = oracle_chain(R, orc, iq[c], mode, block_if)
+        compare(parts, reads, want, c, n_blocks, block_if)
+
+
+@pytest.mark.parametrize("mode,n_ref,block_if,n_blocks", [(0, 15, 9600, 8), (2, 12, 19200, 2)])
+def test_rds_matches_reference_model_golden(sdr, mode, n_ref, block_if, n_blocks):
+    """Directly against what the reference's Python model produced (no oracle in between)."""
+    g = np.load(os.path.join(GOLD, f"rds_mode{mode}.npz"))
+    nbytes = n_blocks * block_if * 20
+    iq = siggen.make_capture(200, mode, n_ref, "rds")[:nbytes][None, :]
+    parts, reads = run_gpu(sdr, iq, mode, block_if)
+    close(np.concatenate(parts[("rrc_i", 0)]), g["rrc_i"], 1e-9, "rrc_i")
+    close(np.concatenate(parts[("rrc_q", 0)]), g["rrc_q"], 1e-9, "rrc_q")
+    for name in STAGES[:8]:
+        got = np.concatenate(parts[(name, 0)])
+        per_block = block_if + 1 if name.startswith("pll") else got.size // n_blocks
+        close(got[-per_block:][::16], g["last16_" + name], TOL[name], name)
+    rd = reads[0]
+    assert list(rd["bit_counts"]) == list(g["bit_counts"])
+    assert np.array_equal(rd["cdr_bits"], g["cdr_bits"])
+    assert np.array_equal(rd["diff_bits"], g["diff_bits"])
+    assert rd["offsets"] == str(g["offsets"])
+
+
+def test_rds_edge_captures(sdr, orc):
+    """Silence (every stage exactly zero: the CDR sees no signs at all), a clipped capture and
+    a plain stereo capture without any 57 kHz subcarrier."""
+    R = orclib.RDS()
+    mode, block_if, n_blocks = 0, 9600, 8
+    nbytes = n_blocks * block_if * 20
+    iq = np.stack([siggen.make_capture(300, mode, 15, "silence")[:nbytes],
+                   siggen.make_capture(301, mode, 15, "clipped")[:nbytes],
+                   siggen.make_capture(302, mode, 15, "stereo")[:nbytes]])
+    parts, reads = run_gpu(sdr, iq, mode, block_if, n_calls=2)
+    for c in range(3):
+        want = oracle_chain(R, orc, iq[c], mode, block_if)
+        compare(parts, reads, want, c, n_blocks, block_if)
+    assert not np.concatenate(parts[("rrc_i", 0)]).any()
+
+
+def test_rds_with_stereo_and_fast_pipelines(sdr, orc):
+    """The chain only depends on fm_demod: attached to a stereo pipeline it gives the same
+    result; attached to the tensor-core (fast) mono pipeline it stays within that variant's
+    bound (fm_demod >= 100 dB SNR) -- checked here at the RRC output."""
+    R = orclib.RDS()
+    mode, block_if, n_blocks = 0, 9600, 8
+    nbytes = n_blocks * block_if * 20
+    iq = siggen.make_capture(200, mode, 15, "rds")[:nbytes][None, :]
+    want = oracle_chain(R, orc, iq[0], mode, block_if)
+    parts, reads = run_gpu(sdr, iq, mode, block_if, channels=2)
+    compare(parts, reads, want, 0, n_blocks, block_if)
+    parts, reads = run_gpu(sdr, iq, mode, block_if, variant=sdr.VARIANT_FAST)
+    got = np.concatenate(parts[("rrc_i", 0)])
+    err = got - want["rrc_i"]
+    snr = 10 * np.log10(np.sum(want["rrc_i"] ** 2) / max(np.sum(err ** 2), 1e-300))
+    assert snr >= 80.0, snr
+    assert np.array_equal(reads[0]["cdr_bits"], np.concatenate(want["cdr_bits"]))
+
+
+def test_rds_reset_and_errors(sdr):
+    mode, block_if = 0, 9600
+    iq = siggen.make_capture(200, mode, 15, "rds")[:4 * 192000][None, :]
+    with sdr.Pipeline(mode=mode, batch=1, max_bytes_per_channel=iq.shape[1]) as p:
+        with sdr.Rds(p, block_if=block_if, max_pending_blocks=4) as r:
+            p.process_host(iq)
+            a = r.read(0)
+            first = r.tap("rrc_i", 0)
+            # result buffer full until read/discard
+            with pytest.raises(sdr.SdrError):
+                p.process_host(iq)
+            r.discard()
+            assert r.pending() == 0
+            p.reset()
+            p.process_host(iq)
+            b = r.read(0)
+            assert np.array_equal(first, r.tap("rrc_i", 0))
+            assert np.array_equal(a["cdr_bits"], b["cdr_bits"]) and a["offsets"] == b["offsets"]
+            # not a whole number of RDS blocks
+            with pytest.raises(sdr.SdrError):
+                p.process_host(iq[:, :100000])
+            # NCO rows were not kept
+            with pytest.raises(sdr.SdrError):
+                r.tap("pll_i", 0)
+    with sdr.Pipeline(mode=1, batch=1, max_bytes_per_channel=1 << 20) as p:
+        with pytest.raises(sdr.SdrError):
+            sdr.Rds(p)
