@@ -157,7 +157,8 @@ def workload_config(args):
     return {"workload": f"mode {args.mode} {'stereo' if args.audio_channels == 2 else 'mono'}, "
                         f"{args.batch} captures per GPU x {args.blocks} reference blocks "
                         f"({args.blocks * BLOCK_BYTES[args.mode]} B each), taps rf 151 / audio 101"
-                        f"{' / stereo 151' if args.audio_channels == 2 else ''}",
+                        f"{' / stereo 151' if args.audio_channels == 2 else ''}"
+                        f"{' + RDS chain (fmRDS.py model, double precision, 9600-sample blocks)' if args.rds else ''}",
             "mode": args.mode, "audio_channels": args.audio_channels, "batch_per_gpu": args.batch,
             "blocks_per_capture": args.blocks, "l2_policy": "input batch larger than L2 (no flush needed)",
             "variant": ("fast (tensor-core RF front end; PCM within +-1 LSB of the reference)"
@@ -208,7 +209,7 @@ def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, wor
     """Device-resident timing of one configuration.  Returns dict with ms/step (max over ranks),
     per-kernel times and launches."""
     dev = torch.device("cuda", torch.cuda.current_device())
-    kind = "stereo"
+    kind = "rds" if args.rds else "stereo"
     d_iq = make_device_batch(torch, mode, args.batch, args.blocks, kind, dev)
     nbytes = d_iq.shape[1]
     variant, vname = pick_variant(sdr, args, mode, audio_channels)
@@ -216,6 +217,14 @@ def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, wor
         variant, vname = sdr.VARIANT_EXACT, "exact"
     p = sdr.Pipeline(mode=mode, channels=audio_channels, batch=args.batch, device=dev.index,
                      max_bytes_per_channel=nbytes, variant=variant, **TAPS)
+    rds = None
+    if args.rds:
+        # the RDS chain follows every process call on the same stream; its bit buffer is sized
+        # for the whole run so that no host read-back falls inside the timed region
+        if nbytes % 192000:
+            raise SystemExit("--rds needs --blocks such that a capture is a multiple of 192000 B "
+                             "(mode 0: 15, 30, ...; mode 2: 12, 24, ...)")
+        rds = sdr.Rds(p, block_if=9600, max_pending_blocks=(steps + warmup) * (nbytes // 192000))
     n_pcm = p.pcm_count(nbytes)
     d_pcm = torch.zeros((args.batch, n_pcm), dtype=torch.int16, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -249,11 +258,17 @@ def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, wor
         ms = float(t.item())
     samples_per_step = args.batch * (nbytes // 2)
     checksum = int(d_pcm[:, :64].to(torch.int64).abs().sum().item())
+    rds_info = None
+    if rds is not None:
+        rd = rds.read(0)
+        rds_info = {"blocks": int(rd["bit_counts"].size), "bits_capture0": int(rd["cdr_bits"].size),
+                    "offsets_capture0_tail": rd["offsets"][-16:]}
+        rds.close()
     p.close()
     del d_iq, d_pcm
     torch.cuda.empty_cache()
     return {"ms_per_step": ms / steps, "samples_per_step": samples_per_step, "launches": launches,
-            "kernels": ktimes, "nbytes": nbytes, "n_pcm": n_pcm, "checksum": checksum, "variant": vname}
+            "kernels": ktimes, "nbytes": nbytes, "n_pcm": n_pcm, "checksum": checksum, "variant": vname, "rds": rds_info}
 
 
 def time_e2e(torch, sdr, args, steps, dist, world):
@@ -321,7 +336,7 @@ def run_ours(args):
         sampler.join(timeout=3)
         clocks = sampler.summary()
 
-    e2e = time_e2e(torch, sdr, args, max(2, min(args.steps, 5)), dist, world)
+    e2e = None if args.rds else time_e2e(torch, sdr, args, max(2, min(args.steps, 5)), dist, world)
 
     others = {}
     if args.others and world == 1:
@@ -377,6 +392,8 @@ def run_ours(args):
             "config": workload_config(args), "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
             "gpu_launches": main["launches"], "clocks": clocks, "pcm_checksum": main["checksum"],
         }
+        if main.get("rds"):
+            line["rds"] = main["rds"]
         if others:
             line["other_configs"] = others
         print(json.dumps(line), flush=True)
@@ -398,6 +415,8 @@ def main():
     ap.add_argument("--e2e-blocks", type=int, default=8)
     ap.add_argument("--others", action="store_true", help="also time mono mode 0 / stereo configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rds", action="store_true",
+                    help="also run the RDS chain (modes 0/2) behind every step; not the default workload")
     ap.add_argument("--variant", default="fast", choices=["fast", "exact"],
                     help="fast: tensor-core RF front end (mono, +-1 LSB PCM); exact: bit-identical CUDA-core path")
     args = ap.parse_args()

@@ -7,8 +7,9 @@
 //
 //   R1  k_rds_fir<151, float in>     channel band-pass 54-60 kHz            fmRDS.py:223
 //   R2  k_rds_fir<151, squared in>   x^2, carrier band-pass 113.5-114.5 kHz fmRDS.py:230-233
-//   R3  k_rds_pll                    PLL at 114 kHz, NCO I and Q (scale 0.5, 3pi/8),
-//                                    all-pass delay (75) and both mixers   fmRDS.py:227,236-241,251
+//   R3a k_rds_pll                    PLL at 114 kHz (sequential, one lane per capture)  fmRDS.py:236
+//   R3b k_rds_mix                    NCO I and Q (scale 0.5, 3pi/8), all-pass delay (75)
+//                                    and both mixers                       fmRDS.py:227,241,251
 //   R4  k_rds_resample               rational resampler U/D, 101 taps per phase, gain U
 //                                                                           fmRDS.py:244,252
 //   R5  k_rds_fir<101>               root-raised-cosine filter, I and Q     fmRDS.py:248,254
@@ -27,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -130,14 +132,167 @@ k_rds_fir(const RdsFirArgs a, const __grid_constant__ DTaps<T> taps) {
 }
 
 // ---------------------------------------------------------------------------
-// R3: PLL + NCO (fmSupportLib.py:297-354) with the all-pass delay and the two mixers
-// (fmRDS.py:227,241,251) as its output stage.  Sequential per capture: one lane per capture.
-// ncoOut[0] of a call is the last NCO value of the previous call (state[4] / state[6]); the
-// mixers use ncoOut[0..N), i.e. the NCO delayed by one sample.
+// R3a: PLL (fmSupportLib.py:297-354).  Sequential per capture: one lane per capture, so what
+// counts is the length of the dependent chain per sample.  The model's chain is
+//     errorD = atan2(x * -sin(t), x * cos(t));  integrator += Ki*errorD;
+//     phaseEst += Kp*errorD + integrator;       t' = 2*pi*(f/Fs)*n + phaseEst
+// with t the NCO phase of the previous sample.  The phase detector's arguments are a real
+// sample times a unit phasor, so its result is that phasor's angle: -t wrapped to (-pi, pi]
+// when x > 0, pi - t wrapped when x < 0 (and atan2's signed-zero cases when x == 0).  The
+// kernel therefore carries t reduced modulo 2*pi (two fused multiply-adds against a two-part
+// 2*pi) instead of sin/cos of it, and no arctangent, sine or cosine is left on the chain:
+// eight dependent double-precision operations (8 cycles each on B200) and one integer
+// test-and-select per sample instead of ~100 operations, and no branch that depends on them.  The result
+// differs from the model's only by the rounding of sin, cos and atan2 themselves (~1e-16 in
+// errorD), far inside the parity bound.  The NCO phase t' of every sample goes to `theta`;
+// R3b turns it into the NCO outputs and the mixer products in parallel.
+// theta rows: [0] = last phase of the previous call (NaN before the first sample), [1+k] = t'
+// of sample k.
 // ---------------------------------------------------------------------------
 struct RdsPllArgs {
   const double *carr;  // [B][carr_stride]
   size_t carr_stride;
+  double *theta;  // [B][theta_stride]
+  size_t theta_stride;
+  double *state;  // [B][8]: integrator, phaseEst, reduced NCO phase, -, -, trigOffset
+  int n, batch;
+  double freq, Fs, normBandwidth;
+};
+
+constexpr int RDS_PLL_PITCH = 33;  // doubles per tile row: per-lane 64-bit reads fall on distinct bank pairs
+constexpr double RDS_PI = 3.141592653589793;
+constexpr double RDS_2PI_HI = 6.283185307179586;        // fl(2*pi)
+constexpr double RDS_2PI_LO = 2.4492935982947064e-16;   // 2*pi - fl(2*pi)
+constexpr double RDS_INV_2PI = 0.15915494309189535;
+
+// x - 2*pi*rint(x / (2*pi)), |result| <= pi (+ a rounding), absolute error ~3e-16 for |x| < 2^40
+__device__ __forceinline__ double rds_reduce_2pi(double x) {
+  const double k = rint(__dmul_rn(x, RDS_INV_2PI));
+  return fma(-k, RDS_2PI_LO, fma(-k, RDS_2PI_HI, x));
+}
+
+static __global__ void __launch_bounds__(32) k_rds_pll(const RdsPllArgs a) {
+  const bool live = (int)(blockIdx.x * blockDim.x + threadIdx.x) < a.batch;
+  const int b = live ? blockIdx.x * blockDim.x + threadIdx.x : a.batch - 1;  // idle lanes shadow the last capture
+  // fmSupportLib.py:303-309
+  const double Kp = __dmul_rn(a.normBandwidth, 2.666);
+  const double Ki = __dmul_rn(__dmul_rn(a.normBandwidth, a.normBandwidth), 3.555);
+  double *st = a.state + (size_t)b * 8;
+  double integrator = st[0], phaseEst = st[1], r = st[2];
+  const double n0 = st[5];
+  const double *in = a.carr + (size_t)b * a.carr_stride;
+  double *th = a.theta + (size_t)b * a.theta_stride + 1;  // (shadow lanes store the same values as the lane they shadow)
+  // fmSupportLib.py:340: 2*pi*(freq/Fs), left to right
+  const double w = __dmul_rn(__dmul_rn(2.0, RDS_PI), __ddiv_rn(a.freq, a.Fs));
+  // Input: the warp copies tiles of 32 captures x 32 samples into shared memory with
+  // asynchronous copies (32 coalesced 256-byte rows per tile, no register in between), one
+  // tile ahead of the one being consumed, so no global-load latency ever meets the recurrence.
+  // (Per-lane loads into a register queue stall on the queue's register moves: 10.9 ms per
+  // 76 800 samples against 6.4 ms with the loads removed.)
+  __shared__ double tile[2][32][RDS_PLL_PITCH];
+  const int lane = threadIdx.x;
+  const int b_first = blockIdx.x * 32;
+  auto fetch = [&](int buf, int k0) {
+    for (int c = 0; c < 32; ++c) {
+      const int bc = min(b_first + c, a.batch - 1);
+      const int k = min(k0 + lane, a.n - 1);
+      const double *src = a.carr + (size_t)bc * a.carr_stride + k;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[buf][c][lane]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  constexpr int HALF_PI_HI = 0x3ff921fb;
+  constexpr unsigned HALF_PI_LO = 0x54442d18u;
+  constexpr double ROUND_MAGIC = 6755399441055744.0;  // 1.5 * 2^52: x + M - M = rint(x) for |x| < 2^51
+  double nd = n0;  // trigOffset, an exact integer
+  fetch(0, 0);
+  for (int k0 = 0, buf = 0; k0 < a.n; k0 += 32, buf ^= 1) {
+    if (k0 + 32 < a.n) {
+      fetch(buf ^ 1, k0 + 32);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const double *xs = tile[buf][lane];
+    const int kn = min(32, a.n - k0);
+    // Only the sign of a sample enters the phase detector: reduce the tile to two bit masks
+    // up front (independent loads and compares), so that the loop below touches nothing but
+    // registers and no branch in it waits for a load.
+    unsigned pos_mask = 0, zero_mask = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const double x = xs[j];
+      pos_mask |= (x > 0.0 ? 1u : 0u) << j;
+      zero_mask |= (x == 0.0 ? 1u : 0u) << j;
+    }
+    double *tp = th + k0;
+    if (!__any_sync(0xffffffffu, zero_mask != 0)) {
+#pragma unroll 8
+      for (int j = 0; j < kn; ++j) {
+        // off the chain: 2*pi*(f/Fs)*trigOffset (fmSupportLib.py:338-340)
+        nd = __dadd_rn(nd, 1.0);
+        const double wn = __dmul_rn(w, nd);
+        // Phase detector (fmSupportLib.py:324-329), see the header.  The sign of r is read
+        // from its high word: an integer test, not a compare on the double-precision pipe.
+        const double c = (pos_mask >> j) & 1u ? 0.0 : (__double2hiint(r) < 0 ? -RDS_PI : RDS_PI);
+        const double errorD = __dsub_rn(c, r);
+        // loop filter and phase estimate (fmSupportLib.py:332-335).  The products are fused
+        // into the sums (the model rounds them first: a difference of ~1e-21 per sample).
+        integrator = fma(Ki, errorD, integrator);
+        phaseEst = __dadd_rn(fma(Kp, errorD, phaseEst), integrator);
+        const double trigArg = __dadd_rn(wn, phaseEst);
+        tp[j] = trigArg;
+        // reduce modulo 2*pi; the turn count is rounded with the magic constant (two 8-cycle
+        // operations where cvt.rni.f64 takes 21, tools/ubench_dp_latency.cu)
+        const double turns = __dsub_rn(fma(trigArg, RDS_INV_2PI, ROUND_MAGIC), ROUND_MAGIC);
+        r = fma(-turns, RDS_2PI_LO, fma(-turns, RDS_2PI_HI, trigArg));
+      }
+    } else {
+      // some capture of this warp has exact zeros in the tile (silence): same step with
+      // atan2's signed-zero cases
+      for (int j = 0; j < kn; ++j) {
+        nd = __dadd_rn(nd, 1.0);
+        const double wn = __dmul_rn(w, nd);
+        const bool r_neg = __double2hiint(r) < 0;
+        double c = (pos_mask >> j) & 1u ? 0.0 : (r_neg ? -RDS_PI : RDS_PI);
+        double rr = r;
+        if ((zero_mask >> j) & 1u) {
+          // atan2(+-0, +-0): 0 when cos(t) has a clear sign bit (|t| <= pi/2), else +-pi by the
+          // sign of -sin(t); |t| compared as an integer (exact for doubles)
+          const int r_abs = __double2hiint(r) & 0x7fffffff;
+          const bool far = r_abs > HALF_PI_HI || (r_abs == HALF_PI_HI && (unsigned)__double2loint(r) > HALF_PI_LO);
+          c = far ? (r_neg ? RDS_PI : -RDS_PI) : 0.0;
+          rr = 0.0;
+        }
+        const double errorD = __dsub_rn(c, rr);
+        integrator = fma(Ki, errorD, integrator);
+        phaseEst = __dadd_rn(fma(Kp, errorD, phaseEst), integrator);
+        const double trigArg = __dadd_rn(wn, phaseEst);
+        tp[j] = trigArg;
+        const double turns = __dsub_rn(fma(trigArg, RDS_INV_2PI, ROUND_MAGIC), ROUND_MAGIC);
+        r = fma(-turns, RDS_2PI_LO, fma(-turns, RDS_2PI_HI, trigArg));
+      }
+    }
+    __syncwarp();
+  }
+  st[0] = integrator;
+  st[1] = phaseEst;
+  st[2] = r;
+  st[5] = nd;
+}
+
+// ---------------------------------------------------------------------------
+// R3b: NCO outputs cos/sin(t*ncoScale + phaseAdjust) (fmSupportLib.py:344-345), the all-pass
+// delay of the channel signal (fmRDS.py:227) and both mixers (fmRDS.py:241,251), one thread
+// per sample.  ncoOut[0] of a call is the last NCO value of the previous call; the mixers use
+// ncoOut[0..N), i.e. the NCO delayed by one sample, so sample k uses theta[k] (theta[0] being
+// the carried phase).  Before the first sample both NCO outputs are 1.0 (fmRDS.py:175).
+// ---------------------------------------------------------------------------
+struct RdsMixArgs {
+  const double *theta;
+  size_t theta_stride;
   const double *chan;  // [B][chan_stride], sample 0 at chan_off
   size_t chan_stride;
   int chan_off;
@@ -146,75 +301,35 @@ struct RdsPllArgs {
   int mix_off;
   double *ncoI, *ncoQ;  // optional [B][nco_stride]: ncoOut[0..N] for the parity taps
   size_t nco_stride;
-  double *state;  // [B][8]
-  int n, batch;
-  double freq, Fs, ncoScale, phaseAdjust, normBandwidth;
+  int n;
+  double ncoScale, phaseAdjust;
 };
 
-static __global__ void k_rds_pll(const RdsPllArgs a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.batch) return;
-  // fmSupportLib.py:303-309
-  const double Kp = __dmul_rn(a.normBandwidth, 2.666);
-  const double Ki = __dmul_rn(__dmul_rn(a.normBandwidth, a.normBandwidth), 3.555);
-  double *st = a.state + (size_t)b * 8;
-  double integrator = st[0], phaseEst = st[1], fbI = st[2], fbQ = st[3];
-  double outI = st[4], trigOffset = st[5], outQ = st[6];
-  const double *in = a.carr + (size_t)b * a.carr_stride;
-  const double *ap = a.chan + (size_t)b * a.chan_stride + a.chan_off - RDS_DELAY;
-  double *mI = a.mixI + (size_t)b * a.mix_stride + a.mix_off;
-  double *mQ = a.mixQ + (size_t)b * a.mix_stride + a.mix_off;
-  double *nI = a.ncoI ? a.ncoI + (size_t)b * a.nco_stride : nullptr;
-  double *nQ = a.ncoQ ? a.ncoQ + (size_t)b * a.nco_stride : nullptr;
-  // fmSupportLib.py:340: 2*pi*(freq/Fs), left to right
-  const double w = __dmul_rn(__dmul_rn(2.0, 3.141592653589793), __ddiv_rn(a.freq, a.Fs));
-  // each lane walks its own rows, so every load is its own line: fetch ahead of the recurrence
-  double xq[4], aq[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    xq[i] = i < a.n ? in[i] : 0.0;
-    aq[i] = i < a.n ? ap[i] : 0.0;
+static __global__ void __launch_bounds__(256) k_rds_mix(const RdsMixArgs a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (k > a.n || (k == a.n && !a.ncoI)) return;
+  const double t = a.theta[(size_t)b * a.theta_stride + k];
+  double oI = 1.0, oQ = 1.0;
+  if (t == t) {
+    const double arg = __dadd_rn(__dmul_rn(t, a.ncoScale), a.phaseAdjust);
+    sincos(rds_reduce_2pi(arg), &oQ, &oI);
   }
-  if (nI) nI[0] = outI;
-  if (nQ) nQ[0] = outQ;
-  for (int k = 0; k < a.n; ++k) {
-    const double x = xq[0], d = aq[0];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      xq[i] = xq[i + 1];
-      aq[i] = aq[i + 1];
-    }
-    xq[3] = (k + 4 < a.n) ? in[k + 4] : 0.0;
-    aq[3] = (k + 4 < a.n) ? ap[k + 4] : 0.0;
-    // mixers: rds_PLL[:-1] * rds_allpass * 2 (fmRDS.py:241,251)
-    mI[k] = __dmul_rn(__dmul_rn(outI, d), 2.0);
-    mQ[k] = __dmul_rn(__dmul_rn(outQ, d), 2.0);
-    // fmSupportLib.py:324-348
-    const double errorI = __dmul_rn(x, fbI);
-    const double errorQ = __dmul_rn(x, -fbQ);
-    const double errorD = atan2(errorQ, errorI);
-    integrator = __dadd_rn(integrator, __dmul_rn(Ki, errorD));
-    phaseEst = __dadd_rn(__dadd_rn(phaseEst, __dmul_rn(Kp, errorD)), integrator);
-    trigOffset = __dadd_rn(trigOffset, 1.0);
-    const double trigArg = __dadd_rn(__dmul_rn(w, trigOffset), phaseEst);
-    sincos(trigArg, &fbQ, &fbI);
-    sincos(__dadd_rn(__dmul_rn(trigArg, a.ncoScale), a.phaseAdjust), &outQ, &outI);
-    if (nI) nI[k + 1] = outI;
-    if (nQ) nQ[k + 1] = outQ;
+  if (a.ncoI) {
+    a.ncoI[(size_t)b * a.nco_stride + k] = oI;
+    a.ncoQ[(size_t)b * a.nco_stride + k] = oQ;
   }
-  st[0] = integrator;
-  st[1] = phaseEst;
-  st[2] = fbI;
-  st[3] = fbQ;
-  st[4] = outI;
-  st[5] = trigOffset;
-  st[6] = outQ;
+  if (k < a.n) {
+    const double d = a.chan[(size_t)b * a.chan_stride + a.chan_off - RDS_DELAY + k];
+    a.mixI[(size_t)b * a.mix_stride + a.mix_off + k] = __dmul_rn(__dmul_rn(oI, d), 2.0);
+    a.mixQ[(size_t)b * a.mix_stride + a.mix_off + k] = __dmul_rn(__dmul_rn(oQ, d), 2.0);
+  }
 }
 
 // ---------------------------------------------------------------------------
 // R4: rational resampler (fmSupportLib.py:388-407): output j takes phase (jD mod U) of the
 // 101*U-tap low-pass and the 101 inputs ending at floor(jD/U); gain U.  poly is the filter
-// regrouped by phase, [U][RDS_POLY_PITCH].  One thread per output, I and Q together.
+// regrouped by phase, [U][RDS_POLY_PITCH].  I and Q share the taps.
 // ---------------------------------------------------------------------------
 struct RdsResampleArgs {
   const double *mixI, *mixQ;
@@ -227,31 +342,69 @@ struct RdsResampleArgs {
   int U, D, n_out;
 };
 
-static __global__ void __launch_bounds__(128) k_rds_resample(const RdsResampleArgs a) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  if (j >= a.n_out) return;
-  const long long m = (long long)j * a.D;
-  const int phase = (int)(m % a.U);
-  const long long base = m / a.U;
-  const double *h = a.poly + (size_t)phase * RDS_POLY_PITCH;
-  const double *xi = a.mixI + (size_t)b * a.mix_stride + a.mix_off + base;
-  const double *xq = a.mixQ + (size_t)b * a.mix_stride + a.mix_off + base;
-  double accI = 0.0, accQ = 0.0;
-#pragma unroll 4
-  for (int k = 0; k < RDS_TP; ++k) {
-    const double hk = __ldg(h + k);
-    accI = fma(hk, xi[-k], accI);
-    accQ = fma(hk, xq[-k], accQ);
+// Lanes are captures: a warp computes one output for 32 captures at a time, so the 101 taps of
+// that output's phase are warp-uniform (one broadcast load each) and the inputs come from a
+// shared-memory tile stored [time][capture] (pitch 33: the transposing stores and the
+// per-capture reads are both conflict-free).  A block owns J consecutive outputs of 32
+// captures; results go back through shared memory so that global stores are contiguous.
+constexpr int RDS_RS_J = 16;      // outputs per block
+constexpr int RDS_RS_PITCH = 33;  // doubles per tile row
+
+static __global__ void __launch_bounds__(256) k_rds_resample(const RdsResampleArgs a, int batch, int rows_cap) {
+  extern __shared__ double rs_sm[];
+  double *tI = rs_sm;
+  double *tQ = tI + (size_t)rows_cap * RDS_RS_PITCH;
+  double *oI = tQ + (size_t)rows_cap * RDS_RS_PITCH;  // [32][J+1]
+  double *oQ = oI + 32 * (RDS_RS_J + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = blockIdx.x * RDS_RS_J;
+  const int b0 = blockIdx.y * 32;
+  const int jn = min(RDS_RS_J, a.n_out - j0);
+  const long long base0 = ((long long)j0 * a.D) / a.U;               // newest input of the first output
+  const long long baseL = ((long long)(j0 + jn - 1) * a.D) / a.U;    // ... of the last one
+  const long long lo = base0 - (RDS_TP - 1);                         // oldest input needed
+  const int rows = (int)(baseL - lo + 1);
+  for (int c = warp; c < 32; c += 8) {
+    if (b0 + c >= batch) continue;
+    const double *sI = a.mixI + (size_t)(b0 + c) * a.mix_stride + a.mix_off + lo;
+    const double *sQ = a.mixQ + (size_t)(b0 + c) * a.mix_stride + a.mix_off + lo;
+    for (int q = lane; q < rows; q += 32) {
+      tI[q * RDS_RS_PITCH + c] = sI[q];
+      tQ[q * RDS_RS_PITCH + c] = sQ[q];
+    }
   }
-  a.rsI[(size_t)b * a.rs_stride + a.rs_off + j] = __dmul_rn(accI, (double)a.U);
-  a.rsQ[(size_t)b * a.rs_stride + a.rs_off + j] = __dmul_rn(accQ, (double)a.U);
+  __syncthreads();
+  for (int jj = warp; jj < jn; jj += 8) {
+    const long long m = (long long)(j0 + jj) * a.D;
+    const int phase = (int)(m % a.U);
+    const int top = (int)(m / a.U - lo);
+    const double *h = a.poly + (size_t)phase * RDS_POLY_PITCH;
+    const double *xi = tI + (size_t)top * RDS_RS_PITCH + lane;
+    const double *xq = tQ + (size_t)top * RDS_RS_PITCH + lane;
+    double accI = 0.0, accQ = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < RDS_TP; ++k) {
+      const double hk = __ldg(h + k);
+      accI = fma(hk, xi[-k * RDS_RS_PITCH], accI);
+      accQ = fma(hk, xq[-k * RDS_RS_PITCH], accQ);
+    }
+    oI[lane * (RDS_RS_J + 1) + jj] = __dmul_rn(accI, (double)a.U);  // fmSupportLib.py:400
+    oQ[lane * (RDS_RS_J + 1) + jj] = __dmul_rn(accQ, (double)a.U);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * RDS_RS_J; i += 256) {
+    const int c = i / RDS_RS_J, jj = i % RDS_RS_J;
+    if (b0 + c < batch && jj < jn) {
+      a.rsI[(size_t)(b0 + c) * a.rs_stride + a.rs_off + j0 + jj] = oI[c * (RDS_RS_J + 1) + jj];
+      a.rsQ[(size_t)(b0 + c) * a.rs_stride + a.rs_off + j0 + jj] = oQ[c * (RDS_RS_J + 1) + jj];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
 // R6: clock and data recovery + Manchester decoding (fmSupportLib.py:103-222), driven as in
 // fmRDS.py:257-268: per block, pair = (0,0), start = 158, prev_size = 0 (which makes the
-// model's "pair with the previous block" branch, :117-125, dead).  One thread per
+// model's "pair with the previous block" branch, :117-125, dead).  One warp per
 // (capture, block).  The model builds the whole array of sampling points, then walks the
 // pairs; a pair of equal signs that cannot be repaired by inverting a small sample moves
 // the start by one symbol and starts over.  Pair decisions only depend on the two samples of
@@ -273,16 +426,34 @@ struct RdsCdrArgs {
   int batch;
 };
 
-static __global__ void k_rds_cdr(const RdsCdrArgs a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// A restart moves the start by exactly one symbol, so every pass looks at the same grid of
+// sampling points x[158 + i*sps], minus its first few: the warp fetches the grid once (lanes
+// in parallel) into shared memory and lane 0 walks it.
+constexpr int RDS_CDR_WARPS = 4;
+constexpr int RDS_CDR_PTS = 512;  // sampling points per block kept in shared memory (else read in place)
+
+static __global__ void __launch_bounds__(32 * RDS_CDR_WARPS) k_rds_cdr(const RdsCdrArgs a) {
+  __shared__ double pts_sm[RDS_CDR_WARPS][RDS_CDR_PTS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * RDS_CDR_WARPS + warp;
   if (idx >= a.batch * a.n_blocks) return;
   const int b = idx / a.n_blocks, blk = idx % a.n_blocks;
-  const double *x = a.rrc + (size_t)b * a.rrc_stride + (size_t)blk * a.block_out;
-  const int n = a.block_out, sps = a.sps;
+  const double *x = a.rrc + (size_t)b * a.rrc_stride + (size_t)blk * a.block_out + RDS_CDR_START;
+  const int sps = a.sps;
+  const int n_pts = (a.block_out - RDS_CDR_START + sps - 1) / sps;  // points i with 158 + i*sps < n
+  const double *pts = x;
+  int step = sps;
+  if (n_pts <= RDS_CDR_PTS) {
+    for (int i = lane; i < n_pts; i += 32) pts_sm[warp][i] = x[(size_t)i * sps];
+    __syncwarp();
+    pts = pts_sm[warp];
+    step = 1;
+  }
+  if (lane != 0) return;
   uint8_t *out = a.bits + ((size_t)b * a.blocks_cap + a.cursor + blk) * a.bits_cap;
   const bool first_ever = (a.first_block + blk) == 0;
   const double limit = 0.3;
-  int start = RDS_CDR_START;
+  int first_pt = 0;  // start = 158 + first_pt * sps
   int n_prefix = 0;
   double pair0 = 0.0;
   int nb = 0;
@@ -291,9 +462,8 @@ static __global__ void k_rds_cdr(const RdsCdrArgs a) {
     double first = 0.0, s0 = 0.0;
     bool restart = false;
     nb = n_prefix;
-    int k = 0;
-    for (int i = start; i < n; i += sps, ++k) {
-      const double xi = x[i];
+    for (int k = 0; first_pt + k < n_pts; ++k) {
+      const double xi = pts[(size_t)(first_pt + k) * step];
       double s = xi;
       // :128-136 a third consecutive high (or low) is inverted
       if (k >= 2 && ((p2 > 0 && p1 > 0 && xi > 0) || (p2 < 0 && p1 < 0 && xi < 0))) s = -xi;
@@ -321,7 +491,7 @@ static __global__ void k_rds_cdr(const RdsCdrArgs a) {
       ++nb;
     }
     if (!restart) break;
-    start += sps;
+    first_pt += 1;
     if (!first_ever) {  // :160-167: symbolToBit looks at pair[0] only (:228-236)
       const uint8_t bit = pair0 > 0 ? 1 : 0;
       if (n_prefix < a.bits_cap) out[n_prefix] = bit;
@@ -336,10 +506,10 @@ static __global__ void k_rds_cdr(const RdsCdrArgs a) {
 // R7: move the tails into the history prefixes; keep the last demod samples.
 // ---------------------------------------------------------------------------
 struct RdsCarryArgs {
-  double *rows[5];
-  size_t strides[5];
-  int src_off[5];  // first element to copy
-  int len[5];
+  double *rows[6];
+  size_t strides[6];
+  int src_off[6];  // first element to copy
+  int len[6];
   const float *demod;  // this call's fm_demod, sample 0 at demod_off
   size_t demod_stride;
   int demod_off;
@@ -351,7 +521,7 @@ struct RdsCarryArgs {
 static __global__ void k_rds_carry(const RdsCarryArgs c) {
   __shared__ double stage[RDS_HC + 8];
   const int b = blockIdx.x, t = threadIdx.x;
-  for (int r = 0; r < 5; ++r) {
+  for (int r = 0; r < 6; ++r) {
     if (!c.rows[r]) continue;
     double *row = c.rows[r] + (size_t)b * c.strides[r];
     for (int i = t; i < c.len[r]; i += blockDim.x) stage[i] = row[c.src_off[r] + i];
@@ -461,10 +631,10 @@ struct sdr_rds {
   int block_if = 0, block_out = 0, block_bytes = 0;
   int blocks_cap = 0, bits_cap = 0;
   size_t cap_if = 0, cap_out = 0;
-  size_t chan_stride = 0, carr_stride = 0, mix_stride = 0, rs_stride = 0, rrc_stride = 0, nco_stride = 0;
+  size_t chan_stride = 0, carr_stride = 0, theta_stride = 0, mix_stride = 0, rs_stride = 0, rrc_stride = 0, nco_stride = 0;
   DTaps<RDS_T> h_chan{}, h_carr{};
   DTaps<RDS_TP> h_rrc{};
-  RBuf<double> poly, chan, carr, mixI, mixQ, rsI, rsQ, rrcI, rrcQ, ncoI, ncoQ, pll;
+  RBuf<double> poly, chan, carr, theta, mixI, mixQ, rsI, rsQ, rrcI, rrcQ, ncoI, ncoQ, pll;
   RBuf<float> hist32;
   RBuf<uint8_t> bits;
   RBuf<int> counts;
@@ -490,10 +660,13 @@ static int rds_reset_device(sdr_rds *r) {
   for (int i = 0; i < 8; ++i)
     if (rows[i]) SDR_CUDA(cudaMemset(rows[i], 0, sizes[i] * sizeof(double)));
   SDR_CUDA(cudaMemset(r->hist32.p, 0, r->hist32.n * sizeof(float)));
-  // fmRDS.py:175 state_rds_pll = [0, 0, 1, 0, 1, 0, 1]
-  std::vector<double> st(B * 8, 0.0);
-  for (size_t b = 0; b < B; ++b) st[b * 8 + 2] = st[b * 8 + 4] = st[b * 8 + 6] = 1.0;
-  SDR_CUDA(cudaMemcpy(r->pll.p, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+  // fmRDS.py:175 state_rds_pll = [0, 0, 1, 0, 1, 0, 1]: integrator, phaseEst and trigOffset 0,
+  // feedback phasor 1+0j (NCO phase 0), both NCO outputs 1.0 (theta[0] = NaN stands for that)
+  SDR_CUDA(cudaMemset(r->pll.p, 0, r->pll.n * sizeof(double)));
+  const double nan = std::nan("");
+  std::vector<double> nans(B, nan);
+  SDR_CUDA(cudaMemcpy2D(r->theta.p, r->theta_stride * sizeof(double), nans.data(), sizeof(double),
+                        sizeof(double), B, cudaMemcpyHostToDevice));
   r->cursor = 0;
   r->blocks_done = 0;
   r->last_n_if = 0;
@@ -566,10 +739,27 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     k_rds_fir<RDS_T, R, NT, 1><<<grid, NT, 0, s>>>(a, r->h_carr);
     if ((rc = sdr_check_launch(p, "k_rds_fir_carrier"))) return rc;
   }
-  {  // R3
+  {  // R3a
     RdsPllArgs a{};
     a.carr = r->carr.p;
     a.carr_stride = r->carr_stride;
+    a.theta = r->theta.p;
+    a.theta_stride = r->theta_stride;
+    a.state = r->pll.p;
+    a.n = n;
+    a.batch = B;
+    // fmRDS.py:236-237
+    a.freq = 114e3;
+    a.Fs = (double)r->view.if_Fs;
+    a.normBandwidth = 0.002;
+    sdr_prof_begin(p, "k_rds_pll", s);
+    k_rds_pll<<<(B + 31) / 32, 32, 0, s>>>(a);
+    if ((rc = sdr_check_launch(p, "k_rds_pll"))) return rc;
+  }
+  {  // R3b
+    RdsMixArgs a{};
+    a.theta = r->theta.p;
+    a.theta_stride = r->theta_stride;
     a.chan = r->chan.p;
     a.chan_stride = r->chan_stride;
     a.chan_off = RDS_HC;
@@ -580,18 +770,13 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     a.ncoI = r->keep_nco ? r->ncoI.p : nullptr;
     a.ncoQ = r->keep_nco ? r->ncoQ.p : nullptr;
     a.nco_stride = r->nco_stride;
-    a.state = r->pll.p;
     a.n = n;
-    a.batch = B;
-    // fmRDS.py:236-237
-    a.freq = 114e3;
-    a.Fs = (double)r->view.if_Fs;
     a.ncoScale = 0.5;
     a.phaseAdjust = 3 * M_PI / 8;
-    a.normBandwidth = 0.002;
-    sdr_prof_begin(p, "k_rds_pll", s);
-    k_rds_pll<<<(B + 31) / 32, 32, 0, s>>>(a);
-    if ((rc = sdr_check_launch(p, "k_rds_pll"))) return rc;
+    dim3 grid((n + 1 + 255) / 256, B);
+    sdr_prof_begin(p, "k_rds_mix", s);
+    k_rds_mix<<<grid, 256, 0, s>>>(a);
+    if ((rc = sdr_check_launch(p, "k_rds_mix"))) return rc;
   }
   {  // R4
     RdsResampleArgs a{};
@@ -607,9 +792,12 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     a.U = r->U;
     a.D = r->D;
     a.n_out = n_out;
-    dim3 grid((n_out + 127) / 128, B);
+    const int rows_cap = (int)(((long long)(RDS_RS_J - 1) * r->D) / r->U) + 2 + RDS_TP;
+    const size_t smem = ((size_t)2 * rows_cap * RDS_RS_PITCH + (size_t)2 * 32 * (RDS_RS_J + 1)) * sizeof(double);
+    dim3 grid((n_out + RDS_RS_J - 1) / RDS_RS_J, (B + 31) / 32);
     sdr_prof_begin(p, "k_rds_resample", s);
-    k_rds_resample<<<grid, 128, 0, s>>>(a);
+    cudaFuncSetAttribute(k_rds_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_rds_resample<<<grid, 256, smem, s>>>(a, B, rows_cap);
     if ((rc = sdr_check_launch(p, "k_rds_resample"))) return rc;
   }
   {  // R5
@@ -645,16 +833,17 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     a.batch = B;
     const int total = B * n_blocks;
     sdr_prof_begin(p, "k_rds_cdr", s);
-    k_rds_cdr<<<(total + 63) / 64, 64, 0, s>>>(a);
+    k_rds_cdr<<<(total + RDS_CDR_WARPS - 1) / RDS_CDR_WARPS, 32 * RDS_CDR_WARPS, 0, s>>>(a);
     if ((rc = sdr_check_launch(p, "k_rds_cdr"))) return rc;
   }
   {  // R7
     RdsCarryArgs c{};
-    double *rows[5] = {r->chan.p, r->mixI.p, r->mixQ.p, r->rsI.p, r->rsQ.p};
-    const size_t strides[5] = {r->chan_stride, r->mix_stride, r->mix_stride, r->rs_stride, r->rs_stride};
-    const int lens[5] = {RDS_HC, RDS_HM, RDS_HM, RDS_HS, RDS_HS};
-    const int srcs[5] = {n, n, n, n_out, n_out};
-    for (int i = 0; i < 5; ++i) {
+    double *rows[6] = {r->chan.p, r->mixI.p, r->mixQ.p, r->rsI.p, r->rsQ.p, r->theta.p};
+    const size_t strides[6] = {r->chan_stride, r->mix_stride, r->mix_stride, r->rs_stride, r->rs_stride,
+                               r->theta_stride};
+    const int lens[6] = {RDS_HC, RDS_HM, RDS_HM, RDS_HS, RDS_HS, 1};
+    const int srcs[6] = {n, n, n, n_out, n_out, n};
+    for (int i = 0; i < 6; ++i) {
       c.rows[i] = rows[i];
       c.strides[i] = strides[i];
       c.len[i] = lens[i];
@@ -798,6 +987,7 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
   auto up = [](size_t v) { return (v + 3) / 4 * 4; };
   r->chan_stride = up(RDS_HC + r->cap_if);
   r->carr_stride = up(r->cap_if);
+  r->theta_stride = up(r->cap_if + 1);
   r->mix_stride = up(RDS_HM + r->cap_if);
   r->rs_stride = up(RDS_HS + r->cap_out);
   r->rrc_stride = up(r->cap_out);
@@ -815,7 +1005,7 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
   for (int ph = 0; ph < r->U; ++ph)
     for (int k = 0; k < RDS_TP; ++k) poly[(size_t)ph * RDS_POLY_PITCH + k] = hr[(size_t)ph + (size_t)k * r->U];
   bool ok = !r->poly.alloc(poly.size()) && !r->chan.alloc(B * r->chan_stride) &&
-            !r->carr.alloc(B * r->carr_stride) && !r->mixI.alloc(B * r->mix_stride) &&
+            !r->carr.alloc(B * r->carr_stride) && !r->theta.alloc(B * r->theta_stride) && !r->mixI.alloc(B * r->mix_stride) &&
             !r->mixQ.alloc(B * r->mix_stride) && !r->rsI.alloc(B * r->rs_stride) &&
             !r->rsQ.alloc(B * r->rs_stride) && !r->rrcI.alloc(B * r->rrc_stride) &&
             !r->rrcQ.alloc(B * r->rrc_stride) && !r->pll.alloc(B * 8) &&
