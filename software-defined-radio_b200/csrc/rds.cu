@@ -48,7 +48,6 @@ constexpr int RDS_HM = 104;  // mixer history prefix: the resampler reaches 100 
 constexpr int RDS_HS = 104;  // resampler-output history prefix: the RRC reaches 100 back
 constexpr int RDS_DELAY = (RDS_T - 1) / 2;  // fmRDS.py:178 state_rds_allpass
 constexpr int RDS_CDR_START = 158;          // fmRDS.py:259 start_init
-constexpr int RDS_POLY_PITCH = 104;
 
 template <int T>
 struct DTaps {
@@ -328,8 +327,8 @@ static __global__ void __launch_bounds__(256) k_rds_mix(const RdsMixArgs a) {
 
 // ---------------------------------------------------------------------------
 // R4: rational resampler (fmSupportLib.py:388-407): output j takes phase (jD mod U) of the
-// 101*U-tap low-pass and the 101 inputs ending at floor(jD/U); gain U.  poly is the filter
-// regrouped by phase, [U][RDS_POLY_PITCH].  I and Q share the taps.
+// 101*U-tap low-pass and the 101 inputs ending at floor(jD/U); gain U.
+// I and Q share the taps.
 // ---------------------------------------------------------------------------
 struct RdsResampleArgs {
   const double *mixI, *mixQ;
@@ -338,61 +337,101 @@ struct RdsResampleArgs {
   double *rsI, *rsQ;
   size_t rs_stride;
   int rs_off;
-  const double *poly;
+  const double *quad;  // [U][quad_rows][4]
   int U, D, n_out;
 };
 
-// Lanes are captures: a warp computes one output for 32 captures at a time, so the 101 taps of
-// that output's phase are warp-uniform (one broadcast load each) and the inputs come from a
-// shared-memory tile stored [time][capture] (pitch 33: the transposing stores and the
-// per-capture reads are both conflict-free).  A block owns J consecutive outputs of 32
-// captures; results go back through shared memory so that global stores are contiguous.
-constexpr int RDS_RS_J = 16;      // outputs per block
+// Lanes are captures and a warp computes FOUR consecutive outputs at a time for 32 captures.
+// The four outputs' input windows overlap (consecutive outputs start D/U = 3.9 or 2.4 samples
+// apart and each reaches 101 samples back), so the warp walks the union of the windows once,
+// newest sample first: one 64-bit shared-memory read per sample and component feeds four
+// accumulators.  The four taps that meet a sample come from a host-built table indexed by the
+// phase of the quad's first output, [U][rows][4], laid out in walk order with zeros where a
+// sample lies outside an output's window -- warp-uniform 16-byte loads.  Every accumulator
+// still sees its 101 products in ascending tap order.  (The first version, one output per
+// warp pass, spent 69 % of the shared-memory/L1 data pipe on 10 % of the FP64 pipe: 2.27 ms.)
+// The input tile is stored [time][capture] (pitch 33: transposing fill and per-capture reads
+// are both conflict-free) and filled with asynchronous 8-byte copies; a block owns 16
+// consecutive outputs of 32 captures and writes its results back through shared memory so
+// that global stores are contiguous.
+constexpr int RDS_RS_J = 16;      // outputs per block (4 quads, one per warp)
 constexpr int RDS_RS_PITCH = 33;  // doubles per tile row
 
-static __global__ void __launch_bounds__(256) k_rds_resample(const RdsResampleArgs a, int batch, int rows_cap) {
-  extern __shared__ double rs_sm[];
+static __global__ void __launch_bounds__(128) k_rds_resample(const RdsResampleArgs a, int batch, int rows_cap,
+                                                             int n_in, int quad_rows) {
+  extern __shared__ __align__(16) double rs_sm[];
   double *tI = rs_sm;
   double *tQ = tI + (size_t)rows_cap * RDS_RS_PITCH;
   double *oI = tQ + (size_t)rows_cap * RDS_RS_PITCH;  // [32][J+1]
   double *oQ = oI + 32 * (RDS_RS_J + 1);
+  // [4 quads][quad_rows][2], on the next 16-byte boundary
+  double2 *tabs = reinterpret_cast<double2 *>(rs_sm + (((size_t)2 * rows_cap * RDS_RS_PITCH + 2 * 32 * (RDS_RS_J + 1) + 1) & ~(size_t)1));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j0 = blockIdx.x * RDS_RS_J;
+  // this block's four table entries, fetched alongside the tile (read in place they cost one
+  // L2 round trip per 128-byte line inside the tap loop: 3.5 ms instead of 2.3 ms)
+  for (int i = threadIdx.x; i < 4 * quad_rows * 2; i += 128) {
+    const int w = i / (quad_rows * 2), e = i % (quad_rows * 2);
+    const int p0w = (int)(((long long)(j0 + 4 * w) * a.D) % a.U);
+    const double2 *src = reinterpret_cast<const double2 *>(a.quad) + (size_t)p0w * quad_rows * 2 + e;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(tabs + i)), "l"(src) : "memory");
+  }
   const int b0 = blockIdx.y * 32;
-  const int jn = min(RDS_RS_J, a.n_out - j0);
-  const long long base0 = ((long long)j0 * a.D) / a.U;               // newest input of the first output
-  const long long baseL = ((long long)(j0 + jn - 1) * a.D) / a.U;    // ... of the last one
-  const long long lo = base0 - (RDS_TP - 1);                         // oldest input needed
+  const long long base0 = ((long long)j0 * a.D) / a.U;                        // newest input of the first output
+  const long long baseL = ((long long)(j0 + RDS_RS_J - 1) * a.D) / a.U;       // ... of the last one (may lie past the data)
+  const long long lo = base0 - (RDS_TP - 1);                                  // oldest input needed
   const int rows = (int)(baseL - lo + 1);
-  for (int c = warp; c < 32; c += 8) {
-    if (b0 + c >= batch) continue;
-    const double *sI = a.mixI + (size_t)(b0 + c) * a.mix_stride + a.mix_off + lo;
-    const double *sQ = a.mixQ + (size_t)(b0 + c) * a.mix_stride + a.mix_off + lo;
+  for (int c = warp; c < 32; c += 4) {
+    const int bc = min(b0 + c, batch - 1);
+    const double *sI = a.mixI + (size_t)bc * a.mix_stride + a.mix_off + lo;
+    const double *sQ = a.mixQ + (size_t)bc * a.mix_stride + a.mix_off + lo;
     for (int q = lane; q < rows; q += 32) {
-      tI[q * RDS_RS_PITCH + c] = sI[q];
-      tQ[q * RDS_RS_PITCH + c] = sQ[q];
+      double *dI = tI + q * RDS_RS_PITCH + c, *dQ = tQ + q * RDS_RS_PITCH + c;
+      if (lo + q < n_in) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dI)), "l"(sI + q) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dQ)), "l"(sQ + q) : "memory");
+      } else {  // past the end of the call: only zero taps of outputs that are not stored meet these
+        *dI = 0.0;
+        *dQ = 0.0;
+      }
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  for (int jj = warp; jj < jn; jj += 8) {
-    const long long m = (long long)(j0 + jj) * a.D;
-    const int phase = (int)(m % a.U);
-    const int top = (int)(m / a.U - lo);
-    const double *h = a.poly + (size_t)phase * RDS_POLY_PITCH;
+  const int jq = j0 + 4 * warp;  // first output of this warp's quad
+  if (jq < a.n_out) {
+    const long long m = (long long)jq * a.D;
+    const int p0 = (int)(m % a.U);
+    const int span = (p0 + 3 * a.D) / a.U;                 // newest input of output 3 - that of output 0
+    const int top = (int)(m / a.U + span - lo);            // tile row of the newest input of output 3
+    const int n_rows = RDS_TP + span;
+    const double2 *tq = tabs + (size_t)warp * quad_rows * 2;
     const double *xi = tI + (size_t)top * RDS_RS_PITCH + lane;
     const double *xq = tQ + (size_t)top * RDS_RS_PITCH + lane;
-    double accI = 0.0, accQ = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < RDS_TP; ++k) {
-      const double hk = __ldg(h + k);
-      accI = fma(hk, xi[-k * RDS_RS_PITCH], accI);
-      accQ = fma(hk, xq[-k * RDS_RS_PITCH], accQ);
+    double aI[4] = {0.0, 0.0, 0.0, 0.0}, aQ[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+    for (int r = 0; r < n_rows; ++r) {
+      const double2 h01 = tq[2 * r], h23 = tq[2 * r + 1];
+      const double vi = xi[-r * RDS_RS_PITCH], vq = xq[-r * RDS_RS_PITCH];
+      aI[0] = fma(h01.x, vi, aI[0]);
+      aI[1] = fma(h01.y, vi, aI[1]);
+      aI[2] = fma(h23.x, vi, aI[2]);
+      aI[3] = fma(h23.y, vi, aI[3]);
+      aQ[0] = fma(h01.x, vq, aQ[0]);
+      aQ[1] = fma(h01.y, vq, aQ[1]);
+      aQ[2] = fma(h23.x, vq, aQ[2]);
+      aQ[3] = fma(h23.y, vq, aQ[3]);
     }
-    oI[lane * (RDS_RS_J + 1) + jj] = __dmul_rn(accI, (double)a.U);  // fmSupportLib.py:400
-    oQ[lane * (RDS_RS_J + 1) + jj] = __dmul_rn(accQ, (double)a.U);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      oI[lane * (RDS_RS_J + 1) + 4 * warp + i] = __dmul_rn(aI[i], (double)a.U);  // fmSupportLib.py:400
+      oQ[lane * (RDS_RS_J + 1) + 4 * warp + i] = __dmul_rn(aQ[i], (double)a.U);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * RDS_RS_J; i += 256) {
+  const int jn = min(RDS_RS_J, a.n_out - j0);
+  for (int i = threadIdx.x; i < 32 * RDS_RS_J; i += 128) {
     const int c = i / RDS_RS_J, jj = i % RDS_RS_J;
     if (b0 + c < batch && jj < jn) {
       a.rsI[(size_t)(b0 + c) * a.rs_stride + a.rs_off + j0 + jj] = oI[c * (RDS_RS_J + 1) + jj];
@@ -630,11 +669,12 @@ struct sdr_rds {
   int mode = 0, U = 0, D = 0, sps = 0;
   int block_if = 0, block_out = 0, block_bytes = 0;
   int blocks_cap = 0, bits_cap = 0;
+  int quad_rows = 0;  // rows of one entry of the resampler's quad table
   size_t cap_if = 0, cap_out = 0;
   size_t chan_stride = 0, carr_stride = 0, theta_stride = 0, mix_stride = 0, rs_stride = 0, rrc_stride = 0, nco_stride = 0;
   DTaps<RDS_T> h_chan{}, h_carr{};
   DTaps<RDS_TP> h_rrc{};
-  RBuf<double> poly, chan, carr, theta, mixI, mixQ, rsI, rsQ, rrcI, rrcQ, ncoI, ncoQ, pll;
+  RBuf<double> quad, chan, carr, theta, mixI, mixQ, rsI, rsQ, rrcI, rrcQ, ncoI, ncoQ, pll;
   RBuf<float> hist32;
   RBuf<uint8_t> bits;
   RBuf<int> counts;
@@ -680,7 +720,9 @@ static int rds_reset_device(sdr_rds *r) {
 
 static int segs_for(int n, int tile, int batch, int z, int *outs_per_seg) {
   const int n_tiles = (n + tile - 1) / tile;
-  int want = (1184 + batch * z - 1) / (batch * z);  // ~ 148 SMs x 8 CTAs
+  // enough blocks for ~10 waves of 148 SMs x 12 resident CTAs: a grid of one or two waves
+  // (the first version: 2048 blocks = 1.15 waves) leaves most SMs idle during the last one
+  int want = (16384 + batch * z - 1) / (batch * z);
   want = std::max(1, std::min(want, n_tiles));
   const int per = (n_tiles + want - 1) / want;
   *outs_per_seg = per * tile;
@@ -788,16 +830,17 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     a.rsQ = r->rsQ.p;
     a.rs_stride = r->rs_stride;
     a.rs_off = RDS_HS;
-    a.poly = r->poly.p;
+    a.quad = r->quad.p;
     a.U = r->U;
     a.D = r->D;
     a.n_out = n_out;
     const int rows_cap = (int)(((long long)(RDS_RS_J - 1) * r->D) / r->U) + 2 + RDS_TP;
-    const size_t smem = ((size_t)2 * rows_cap * RDS_RS_PITCH + (size_t)2 * 32 * (RDS_RS_J + 1)) * sizeof(double);
+    const size_t smem = ((size_t)2 * rows_cap * RDS_RS_PITCH + (size_t)2 * 32 * (RDS_RS_J + 1) + 2 +
+                         (size_t)4 * r->quad_rows * 4) * sizeof(double);
     dim3 grid((n_out + RDS_RS_J - 1) / RDS_RS_J, (B + 31) / 32);
     sdr_prof_begin(p, "k_rds_resample", s);
     cudaFuncSetAttribute(k_rds_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_rds_resample<<<grid, 256, smem, s>>>(a, B, rows_cap);
+    k_rds_resample<<<grid, 128, smem, s>>>(a, B, rows_cap, n, r->quad_rows);
     if ((rc = sdr_check_launch(p, "k_rds_resample"))) return rc;
   }
   {  // R5
@@ -1001,10 +1044,20 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
   std::memcpy(r->h_chan.h, hc.data(), sizeof(r->h_chan.h));
   std::memcpy(r->h_carr.h, hk.data(), sizeof(r->h_carr.h));
   std::memcpy(r->h_rrc.h, hq.data(), sizeof(r->h_rrc.h));
-  std::vector<double> poly((size_t)r->U * RDS_POLY_PITCH, 0.0);
-  for (int ph = 0; ph < r->U; ++ph)
-    for (int k = 0; k < RDS_TP; ++k) poly[(size_t)ph * RDS_POLY_PITCH + k] = hr[(size_t)ph + (size_t)k * r->U];
-  bool ok = !r->poly.alloc(poly.size()) && !r->chan.alloc(B * r->chan_stride) &&
+  // Quad table of the resampler: for a quad whose first output has phase p0, output i has
+  // phase (p0 + i*D) mod U and its newest input lies floor((p0 + i*D)/U) samples after that of
+  // output 0; row r of the entry is the sample r steps before the newest input of output 3.
+  r->quad_rows = RDS_TP + (r->U - 1 + 3 * r->D) / r->U;
+  std::vector<double> quad((size_t)r->U * r->quad_rows * 4, 0.0);
+  for (int p0 = 0; p0 < r->U; ++p0) {
+    const int span = (p0 + 3 * r->D) / r->U;
+    for (int i = 0; i < 4; ++i) {
+      const int ph = (p0 + i * r->D) % r->U, off = (p0 + i * r->D) / r->U;
+      for (int k = 0; k < RDS_TP; ++k)
+        quad[((size_t)p0 * r->quad_rows + (size_t)(k + span - off)) * 4 + i] = hr[(size_t)ph + (size_t)k * r->U];
+    }
+  }
+  bool ok = !r->quad.alloc(quad.size()) && !r->chan.alloc(B * r->chan_stride) &&
             !r->carr.alloc(B * r->carr_stride) && !r->theta.alloc(B * r->theta_stride) && !r->mixI.alloc(B * r->mix_stride) &&
             !r->mixQ.alloc(B * r->mix_stride) && !r->rsI.alloc(B * r->rs_stride) &&
             !r->rsQ.alloc(B * r->rs_stride) && !r->rrcI.alloc(B * r->rrc_stride) &&
@@ -1014,9 +1067,9 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
             !r->counts.alloc(B * (size_t)r->blocks_cap);
   if (ok && r->keep_nco) ok = !r->ncoI.alloc(B * r->nco_stride) && !r->ncoQ.alloc(B * r->nco_stride);
   if (!ok) { delete r; return SDR_ERR_NOMEM; }
-  if (cudaMemcpy(r->poly.p, poly.data(), poly.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+  if (cudaMemcpy(r->quad.p, quad.data(), quad.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
     delete r;
-    return fail(SDR_ERR_CUDA, "RDS: uploading the polyphase table failed");
+    return fail(SDR_ERR_CUDA, "RDS: uploading the resampler table failed");
   }
   r->h_bits.assign(B * (size_t)r->blocks_cap * (size_t)r->bits_cap, 0);
   r->h_counts.assign(B * (size_t)r->blocks_cap, 0);
