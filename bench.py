@@ -91,20 +91,25 @@ class ClockSampler(threading.Thread):
 # /root/reference, else the oracle port), all host threads, bounded sample of the same workload
 # --------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    kind, mode, channels, seed, n_blocks, reps = args
+    kind, mode, channels, seed, n_blocks, reps, rds = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orclib
     from sdr_b200 import siggen
     lib = orclib.REF() if kind == "reference" else orclib.ORC()
-    iq = siggen.make_capture(seed, mode, n_blocks, "stereo")
+    iq = siggen.make_capture(seed, mode, n_blocks, "rds" if rds else "stereo")
+    rdo = orclib.RDS() if rds else None
     t0 = time.perf_counter()
     for _ in range(reps):
-        lib.run_chain(iq, mode, channels, TAPS["rf_taps"], TAPS["audio_taps"], TAPS["stereo_taps"],
-                      keep_taps=False)
+        _, taps = lib.run_chain(iq, mode, channels, TAPS["rf_taps"], TAPS["audio_taps"], TAPS["stereo_taps"],
+                                keep_taps=rds)
+        if rds:  # the RDS model has no C++ form: the oracle's C restatement of fmRDS.py follows
+            fm = taps["demod"].astype(np.float64)
+            rdo.run_chain(fm[:fm.size // 9600 * 9600], mode, 9600, keep=())
     return time.perf_counter() - t0, reps * iq.size // 2
 
 
-def cpu_baseline(mode: int, channels: int, seconds: float = 12.0, cores: int | None = None):
+def cpu_baseline(mode: int, channels: int, seconds: float = 12.0, cores: int | None = None,
+                 rds: bool = False):
     """Times the CPU path on `cores` processes, one independent capture each (embarrassingly
     parallel, like the GPU batch).  Returns (MS/s, kind, cores, sample description)."""
     import multiprocessing as mp
@@ -113,18 +118,21 @@ def cpu_baseline(mode: int, channels: int, seconds: float = 12.0, cores: int | N
     import sdr_b200  # noqa: F401  (registers the package alias for the workers)
     kind = "reference" if orclib.REF() is not None else "port"
     cores = cores or os.cpu_count() or 1
-    n_blocks = 8
+    n_blocks = ({0: 15, 2: 12}[mode] if rds else 8)
     # calibrate one capture on one core, then size reps for ~`seconds` of work per core
-    t, n = _cpu_worker((kind, mode, channels, 0, n_blocks, 1))
+    t, n = _cpu_worker((kind, mode, channels, 0, n_blocks, 1, rds))
     reps = max(1, int(seconds / max(t, 1e-3)))
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(kind, mode, channels, c, n_blocks, reps) for c in range(cores)])
+        res = pool.map(_cpu_worker, [(kind, mode, channels, c, n_blocks, reps, rds) for c in range(cores)])
     wall = time.perf_counter() - t0
     total = sum(r[1] for r in res)
     sample = (f"{cores} captures x {n_blocks} reference blocks x {reps} passes, mode {mode}, "
               f"{'stereo' if channels == 2 else 'mono'}, taps 151/101/151, one process per core")
+    if rds:
+        sample += "; receiver chain as above + the oracle's C restatement of the Python RDS model"
+        kind = "port"
     return total / wall / 1e6, kind, cores, sample
 
 
@@ -136,7 +144,7 @@ def run_reference(args):
     per_step = max(1.0, min(20.0, 90.0 / (steps + args.warmup)))
     vals = []
     for i in range(args.warmup + steps):
-        v, kind, cores, sample = cpu_baseline(args.mode, args.audio_channels, seconds=per_step)
+        v, kind, cores, sample = cpu_baseline(args.mode, args.audio_channels, seconds=per_step, rds=args.rds)
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
@@ -383,7 +391,7 @@ def run_ours(args):
                         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()}}
         cb = None
         if world == 1 and not args.no_cpu_baseline:
-            v, kind, cores, sample = cpu_baseline(args.mode, args.audio_channels, seconds=10.0)
+            v, kind, cores, sample = cpu_baseline(args.mode, args.audio_channels, seconds=10.0, rds=args.rds)
             cb = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -55,11 +55,84 @@ def _rds_baseband(rng: np.random.Generator, t: np.ndarray) -> np.ndarray:
     return chips[idx] * np.sin(np.pi * (pos - idx))
 
 
+# ---- RDS with a known group sequence ---------------------------------------------------------
+# Parity-check matrix and offset-word syndromes of the RDS standard as the reference's model
+# holds them (model/fmSupportLib.py:32-57, :62-91).
+_RDS_H = np.array([
+    [1,0,0,0,0,0,0,0,0,0], [0,1,0,0,0,0,0,0,0,0], [0,0,1,0,0,0,0,0,0,0], [0,0,0,1,0,0,0,0,0,0],
+    [0,0,0,0,1,0,0,0,0,0], [0,0,0,0,0,1,0,0,0,0], [0,0,0,0,0,0,1,0,0,0], [0,0,0,0,0,0,0,1,0,0],
+    [0,0,0,0,0,0,0,0,1,0], [0,0,0,0,0,0,0,0,0,1], [1,0,1,1,0,1,1,1,0,0], [0,1,0,1,1,0,1,1,1,0],
+    [0,0,1,0,1,1,0,1,1,1], [1,0,1,0,0,0,0,1,1,1], [1,1,1,0,0,1,1,1,1,1], [1,1,0,0,0,1,0,0,1,1],
+    [1,1,0,1,0,1,0,1,0,1], [1,1,0,1,1,1,0,1,1,0], [0,1,1,0,1,1,1,0,1,1], [1,0,0,0,0,0,0,0,0,1],
+    [1,1,1,1,0,1,1,1,0,0], [0,1,1,1,1,0,1,1,1,0], [0,0,1,1,1,1,0,1,1,1], [1,0,1,0,1,0,0,1,1,1],
+    [1,1,1,0,0,0,1,1,1,1], [1,1,0,0,0,1,1,0,1,1]], dtype=np.int64)
+_RDS_SYNDROME = {"A": [1,1,1,1,0,1,1,0,0,0], "B": [1,1,1,1,0,1,0,1,0,0], "C": [1,0,0,1,0,1,1,1,0,0],
+                 "D": [1,0,0,1,0,1,1,0,0,0]}
+_RDS_CHECKS = np.array([[(c >> (9 - i)) & 1 for i in range(10)] for c in range(1024)], dtype=np.int64)
+_RDS_CHECK_SYN = _RDS_CHECKS @ _RDS_H[16:] % 2
+# Delay of the chip clock that puts the chip centres, after every filter of the receiver, on the
+# model's fixed sampling grid 158 + i*SPS (model/fmRDS.py:259): measured with the oracle.
+_RDS_CHIP_DELAY = {0: 2.0 / 61_750.0, 2: 19.0 / 102_125.0}
+
+
+def rds_block(info16: np.ndarray, offset: str) -> np.ndarray:
+    """26-bit RDS block: 16 information bits + the 10 check bits that give the block the
+    syndrome of `offset` ('A', 'B', 'C' or 'D') under the model's parity-check matrix."""
+    need = (np.array(_RDS_SYNDROME[offset]) + np.asarray(info16, np.int64) @ _RDS_H[:16]) % 2
+    idx = np.where((_RDS_CHECK_SYN == need).all(axis=1))[0]
+    assert idx.size == 1
+    return np.concatenate((np.asarray(info16, np.int64), _RDS_CHECKS[idx[0]]))
+
+
+def rds_group_bits(channel: int, mode: int, n_blocks: int) -> np.ndarray:
+    """The bit sequence (before differential encoding) that kind="rds_groups" transmits: groups
+    of four valid blocks A, B, C, D with seed-drawn information words."""
+    m = MODES[mode]
+    seconds = n_blocks * m["block_bytes"] // 2 / float(m["rf_Fs"])
+    nbits = int(seconds * 1187.5) + 64
+    rng = np.random.default_rng(SEED_BASE + 7919 * (channel + 1))
+    blocks = []
+    while 26 * len(blocks) < nbits:
+        for off in "ABCD":
+            blocks.append(rds_block(rng.integers(0, 2, 16), off))
+    return np.concatenate(blocks)[:nbits].astype(np.uint8)
+
+
+def _rrc_pulse(t: np.ndarray, T: float, beta: float = 0.9) -> np.ndarray:
+    x = t / T
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = (np.sin(np.pi * x * (1 - beta)) + 4 * beta * x * np.cos(np.pi * x * (1 + beta))) / \
+              (np.pi * x * (1 - (4 * beta * x) ** 2))
+    out[np.abs(x) < 1e-9] = 1 - beta + 4 * beta / np.pi
+    out[np.abs(np.abs(x) - 1 / (4 * beta)) < 1e-9] = beta / np.sqrt(2) * (
+        (1 + 2 / np.pi) * np.sin(np.pi / (4 * beta)) + (1 - 2 / np.pi) * np.cos(np.pi / (4 * beta)))
+    return out
+
+
+def _rds_group_baseband(bits: np.ndarray, t: np.ndarray, delay: float) -> np.ndarray:
+    """Differential encoding, biphase chips at 2375 chips/s (bit 1 = high, low), each chip a
+    root-raised-cosine pulse (roll-off 0.9, the receiver's matched filter)."""
+    d = np.bitwise_xor.accumulate(bits.astype(np.int64))
+    chips = np.empty(2 * d.size)
+    chips[0::2] = 2.0 * d - 1.0
+    chips[1::2] = -(2.0 * d - 1.0)
+    T = 1.0 / 2375.0
+    n0 = np.floor((t - delay) / T).astype(np.int64)
+    s = np.zeros_like(t)
+    for k in range(-3, 5):
+        n = n0 + k
+        ok = (n >= 0) & (n < chips.size)
+        s += np.where(ok, chips[np.clip(n, 0, chips.size - 1)], 0.0) * _rrc_pulse(t - delay - n * T, T)
+    return s
+
+
 def make_capture(channel: int, mode: int, n_blocks: int, kind: str = "stereo",
                  cnr_db: float | None = None) -> np.ndarray:
     """Return ``n_blocks`` reference blocks of interleaved uint8 I/Q for one channel.
 
     kind: "mono" (L+R only), "stereo" (pilot + 38 kHz DSB-SC), "rds" (stereo + 57 kHz RDS),
+          "rds_groups" (stereo + an RDS subcarrier that carries rds_group_bits(): valid groups
+          of blocks A-D, root-raised-cosine chips timed for the model's sampling grid; modes 0, 2),
           "silence" (all bytes 128: exercises fmDemod's zero-denominator branch,
           src/filter.cpp:254), "clipped" (over-driven, saturating the 8-bit range).
     """
@@ -73,6 +146,12 @@ def make_capture(channel: int, mode: int, n_blocks: int, kind: str = "stereo",
     left = _audio(rng, t)
     right = _audio(rng, t)
     mpx = 0.45 * (left + right)
+    if kind == "rds_groups":
+        bits = rds_group_bits(channel, mode, n_blocks)
+        mpx = 0.4 * (left + right) + 0.1 * np.sin(2 * np.pi * 19_000.0 * t)
+        mpx = mpx + 0.4 * (left - right) * np.sin(2 * np.pi * 38_000.0 * t)
+        mpx = mpx + 0.08 * _rds_group_baseband(bits, t, _RDS_CHIP_DELAY[mode]) * \
+            np.cos(2 * np.pi * 57_000.0 * t + 0.3)
     if kind in ("stereo", "rds", "clipped"):
         mpx = mpx + 0.1 * np.sin(2 * np.pi * 19_000.0 * t)
         mpx = mpx + 0.45 * (left - right) * np.sin(2 * np.pi * 38_000.0 * t)
