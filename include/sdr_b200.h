@@ -197,7 +197,8 @@ int sdr_pipeline_kernel_times(sdr_pipeline *p, int index, char *name, size_t nam
 /* Once created, the chain runs at the end of every sdr_pipeline_process_*    */
 /* call of its pipeline (same stream); the pipeline's granule becomes one     */
 /* RDS block (sdr_rds_info.block_bytes).  sdr_pipeline_reset resets it too.   */
-/* Destroy the sdr_rds handle before its pipeline.                            */
+/* Destroy the sdr_rds handle before its pipeline.  sdr_pipeline_copy_state   */
+/* does not copy the RDS chain's state.                                       */
 /* ------------------------------------------------------------------------ */
 typedef struct sdr_rds sdr_rds;
 

@@ -15,6 +15,13 @@
 //            --blocks N               reference blocks per device call (default 1 = the
 //                                     reference's latency; larger is faster)
 //            --device D               CUDA ordinal
+//            --rds FILE               modes 0 and 2: also run the RDS chain of the reference's
+//                                     Python model (model/fmRDS.py:222-276) and write one line per
+//                                     RDS block to FILE: "<block> <offset> <bits>" with the frame
+//                                     synchroniser's result (A, B, C, c = C', D or -) and the
+//                                     differentially decoded bits.  Input is then consumed in
+//                                     units of 15 (mode 0) / 12 (mode 2) reference blocks, the
+//                                     smallest span that is whole in both block sizes.
 //
 // The reference's two threads and bounded std::queue (project.cpp:141-149,181-189,471-496)
 // become: a reader thread filling two page-locked buffers, and the main thread handing
@@ -49,7 +56,7 @@ int die(const char *what) {
 
 void usage(const char *argv0) {
   std::fprintf(stderr,
-               "Usage: %s\nor\nUsage: %s <mode> [<channels>] [--taps rf,audio,stereo] [--blocks N] [--device D]\n"
+               "Usage: %s\nor\nUsage: %s <mode> [<channels>] [--taps rf,audio,stereo] [--blocks N] [--device D] [--rds FILE]\n"
                "\t\t <mode> is a value from 0 to 3, <channels> is 1 (mono) or 2 (stereo)\n",
                argv0, argv0);
 }
@@ -60,6 +67,7 @@ int main(int argc, char *argv[]) {
   int mode = 0, channels = 1, device = 0, blocks = 1;
   int rf_taps = 151, audio_taps = 101, stereo_taps = 151;
   std::vector<std::string> pos;
+  std::string rds_path;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "--taps" && i + 1 < argc) {
@@ -71,6 +79,8 @@ int main(int argc, char *argv[]) {
       blocks = std::atoi(argv[++i]);
     } else if (a == "--device" && i + 1 < argc) {
       device = std::atoi(argv[++i]);
+    } else if (a == "--rds" && i + 1 < argc) {
+      rds_path = argv[++i];
     } else if (a == "-h" || a == "--help") {
       usage(argv[0]);
       return 0;
@@ -97,7 +107,17 @@ int main(int argc, char *argv[]) {
 
   sdr_mode_info mi;
   if (sdr_mode_lookup(mode, channels, &mi)) return die("sdr_mode_lookup");
-  const size_t block_bytes = (size_t)mi.block_bytes;  // project.cpp:55-57
+  size_t block_bytes = (size_t)mi.block_bytes;  // project.cpp:55-57
+  if (!rds_path.empty()) {
+    if (mode != 0 && mode != 2) {  // fmRDS.py:55-75 defines the RDS parameters for these two only
+      std::fprintf(stderr, "RDS is defined for modes 0 and 2 only\n");
+      return 1;
+    }
+    // one RDS block = 9600 IF samples (fmRDS.py:149) = 192000 bytes; consume whole blocks of both kinds
+    size_t a = block_bytes, b = 9600 * (size_t)mi.rf_decim * 2;
+    while (b) { const size_t t = a % b; a = b; b = t; }
+    block_bytes = block_bytes / a * (9600 * (size_t)mi.rf_decim * 2);
+  }
   const size_t call_bytes = block_bytes * (size_t)blocks;
   std::fprintf(stderr, "block_size = %zu, %d block(s) per device call\n", block_bytes, blocks);
 
@@ -113,6 +133,23 @@ int main(int argc, char *argv[]) {
   cfg.max_bytes_per_channel = call_bytes;
   sdr_pipeline *pipe = nullptr;
   if (sdr_pipeline_create(&cfg, &pipe)) return die("sdr_pipeline_create");
+  sdr_rds *rds = nullptr;
+  std::FILE *rds_out = nullptr;
+  sdr_rds_info_t ri{};
+  if (!rds_path.empty()) {
+    sdr_rds_config rc{};
+    rc.block_if = 9600;
+    if (sdr_rds_create(pipe, &rc, &rds) || sdr_rds_info(rds, &ri)) return die("sdr_rds_create");
+    rds_out = std::fopen(rds_path.c_str(), "w");
+    if (!rds_out) {
+      std::perror(rds_path.c_str());
+      return 2;
+    }
+  }
+  std::vector<uint8_t> rds_bits((size_t)ri.max_pending_blocks * (size_t)ri.max_bits_per_block + 1);
+  std::vector<int> rds_counts((size_t)ri.max_pending_blocks + 1);
+  std::vector<char> rds_offsets((size_t)ri.max_pending_blocks + 1);
+  size_t rds_block_index = 0;
   size_t pcm_per_call = 0;
   if (sdr_pipeline_pcm_count(pipe, call_bytes, &pcm_per_call)) return die("sdr_pipeline_pcm_count");
 
@@ -170,6 +207,22 @@ int main(int argc, char *argv[]) {
         break;
       }
       std::fwrite(pcm, sizeof(int16_t), n_pcm, stdout);
+      if (rds) {
+        size_t n_bits = 0, n_blocks = 0;
+        if (sdr_rds_read(rds, 0, nullptr, rds_bits.data(), rds_bits.size(), &n_bits, rds_counts.data(),
+                         rds_offsets.data(), rds_counts.size(), &n_blocks) ||
+            sdr_rds_discard(rds)) {
+          rc = die("sdr_rds_read");
+          break;
+        }
+        size_t at = 0;
+        for (size_t b = 0; b < n_blocks; ++b) {
+          std::fprintf(rds_out, "%zu %c ", rds_block_index++, rds_offsets[b] == ' ' ? '-' : rds_offsets[b]);
+          for (int i = 0; i < rds_counts[b]; ++i) std::fputc('0' + rds_bits[at + (size_t)i], rds_out);
+          std::fputc('\n', rds_out);
+          at += (size_t)rds_counts[b];
+        }
+      }
       total_in += s.bytes;
       total_out += n_pcm;
     }
@@ -188,6 +241,8 @@ int main(int argc, char *argv[]) {
                total_out);
   for (auto &s : slots) sdr_host_free(s.data);
   sdr_host_free(pcm);
+  if (rds_out) std::fclose(rds_out);
+  sdr_rds_destroy(rds);
   sdr_pipeline_destroy(pipe);
   return 0;
 }

@@ -179,7 +179,6 @@ static __global__ void __launch_bounds__(32) k_rds_pll(const RdsPllArgs a) {
   double *st = a.state + (size_t)b * 8;
   double integrator = st[0], phaseEst = st[1], r = st[2];
   const double n0 = st[5];
-  const double *in = a.carr + (size_t)b * a.carr_stride;
   double *th = a.theta + (size_t)b * a.theta_stride + 1;  // (shadow lanes store the same values as the lane they shadow)
   // fmSupportLib.py:340: 2*pi*(freq/Fs), left to right
   const double w = __dmul_rn(__dmul_rn(2.0, RDS_PI), __ddiv_rn(a.freq, a.Fs));

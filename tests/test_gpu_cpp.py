@@ -42,3 +42,27 @@ def test_project_cli_stdin_to_stdout(orc, argv, mode, ch):
 def test_project_cli_rejects_bad_mode():
     r = subprocess.run([os.path.join(PKG, "sdr_project"), "7"], input=b"", capture_output=True, timeout=60)
     assert r.returncode == 1 and b"Wrong mode" in r.stderr
+
+
+@pytest.mark.parametrize("mode,n_ref", [(0, 30), (2, 24)])
+def test_project_cli_rds(orc, tmp_path, mode, n_ref):
+    """`sdr_project <mode> 1 --rds FILE`: PCM on stdout as before, one line per RDS block in FILE
+    with the frame synchroniser's result and the differentially decoded bits -- identical to
+    the oracle's restatement of model/fmRDS.py:222-276 on the same fm_demod."""
+    import orclib
+    iq = siggen.make_capture(5, mode, n_ref, "rds_groups")
+    out = tmp_path / "rds.txt"
+    r = subprocess.run([os.path.join(PKG, "sdr_project"), str(mode), "1", "--rds", str(out)],
+                       input=iq.tobytes(), capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    want_pcm, taps = orc.run_chain(iq, mode, 1)
+    assert np.array_equal(np.frombuffer(r.stdout, dtype=np.int16), want_pcm)
+    fm = taps["demod"].astype(np.float64)
+    want = orclib.RDS().run_chain(fm[:fm.size // 9600 * 9600], mode, 9600, keep=())
+    lines = out.read_text().splitlines()
+    assert len(lines) == len(want["diff_bits"])
+    for i, line in enumerate(lines):
+        idx, off, *bits = line.split(" ")
+        assert int(idx) == i
+        assert off == (want["offsets"][i] if want["offsets"][i] != " " else "-")
+        assert (bits[0] if bits else "") == "".join(str(int(b)) for b in want["diff_bits"][i])
