@@ -88,6 +88,20 @@ def test_chain_matches_golden(orc, mode):
                 assert str(g[f"{key}_sha_{name}"]) == sha(arr), (key, name)
 
 
+def test_chain_matches_golden_on_recorded_iq(orc):
+    """The only recorded I/Q data the reference ships (two blocks its front end printed into
+    data/data/pipeData.txt; tests/golden/make_golden_real.py recovers the bytes) and what the
+    unmodified reference makes of it."""
+    g = np.load(os.path.join(GOLD, "real_iq.npz"))
+    for ch in (1, 2):
+        for tname, taps in TAPSETS.items():
+            pcm, t = orc.run_chain(g["iq"], 0, ch, *taps)
+            key = f"c{ch}_{tname}"
+            assert np.array_equal(pcm, g[key + "_pcm"]), key
+            for name, arr in t.items():
+                assert str(g[f"{key}_sha_{name}"]) == sha(arr), (key, name)
+
+
 @pytest.mark.parametrize("mode,ch", [(0, 1), (0, 2), (1, 2), (2, 1), (2, 2), (3, 2)])
 def test_chain_matches_compiled_reference(orc, ref, mode, ch):
     iq = siggen.make_capture(7 * mode + ch, mode, 3, "stereo")
