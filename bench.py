@@ -162,11 +162,20 @@ def run_reference(args):
 
 
 def workload_config(args):
+    if args.mixed:
+        return {"workload": f"mode {args.mode} mixed: {args.batch // 2} mono + {args.batch // 2} stereo captures per "
+                            f"GPU x {args.blocks} reference blocks ({args.blocks * BLOCK_BYTES[args.mode]} B each), "
+                            f"{args.streams} pipeline handles on {args.streams} CUDA streams, taps 151/101/151",
+                "mode": args.mode, "audio_channels": "1+2", "batch_per_gpu": args.batch,
+                "blocks_per_capture": args.blocks, "streams": args.streams,
+                "l2_policy": "input batch larger than L2 (no flush needed)",
+                "variant": "mono: fast (+-1 LSB), stereo: exact (bit-identical)"}
     return {"workload": f"mode {args.mode} {'stereo' if args.audio_channels == 2 else 'mono'}, "
                         f"{args.batch} captures per GPU x {args.blocks} reference blocks "
                         f"({args.blocks * BLOCK_BYTES[args.mode]} B each), taps rf 151 / audio 101"
                         f"{' / stereo 151' if args.audio_channels == 2 else ''}"
-                        f"{' + RDS chain (fmRDS.py model, double precision, 9600-sample blocks)' if args.rds else ''}",
+                        f"{' + RDS chain (fmRDS.py model, double precision, 9600-sample blocks)' if args.rds else ''}"
+                        f"{f', {args.streams} pipeline handles on {args.streams} CUDA streams' if args.streams > 1 else ''}",
             "mode": args.mode, "audio_channels": args.audio_channels, "batch_per_gpu": args.batch,
             "blocks_per_capture": args.blocks, "l2_policy": "input batch larger than L2 (no flush needed)",
             "variant": ("fast (tensor-core RF front end; PCM within +-1 LSB of the reference)"
@@ -215,68 +224,109 @@ def pick_variant(sdr, args, mode, audio_channels):
 def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, world, profile=True,
                 force_exact=False):
     """Device-resident timing of one configuration.  Returns dict with ms/step (max over ranks),
-    per-kernel times and launches."""
+    per-kernel times and launches.
+
+    With --streams S the batch is cut into S groups of captures, each owned by its own pipeline
+    handle on its own CUDA stream (captures are independent, handles are independent): kernels
+    that cannot fill the GPU on their own -- the sequential PLL, one lane per capture -- then run
+    beside the other groups' kernels.  With --mixed the first half of the groups is mono (the
+    fast variant unless --variant exact), the second half stereo: BASELINE.json configs[3]."""
     dev = torch.device("cuda", torch.cuda.current_device())
     kind = "rds" if args.rds else "stereo"
     d_iq = make_device_batch(torch, mode, args.batch, args.blocks, kind, dev)
     nbytes = d_iq.shape[1]
-    variant, vname = pick_variant(sdr, args, mode, audio_channels)
-    if force_exact:
-        variant, vname = sdr.VARIANT_EXACT, "exact"
-    p = sdr.Pipeline(mode=mode, channels=audio_channels, batch=args.batch, device=dev.index,
-                     max_bytes_per_channel=nbytes, variant=variant, **TAPS)
-    rds = None
-    if args.rds:
-        # the RDS chain follows every process call on the same stream; its bit buffer is sized
-        # for the whole run so that no host read-back falls inside the timed region
-        if nbytes % 192000:
-            raise SystemExit("--rds needs --blocks such that a capture is a multiple of 192000 B "
-                             "(mode 0: 15, 30, ...; mode 2: 12, 24, ...)")
-        rds = sdr.Rds(p, block_if=9600, max_pending_blocks=(steps + warmup) * (nbytes // 192000))
-    n_pcm = p.pcm_count(nbytes)
-    d_pcm = torch.zeros((args.batch, n_pcm), dtype=torch.int16, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    S = max(1, args.streams)
+    if args.batch % S or (args.mixed and S % 2):
+        raise SystemExit("--batch must be a multiple of --streams (and --streams even with --mixed)")
+    per = args.batch // S
+    groups = []  # (pipeline, rds, rows, d_pcm, stream, variant name)
+    main_stream = torch.cuda.current_stream()
+    for i in range(S):
+        ch = (1 if i < S // 2 else 2) if args.mixed else audio_channels
+        variant, vname = pick_variant(sdr, args, mode, ch)
+        if force_exact:
+            variant, vname = sdr.VARIANT_EXACT, "exact"
+        p = sdr.Pipeline(mode=mode, channels=ch, batch=per, device=dev.index,
+                         max_bytes_per_channel=nbytes, variant=variant, **TAPS)
+        rds = None
+        if args.rds:
+            # the RDS chain follows every process call on the same stream; its bit buffer is sized
+            # for the whole run so that no host read-back falls inside the timed region
+            if nbytes % 192000:
+                raise SystemExit("--rds needs --blocks such that a capture is a multiple of 192000 B "
+                                 "(mode 0: 15, 30, ...; mode 2: 12, 24, ...)")
+            rds = sdr.Rds(p, block_if=9600, max_pending_blocks=(steps + warmup) * (nbytes // 192000))
+        n_pcm = p.pcm_count(nbytes)
+        d_pcm = torch.zeros((per, n_pcm), dtype=torch.int16, device=dev)
+        # alternating priorities: when two groups have throughput kernels ready, one goes first,
+        # so the groups fall out of step and one group's PLL runs beside the other's FIR kernels
+        stream = main_stream if S == 1 else torch.cuda.Stream(device=dev, priority=-(i % 2))
+        groups.append((p, rds, d_iq[i * per:(i + 1) * per], d_pcm, stream, vname))
 
-    def step():
-        p.process_device(d_iq.data_ptr(), d_iq.stride(0), nbytes, d_pcm.data_ptr(), d_pcm.stride(0), stream)
+    def run(n_steps):
+        """n_steps of every group; groups only meet at the start and at the end (no barrier per
+        step: a group's next call may start while another group is still in its PLL)."""
+        if S > 1:
+            fork = torch.cuda.Event()
+            fork.record(main_stream)
+        for (p, _, rows, d_pcm, stream, _) in groups:
+            if S > 1:
+                stream.wait_event(fork)
+            for _ in range(n_steps):
+                p.process_device(rows.data_ptr(), rows.stride(0), nbytes, d_pcm.data_ptr(), d_pcm.stride(0),
+                                 stream.cuda_stream)
+            if S > 1:
+                j = torch.cuda.Event()
+                j.record(stream)
+                main_stream.wait_event(j)
 
-    for _ in range(warmup):
-        step()
+    run(warmup)
     torch.cuda.synchronize()
-    p.launch_count(reset=True)
-    p.profile(profile)
+    for g in groups:
+        g[0].launch_count(reset=True)
+        g[0].profile(profile)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        step()
+    run(steps)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    launches = p.launch_count()
-    ktimes = p.kernel_times(reset=True) if profile else {}
-    p.profile(False)
+    launches = sum(g[0].launch_count() for g in groups)
+    ktimes = {}
+    if profile:
+        for g in groups:  # summed over the groups (with S > 1 they overlap in time)
+            for k, (t, n) in g[0].kernel_times(reset=True).items():
+                a = ktimes.get(k, (0.0, 0))
+                ktimes[k] = (a[0] + t, a[1] + n)
+    for g in groups:
+        g[0].profile(False)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     samples_per_step = args.batch * (nbytes // 2)
-    checksum = int(d_pcm[:, :64].to(torch.int64).abs().sum().item())
+    checksum = int(sum(int(g[3][:, :64].to(torch.int64).abs().sum().item()) for g in groups))
     rds_info = None
-    if rds is not None:
-        rd = rds.read(0)
+    if groups[0][1] is not None:
+        rd = groups[0][1].read(0)
         rds_info = {"blocks": int(rd["bit_counts"].size), "bits_capture0": int(rd["cdr_bits"].size),
                     "offsets_capture0_tail": rd["offsets"][-16:]}
-        rds.close()
-    p.close()
-    del d_iq, d_pcm
+    for g in groups:
+        if g[1] is not None:
+            g[1].close()
+        g[0].close()
+    n_pcm_total = sum(int(g[3].shape[1]) * per for g in groups)
+    vname = "+".join(sorted({g[5] for g in groups}))
+    del d_iq, groups
     torch.cuda.empty_cache()
     return {"ms_per_step": ms / steps, "samples_per_step": samples_per_step, "launches": launches,
-            "kernels": ktimes, "nbytes": nbytes, "n_pcm": n_pcm, "checksum": checksum, "variant": vname, "rds": rds_info}
+            "kernels": ktimes, "nbytes": nbytes, "n_pcm": n_pcm_total // args.batch, "checksum": checksum,
+            "variant": vname, "rds": rds_info, "pcm_values_per_step": n_pcm_total}
 
 
 def time_e2e(torch, sdr, args, steps, dist, world):
@@ -344,7 +394,8 @@ def run_ours(args):
         sampler.join(timeout=3)
         clocks = sampler.summary()
 
-    e2e = None if args.rds else time_e2e(torch, sdr, args, max(2, min(args.steps, 5)), dist, world)
+    e2e = None if (args.rds or args.mixed or args.streams > 1) else \
+        time_e2e(torch, sdr, args, max(2, min(args.steps, 5)), dist, world)
 
     others = {}
     if args.others and world == 1:
@@ -365,6 +416,8 @@ def run_ours(args):
         value = total_samples / (main["ms_per_step"] * 1e-3) / 1e6
         peak, peak_src = measured_peak()
         bps = algorithmic_bytes_per_sample(args.mode, args.audio_channels)
+        if args.mixed:  # 2 B in + the PCM both halves write
+            bps = 0.5 * (algorithmic_bytes_per_sample(args.mode, 1) + algorithmic_bytes_per_sample(args.mode, 2))
         # dominant kernel: the one with the largest total time in the timed region
         kt = main["kernels"]
         dom = max(kt, key=lambda k: kt[k][0]) if kt else None
@@ -390,7 +443,10 @@ def run_ours(args):
                         "whole_step_frac": value * 1e6 * bps / 1e9 / peak / world,
                         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()}}
         cb = None
-        if world == 1 and not args.no_cpu_baseline:
+        if roofline and args.streams > 1:
+            roofline["note"] = ("per-kernel times are summed over the pipeline handles, which overlap in "
+                                "time: shares of the step do not apply; whole_step_frac is the measured one")
+        if world == 1 and not args.no_cpu_baseline and not args.mixed:
             v, kind, cores, sample = cpu_baseline(args.mode, args.audio_channels, seconds=10.0, rds=args.rds)
             cb = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         line = {
@@ -423,12 +479,18 @@ def main():
     ap.add_argument("--e2e-blocks", type=int, default=8)
     ap.add_argument("--others", action="store_true", help="also time mono mode 0 / stereo configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="pipeline handles per GPU, each with batch/streams captures on its own CUDA stream")
+    ap.add_argument("--mixed", action="store_true",
+                    help="half of the handles mono, half stereo (BASELINE configs[3]); needs --streams >= 2")
     ap.add_argument("--rds", action="store_true",
                     help="also run the RDS chain (modes 0/2) behind every step; not the default workload")
     ap.add_argument("--variant", default="fast", choices=["fast", "exact"],
                     help="fast: tensor-core RF front end (mono, +-1 LSB PCM); exact: bit-identical CUDA-core path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.mixed and args.streams < 2:
+        args.streams = 2
     if args.impl == "reference":
         run_reference(args)
     else:
