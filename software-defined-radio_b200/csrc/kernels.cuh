@@ -1280,6 +1280,11 @@ k_bpf_dual(const BpfArgs a, const __grid_constant__ TapArray<taps_groups(T, 1, R
 // ---------------------------------------------------------------------------
 // K5: PLL + NCO (fmPLL, filter.cpp:32-80).  The recurrence is inherently
 // sequential, so one lane owns one capture and walks its samples in order.
+// ncoOut[k+1] = cosf(trigArg*ncoScale + phaseAdjust) (filter.cpp:71) is not fed back, so
+// K5a (k_pll) only stores its ARGUMENT and K5b (k_nco_cos) evaluates the cosines for
+// all samples in parallel.  In one warp the cosine's ~150 instructions, although off the
+// dependency chain, are issued in order between the chain's: 855 cycles per sample with
+// it, 590 without (tools/ubench_pll_chain.cu).
 // The NCO output is written one slot late (slot k+1 at step k) which is exactly
 // the reference's ncoOut vector: ncoOut[0] is the last value of the previous
 // block (state[4]) and the mixer reads ncoOut[0..N) (project.cpp:246-248).
@@ -1308,11 +1313,6 @@ static __global__ void k_pll(const PllArgs a) {
   float *out = a.out + (size_t)b * a.out_stride + a.out_off;
   // filter.cpp:68: 2*PI*(freq/Fs) evaluated in double from the float quotient
   const double w = __dmul_rn(6.283185307179586476925286766559, (double)xdiv(a.freq, a.Fs));
-  float last = st[4];
-  // The NCO output of sample k is not fed back, so it is evaluated one iteration late,
-  // next to (and overlapped with) the feedback chain of sample k+1.
-  float pending_arg = 0.0f;
-  bool have_pending = false;
   // input samples are fetched 8 steps ahead (each lane walks its own row, so every load is a
   // separate line: its latency must not sit on the recurrence)
   float xq[8];
@@ -1327,32 +1327,31 @@ static __global__ void k_pll(const PllArgs a) {
     const float eQ = xmul(x, -fbQ);
     float eD;
     if (!atan2f_common(eQ, eI, eD)) eD = atan2f_glibc(eQ, eI);
-    {
-      const float c = cosf_glibc_bf(pending_arg);  // NCO output of sample k-1
-      if (have_pending) {
-        last = c;
-        out[k] = c;
-      }
-    }
     integrator = xadd(integrator, xmul(Ki, eD));
     phaseEst = xadd(xadd(phaseEst, xmul(Kp, eD)), integrator);
     trigOffset = xadd(trigOffset, 1.0f);
     const float trigArg =
         __double2float_rn(__dadd_rn(__dmul_rn(w, (double)trigOffset), (double)phaseEst));
     sincosf_glibc_bf(trigArg, fbQ, fbI);
-    pending_arg = xadd(xmul(trigArg, a.ncoScale), a.phaseAdjust);
-    have_pending = true;
-  }
-  if (have_pending) {
-    last = cosf_glibc_bf(pending_arg);
-    out[a.n] = last;
+    out[k + 1] = xadd(xmul(trigArg, a.ncoScale), a.phaseAdjust);  // K5b turns it into ncoOut[k+1]
   }
   st[0] = integrator;
   st[1] = phaseEst;
   st[2] = fbI;
   st[3] = fbQ;
-  st[4] = last;
   st[5] = trigOffset;
+}
+
+// K5b: ncoOut[k+1] = cosf(argument) in place, one thread per sample; the last one is also the
+// next call's ncoOut[0] (state[4], filter.cpp:79).
+static __global__ void __launch_bounds__(256) k_nco_cos(const PllArgs a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (k >= a.n) return;
+  float *slot = a.out + (size_t)b * a.out_stride + a.out_off + k + 1;
+  const float c = cosf_glibc_bf(*slot);
+  *slot = c;
+  if (k == a.n - 1) a.state[(size_t)b * 8 + 4] = c;
 }
 
 // ---------------------------------------------------------------------------
