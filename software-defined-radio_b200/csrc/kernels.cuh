@@ -1302,8 +1302,9 @@ struct PllArgs {
 };
 
 static __global__ void k_pll(const PllArgs a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.batch) return;
+  // lanes past the batch shadow the last capture (same loads, same stores of the same values):
+  // the tile copies below are warp-collective
+  const int b = min((int)(blockIdx.x * blockDim.x + threadIdx.x), a.batch - 1);
   // filter.cpp:35-39
   const float Kp = xmul(a.normBandwidth, 2.666f);
   const float Ki = xmul(xmul(a.normBandwidth, a.normBandwidth), 3.555f);
@@ -1313,27 +1314,48 @@ static __global__ void k_pll(const PllArgs a) {
   float *out = a.out + (size_t)b * a.out_stride + a.out_off;
   // filter.cpp:68: 2*PI*(freq/Fs) evaluated in double from the float quotient
   const double w = __dmul_rn(6.283185307179586476925286766559, (double)xdiv(a.freq, a.Fs));
-  // input samples are fetched 8 steps ahead (each lane walks its own row, so every load is a
-  // separate line: its latency must not sit on the recurrence)
-  float xq[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) xq[i] = (i < a.n) ? in[i] : 0.0f;
-  for (int k = 0; k < a.n; ++k) {
-    const float x = xq[0];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) xq[i] = xq[i + 1];
-    xq[7] = (k + 8 < a.n) ? in[k + 8] : 0.0f;
-    const float eI = xmul(x, fbI);
-    const float eQ = xmul(x, -fbQ);
-    float eD;
-    if (!atan2f_common(eQ, eI, eD)) eD = atan2f_glibc(eQ, eI);
-    integrator = xadd(integrator, xmul(Ki, eD));
-    phaseEst = xadd(xadd(phaseEst, xmul(Kp, eD)), integrator);
-    trigOffset = xadd(trigOffset, 1.0f);
-    const float trigArg =
-        __double2float_rn(__dadd_rn(__dmul_rn(w, (double)trigOffset), (double)phaseEst));
-    sincosf_glibc_bf(trigArg, fbQ, fbI);
-    out[k + 1] = xadd(xmul(trigArg, a.ncoScale), a.phaseAdjust);  // K5b turns it into ncoOut[k+1]
+  // Input: the warp copies tiles of 32 captures x 32 samples into shared memory with
+  // asynchronous copies (32 coalesced 128-byte rows per tile, no register in between), one
+  // tile ahead of the one being consumed, so no global-load latency meets the recurrence.
+  __shared__ float tile[2][32][33];
+  const int lane = threadIdx.x & 31;
+  const int b_first = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
+  auto fetch = [&](int buf, int k0) {
+    for (int c = 0; c < 32; ++c) {
+      const int bc = min(b_first + c, a.batch - 1);
+      const int k = min(k0 + lane, a.n - 1);
+      const float *src = a.in + (size_t)bc * a.in_stride + k;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[buf][c][lane]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(0, 0);
+  for (int k0 = 0, buf = 0; k0 < a.n; k0 += 32, buf ^= 1) {
+    if (k0 + 32 < a.n) {
+      fetch(buf ^ 1, k0 + 32);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const float *xs = tile[buf][lane];
+    const int kn = min(32, a.n - k0);
+    for (int j = 0; j < kn; ++j) {
+      const float x = xs[j];
+      const float eI = xmul(x, fbI);
+      const float eQ = xmul(x, -fbQ);
+      float eD;
+      if (!atan2f_common(eQ, eI, eD)) eD = atan2f_glibc(eQ, eI);
+      integrator = xadd(integrator, xmul(Ki, eD));
+      phaseEst = xadd(xadd(phaseEst, xmul(Kp, eD)), integrator);
+      trigOffset = xadd(trigOffset, 1.0f);
+      const float trigArg =
+          __double2float_rn(__dadd_rn(__dmul_rn(w, (double)trigOffset), (double)phaseEst));
+      sincosf_glibc_bf(trigArg, fbQ, fbI);
+      out[k0 + j + 1] = xadd(xmul(trigArg, a.ncoScale), a.phaseAdjust);  // K5b turns it into ncoOut[k+1]
+    }
+    __syncwarp();
   }
   st[0] = integrator;
   st[1] = phaseEst;
@@ -1342,16 +1364,25 @@ static __global__ void k_pll(const PllArgs a) {
   st[5] = trigOffset;
 }
 
-// K5b: ncoOut[k+1] = cosf(argument) in place, one thread per sample; the last one is also the
-// next call's ncoOut[0] (state[4], filter.cpp:79).
+// K5b: ncoOut[k+1] = cosf(argument) in place, four samples per thread; the last one is also the
+// next call's ncoOut[0] (state[4], filter.cpp:79).  Throughput-bound, so the branchy form
+// (only the reduction path and the polynomial that are needed) is the right one here.
 static __global__ void __launch_bounds__(256) k_nco_cos(const PllArgs a) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int b = blockIdx.y;
-  if (k >= a.n) return;
-  float *slot = a.out + (size_t)b * a.out_stride + a.out_off + k + 1;
-  const float c = cosf_glibc_bf(*slot);
-  *slot = c;
-  if (k == a.n - 1) a.state[(size_t)b * 8 + 4] = c;
+  if (k0 >= a.n) return;
+  float *slot = a.out + (size_t)b * a.out_stride + a.out_off + k0 + 1;
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = k0 + i < a.n ? slot[i] : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = cosf_glibc(v[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (k0 + i < a.n) {
+      slot[i] = v[i];
+      if (k0 + i == a.n - 1) a.state[(size_t)b * 8 + 4] = v[i];
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -218,7 +218,7 @@ extern "C" int sdr_pll(int device, const float *in, size_t n, float *out, float 
             freq, Fs, ncoScale, phaseAdjust, normBandwidth};
   k_pll<<<1, 32>>>(a);
   if ((rc = launch_ok("k_pll"))) return rc;
-  if (n) k_nco_cos<<<dim3(((unsigned)n + 255) / 256, 1), 256>>>(a);
+  if (n) k_nco_cos<<<dim3(((unsigned)n + 1023) / 1024, 1), 256>>>(a);
   if ((rc = launch_ok("k_nco_cos"))) return rc;
   SDR_CUDA(cudaMemcpy(out, dout.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
   SDR_CUDA(cudaMemcpy(st8, dst.p, sizeof st8, cudaMemcpyDeviceToHost));

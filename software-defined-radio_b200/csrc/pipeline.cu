@@ -886,7 +886,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
     k_pll<<<(B + 31) / 32, 32, 0, s>>>(pa);
     if ((rc = check_launch(p, "k_pll"))) return rc;
     prof_begin(p, "k_nco_cos", s);
-    k_nco_cos<<<dim3(((unsigned)n_if + 255) / 256, B), 256, 0, s>>>(pa);
+    k_nco_cos<<<dim3(((unsigned)n_if + 1023) / 1024, B), 256, 0, s>>>(pa);
     if ((rc = check_launch(p, "k_nco_cos"))) return rc;
   }
 

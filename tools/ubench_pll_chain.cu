@@ -31,8 +31,8 @@ __global__ void chain(float *out, float a, float b, int iters) {
       x = xadd(xmul(s, 100.0f), 500.0f);
       y = c;
     }
-    if (OP == 2) {  // IEEE division only
-      x = xadd(xdiv(x, y), 1.5f);
+    if (OP == 2) {  // IEEE division + one add (bounded orbit)
+      x = xadd(xdiv(1.7f, x), 0.3f);
     }
     if (OP == 3) {  // loop filter + trigArg (float -> double -> float)
       integ = xadd(integ, xmul(1e-4f, x));
@@ -71,6 +71,7 @@ __global__ void chain(float *out, float a, float b, int iters) {
 int main() {
   float *d;
   cudaMalloc(&d, 128 * sizeof(float));
+
   const char *names[] = {"atan2f", "sincosf (large arg)", "IEEE division", "loop filter + trigArg", "whole step",
                          "whole step + NCO cos"};
   for (int op = 0; op < 6; ++op) {
