@@ -152,8 +152,10 @@ struct sdr_pipeline {
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
-static sdr_pipeline::Site *g_open_site = nullptr;  // site between prof_begin and check_launch
-static cudaStream_t g_open_stream = nullptr;
+// site between prof_begin and check_launch (per host thread: distinct handles may be driven by
+// distinct threads)
+static thread_local sdr_pipeline::Site *g_open_site = nullptr;
+static thread_local cudaStream_t g_open_stream = nullptr;
 
 // Called right before a kernel launch; records the start event when profiling.
 static void prof_begin(sdr_pipeline *p, const char *name, cudaStream_t s) {

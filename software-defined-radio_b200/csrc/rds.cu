@@ -30,6 +30,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -356,7 +357,7 @@ struct RdsResampleArgs {
 constexpr int RDS_RS_J = 16;      // outputs per block (4 quads, one per warp)
 constexpr int RDS_RS_PITCH = 33;  // doubles per tile row
 
-static __global__ void __launch_bounds__(128) k_rds_resample(const RdsResampleArgs a, int batch, int rows_cap,
+static __global__ void __launch_bounds__(256) k_rds_resample(const RdsResampleArgs a, int batch, int rows_cap,
                                                              int n_in, int quad_rows) {
   extern __shared__ __align__(16) double rs_sm[];
   double *tI = rs_sm;
@@ -369,7 +370,7 @@ static __global__ void __launch_bounds__(128) k_rds_resample(const RdsResampleAr
   const int j0 = blockIdx.x * RDS_RS_J;
   // this block's four table entries, fetched alongside the tile (read in place they cost one
   // L2 round trip per 128-byte line inside the tap loop: 3.5 ms instead of 2.3 ms)
-  for (int i = threadIdx.x; i < 4 * quad_rows * 2; i += 128) {
+  for (int i = threadIdx.x; i < 4 * quad_rows * 2; i += 256) {
     const int w = i / (quad_rows * 2), e = i % (quad_rows * 2);
     const int p0w = (int)(((long long)(j0 + 4 * w) * a.D) % a.U);
     const double2 *src = reinterpret_cast<const double2 *>(a.quad) + (size_t)p0w * quad_rows * 2 + e;
@@ -380,7 +381,7 @@ static __global__ void __launch_bounds__(128) k_rds_resample(const RdsResampleAr
   const long long baseL = ((long long)(j0 + RDS_RS_J - 1) * a.D) / a.U;       // ... of the last one (may lie past the data)
   const long long lo = base0 - (RDS_TP - 1);                                  // oldest input needed
   const int rows = (int)(baseL - lo + 1);
-  for (int c = warp; c < 32; c += 4) {
+  for (int c = warp; c < 32; c += 8) {
     const int bc = min(b0 + c, batch - 1);
     const double *sI = a.mixI + (size_t)bc * a.mix_stride + a.mix_off + lo;
     const double *sQ = a.mixQ + (size_t)bc * a.mix_stride + a.mix_off + lo;
@@ -398,39 +399,37 @@ static __global__ void __launch_bounds__(128) k_rds_resample(const RdsResampleAr
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int jq = j0 + 4 * warp;  // first output of this warp's quad
+  // warps 0-3 take the I component of quads 0-3, warps 4-7 the Q component: twice the warps per
+  // tile to hide the shared-memory latency of the tap loop
+  const int quad = warp & 3;
+  const bool is_q = warp >= 4;
+  const int jq = j0 + 4 * quad;  // first output of this warp's quad
   if (jq < a.n_out) {
     const long long m = (long long)jq * a.D;
     const int p0 = (int)(m % a.U);
     const int span = (p0 + 3 * a.D) / a.U;                 // newest input of output 3 - that of output 0
     const int top = (int)(m / a.U + span - lo);            // tile row of the newest input of output 3
     const int n_rows = RDS_TP + span;
-    const double2 *tq = tabs + (size_t)warp * quad_rows * 2;
-    const double *xi = tI + (size_t)top * RDS_RS_PITCH + lane;
-    const double *xq = tQ + (size_t)top * RDS_RS_PITCH + lane;
-    double aI[4] = {0.0, 0.0, 0.0, 0.0}, aQ[4] = {0.0, 0.0, 0.0, 0.0};
+    const double2 *tq = tabs + (size_t)quad * quad_rows * 2;
+    const double *x = (is_q ? tQ : tI) + (size_t)top * RDS_RS_PITCH + lane;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 8
     for (int r = 0; r < n_rows; ++r) {
       const double2 h01 = tq[2 * r], h23 = tq[2 * r + 1];
-      const double vi = xi[-r * RDS_RS_PITCH], vq = xq[-r * RDS_RS_PITCH];
-      aI[0] = fma(h01.x, vi, aI[0]);
-      aI[1] = fma(h01.y, vi, aI[1]);
-      aI[2] = fma(h23.x, vi, aI[2]);
-      aI[3] = fma(h23.y, vi, aI[3]);
-      aQ[0] = fma(h01.x, vq, aQ[0]);
-      aQ[1] = fma(h01.y, vq, aQ[1]);
-      aQ[2] = fma(h23.x, vq, aQ[2]);
-      aQ[3] = fma(h23.y, vq, aQ[3]);
+      const double v = x[-r * RDS_RS_PITCH];
+      acc[0] = fma(h01.x, v, acc[0]);
+      acc[1] = fma(h01.y, v, acc[1]);
+      acc[2] = fma(h23.x, v, acc[2]);
+      acc[3] = fma(h23.y, v, acc[3]);
     }
+    double *o = is_q ? oQ : oI;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      oI[lane * (RDS_RS_J + 1) + 4 * warp + i] = __dmul_rn(aI[i], (double)a.U);  // fmSupportLib.py:400
-      oQ[lane * (RDS_RS_J + 1) + 4 * warp + i] = __dmul_rn(aQ[i], (double)a.U);
-    }
+    for (int i = 0; i < 4; ++i)
+      o[lane * (RDS_RS_J + 1) + 4 * quad + i] = __dmul_rn(acc[i], (double)a.U);  // fmSupportLib.py:400
   }
   __syncthreads();
   const int jn = min(RDS_RS_J, a.n_out - j0);
-  for (int i = threadIdx.x; i < 32 * RDS_RS_J; i += 128) {
+  for (int i = threadIdx.x; i < 32 * RDS_RS_J; i += 256) {
     const int c = i / RDS_RS_J, jj = i % RDS_RS_J;
     if (b0 + c < batch && jj < jn) {
       a.rsI[(size_t)(b0 + c) * a.rs_stride + a.rs_off + j0 + jj] = oI[c * (RDS_RS_J + 1) + jj];
@@ -839,7 +838,7 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     dim3 grid((n_out + RDS_RS_J - 1) / RDS_RS_J, (B + 31) / 32);
     sdr_prof_begin(p, "k_rds_resample", s);
     cudaFuncSetAttribute(k_rds_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_rds_resample<<<grid, 128, smem, s>>>(a, B, rows_cap, n, r->quad_rows);
+    k_rds_resample<<<grid, 256, smem, s>>>(a, B, rows_cap, n, r->quad_rows);
     if ((rc = sdr_check_launch(p, "k_rds_resample"))) return rc;
   }
   {  // R5
