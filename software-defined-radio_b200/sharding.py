@@ -37,3 +37,21 @@ def gather_pcm(local_pcm: np.ndarray, n_captures: int, dist=None, dst: int = 0):
     if rank != dst:
         return None
     return np.concatenate([out[r].view(torch.int16)[: e - b].numpy() for r, (b, e) in enumerate(sizes)], axis=0)
+
+
+def gather_rds(local_reads: list, n_captures: int, dist=None, dst: int = 0):
+    """Final host gather of the RDS bit layer: `local_reads` is this rank's list of per-capture
+    results (what ``Rds.read(c)`` returns: a dict of small arrays and the offsets string), in
+    shard order.  Rank `dst` receives the list for all captures in capture order, other ranks
+    None.  The payload is a few hundred bits per capture and block, so it travels as objects."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_reads
+    world, rank = dist.get_world_size(), dist.get_rank()
+    out = [None] * world if rank == dst else None
+    dist.gather_object(local_reads, out, dst=dst)
+    if rank != dst:
+        return None
+    merged = [r for part in out for r in part]
+    if len(merged) != n_captures:
+        raise ValueError("shards do not add up to the batch")
+    return merged

@@ -62,3 +62,46 @@ def test_two_ranks_gather_equals_single_process(tmp_path):
     want = np.stack([orc.run_chain(siggen.make_capture(c, 0, 1, "stereo"), 0, 2, 13, 13, 13, keep_taps=False)[0]
                      for c in range(n)])
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def _rds_reads(orc, captures):
+    """What sdr_b200.Rds.read(c) returns, produced by the CPU oracles (the test's stand-in for
+    the per-rank GPU chain)."""
+    R = orclib.RDS()
+    out = []
+    for c in captures:
+        iq = siggen.make_capture(c, 0, 15, "rds")
+        _, taps = orc.run_chain(iq, 0, 1, 13, 13, 13)
+        r = R.run_chain(taps["demod"].astype(np.float64), 0, 9600, keep=())
+        out.append(dict(cdr_bits=np.concatenate(r["cdr_bits"]), diff_bits=np.concatenate(r["diff_bits"]),
+                        bit_counts=np.array([b.size for b in r["cdr_bits"]], np.int32), offsets=r["offsets"]))
+    return out
+
+
+def _rds_worker(rank, world, port, n_captures, result_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b, e = sharding.shard_range(n_captures, world, rank)
+        full = sharding.gather_rds(_rds_reads(orclib.ORC(), range(b, e)), n_captures, dist)
+        if rank == 0:
+            np.save(result_path, np.array(full, dtype=object), allow_pickle=True)
+        else:
+            assert full is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_gather_rds_bits(tmp_path):
+    n = 3  # shards of 2 and 1
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "rds.npy")
+    mp.spawn(_rds_worker, args=(2, port, n, out), nprocs=2, join=True)
+    got = list(np.load(out, allow_pickle=True))
+    want = _rds_reads(orclib.ORC(), range(n))
+    assert len(got) == n
+    for g, w in zip(got, want):
+        assert g["offsets"] == w["offsets"]
+        for k in ("cdr_bits", "diff_bits", "bit_counts"):
+            assert np.array_equal(g[k], w[k]), k
