@@ -229,8 +229,11 @@ __device__ __forceinline__ float cosf_glibc(float y) {
 // ---------------------------------------------------------------------------
 
 // atan2f for the common case: x, y finite and non-zero, x != 1.0f, exponents within 2^60
-// of each other, |y/x| < 2^25.  Returns false (and leaves `out` alone) otherwise; the
-// caller then falls back to atan2f_glibc.
+// of each other, |y/x| < 2^25.  Returns false otherwise (`out` is then meaningless); the
+// caller then falls back to atan2f_glibc.  The validity test is evaluated LAST: the common path
+// runs on whatever arrives (a zero, infinity or NaN only produces a value that is discarded), so
+// the branch on it -- which needs the first quotient -- does not sit in the middle of the PLL's
+// dependency chain (305 -> 280 cycles, tools/ubench_pll_chain.cu).
 __device__ __forceinline__ bool atan2f_common(float y, float x, float &out) {
   const float pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
   const int32_t hx = __float_as_int(x), hy = __float_as_int(y);
@@ -240,7 +243,6 @@ __device__ __forceinline__ bool atan2f_common(float y, float x, float &out) {
   const int32_t it = __float_as_int(t);
   const bool common = (iy != 0) & (ix != 0) & (ix < 0x7f800000) & (iy < 0x7f800000) &
                       (hx != 0x3f800000) & (k <= 60) & (k >= -60) & (it < 0x4c000000);
-  if (!common) return false;
   // atanf(t), t >= 0: argument reduction x = num/den with per-range constants
   //   range        num                den               hi/lo
   //   t < 7/16     t                  1                 0
@@ -276,7 +278,7 @@ __device__ __forceinline__ bool atan2f_common(float y, float x, float &out) {
   const float pos = xneg ? xsub(pi, zl) : zz;
   const float neg = xneg ? xsub(zl, pi) : __int_as_float(__float_as_int(zz) ^ (int32_t)0x80000000);
   out = yneg ? neg : pos;
-  return true;
+  return common;
 }
 
 // Branch-free argument reduction: all three glibc paths are evaluated and the one

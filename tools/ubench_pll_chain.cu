@@ -72,6 +72,7 @@ int main() {
   float *d;
   cudaMalloc(&d, 128 * sizeof(float));
 
+
   const char *names[] = {"atan2f", "sincosf (large arg)", "IEEE division", "loop filter + trigArg", "whole step",
                          "whole step + NCO cos"};
   for (int op = 0; op < 6; ++op) {
