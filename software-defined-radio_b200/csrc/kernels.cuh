@@ -1341,8 +1341,10 @@ static __global__ void k_pll(const PllArgs a) {
     __syncwarp();
     const float *xs = tile[buf][lane];
     const int kn = min(32, a.n - k0);
+    float x_next = xs[0];
     for (int j = 0; j < kn; ++j) {
-      const float x = xs[j];
+      const float x = x_next;
+      x_next = xs[min(j + 1, 31)];  // a step ahead: the shared-memory latency stays off the chain
       const float eI = xmul(x, fbI);
       const float eQ = xmul(x, -fbQ);
       float eD;
