@@ -1204,6 +1204,11 @@ extern "C" int sdr_pipeline_process_host(sdr_pipeline *p, const uint8_t *iq, siz
   SDR_CUDA(cudaSetDevice(p->cfg.device));
   const size_t B = (size_t)p->cfg.batch;
   const size_t gran = (size_t)p->granule_bytes;
+  // the follower stage refuses the whole call before its first slice is enqueued
+  if (p->hook) {
+    const int hrc = p->hook(p->hook_ctx, 4, nbytes / 2 / (size_t)p->m.rf_decim, nullptr);
+    if (hrc) return hrc;
+  }
   // slice: <= capacity, and about 64 MiB over the whole batch
   size_t cap_bytes = p->cap_if * p->m.rf_decim * 2;
   size_t slice = std::max<size_t>(gran, ((64ull << 20) / B) / gran * gran);

@@ -21,7 +21,9 @@ struct DemodView {
 
 // event 0: a process call produced n_if fm_demod samples per capture (kernels go on stream s);
 // event 1: sdr_pipeline_reset;
-// event 2: a process call of n_if samples is about to be enqueued (validate only).
+// event 2: a process call of n_if samples is about to be enqueued (validate only);
+// event 4: a host call of n_if samples in total is about to be cut into process calls (validate
+//          what concerns the whole: room for its results).
 typedef int (*PipelineHook)(void *ctx, int event, size_t n_if, cudaStream_t s);
 
 int pipeline_view(sdr_pipeline *p, DemodView *v);

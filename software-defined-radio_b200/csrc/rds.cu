@@ -912,6 +912,13 @@ static int rds_hook(void *ctx, int event, size_t n_if, cudaStream_t s) {
   sdr_rds *r = static_cast<sdr_rds *>(ctx);
   if (event == 1) return rds_reset_device(r);
   if (event == 2) return rds_validate(r, n_if);
+  if (event == 4) {
+    if (n_if % (size_t)r->block_if) return fail(SDR_ERR_INVALID, "RDS: the call is not a whole number of RDS blocks");
+    if (r->cursor + (long long)(n_if / (size_t)r->block_if) > r->blocks_cap)
+      return fail(SDR_ERR_CAPACITY, "RDS: result buffer too small for this call; raise max_pending_blocks or "
+                                    "call sdr_rds_read, then sdr_rds_discard");
+    return SDR_OK;
+  }
   return rds_process(r, n_if, s);
 }
 

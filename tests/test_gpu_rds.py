@@ -179,6 +179,17 @@ def test_rds_reset_and_errors(sdr):
             b = r.read(0)
             assert np.array_equal(first, r.tap("rrc_i", 0))
             assert np.array_equal(a["cdr_bits"], b["cdr_bits"]) and a["offsets"] == b["offsets"]
+            # a host call whose blocks would not fit is refused as a whole (nothing is processed)
+            r.discard()
+            p.reset()
+            long_iq = np.concatenate([iq, iq], axis=1)
+            with sdr.Pipeline(mode=mode, batch=1, max_bytes_per_channel=192000) as p2:
+                with sdr.Rds(p2, block_if=block_if, max_pending_blocks=4) as r2:
+                    with pytest.raises(sdr.SdrError):
+                        p2.process_host(long_iq)      # 8 blocks, room for 4, sliced into 1-block calls
+                    assert r2.pending() == 0
+                    p2.process_host(iq)               # state untouched: same result as a fresh run
+                    assert np.array_equal(r2.read(0)["cdr_bits"], a["cdr_bits"])
             # not a whole number of RDS blocks
             with pytest.raises(sdr.SdrError):
                 p.process_host(iq[:, :100000])
