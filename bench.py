@@ -369,6 +369,26 @@ def time_e2e(torch, sdr, args, steps, dist, world):
             "api": "sdr_pipeline_process_host (pinned host buffers, 3 streams, double-buffered slices)"}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPUs next to its GPU (NVML's affinity mask) before any pinned host
+    memory is allocated, so that the end-to-end leg's H2D copies read local memory: with one
+    rank per GPU the ranks otherwise share whichever NUMA node they happened to start on."""
+    before = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass  # no NVML / no permission: keep the inherited affinity
+    return before  # the caller restores it before the CPU-baseline leg forks its workers
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -380,6 +400,7 @@ def run_ours(args):
     if not torch.cuda.is_available() or sdr.device_count() < 1:
         raise SystemExit("bench.py needs a B200 (sm_100) GPU: the product has no CPU fallback")
     torch.cuda.set_device(local)
+    affinity_before = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -396,6 +417,7 @@ def run_ours(args):
 
     e2e = None if (args.rds or args.mixed or args.streams > 1) else \
         time_e2e(torch, sdr, args, max(2, min(args.steps, 5)), dist, world)
+    os.sched_setaffinity(0, affinity_before)
 
     others = {}
     if args.others and world == 1:
