@@ -199,3 +199,23 @@ def test_rds_reset_and_errors(sdr):
     with sdr.Pipeline(mode=1, batch=1, max_bytes_per_channel=1 << 20) as p:
         with pytest.raises(sdr.SdrError):
             sdr.Rds(p)
+
+
+def test_rds_wide_batch(sdr, orc):
+    """70 captures: two full warps of captures plus a partial one in every lanes=captures kernel
+    (PLL, resampler), several grid rows in the others; every capture is a different signal."""
+    R = orclib.RDS()
+    mode, block_if, n_blocks = 0, 9600, 8
+    nbytes = n_blocks * block_if * 20
+    iq = np.ascontiguousarray(siggen.make_batch(70, mode, 15, "rds", distinct=5)[:, :nbytes])
+    with sdr.Pipeline(mode=mode, channels=1, batch=70, max_bytes_per_channel=nbytes) as p:
+        with sdr.Rds(p, block_if=block_if, keep_nco=True) as r:
+            p.process_host(iq[:, :nbytes // 2])
+            first = {c: {k: r.tap(k, c) for k in STAGES} for c in (0, 31, 32, 63, 64, 69)}
+            p.process_host(iq[:, nbytes // 2:])
+            second = {c: {k: r.tap(k, c) for k in STAGES} for c in first}
+            reads = {c: r.read(c) for c in first}
+    for c in first:
+        want = oracle_chain(R, orc, iq[c], mode, block_if)
+        parts = {(k, c): [first[c][k], second[c][k]] for k in STAGES}
+        compare(parts, {c: reads[c]}, want, c, n_blocks, block_if)
