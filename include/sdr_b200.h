@@ -207,6 +207,9 @@ typedef struct {
                              (fmRDS.py:149-152: 9600 in mode 0, 1536000 in mode 2); a multiple of 9600 */
   int max_pending_blocks; /* blocks whose bits may wait for sdr_rds_read; 0 = default */
   int keep_nco;           /* keep the PLL's NCO outputs for sdr_rds_tap (SDR_RDS_TAP_PLL_*) */
+  int cdr_carry;          /* 0: the CDR state is re-created for every block, as fmRDS.py:257-260 does;
+                             1: it is carried from block to block (pair, start, prev_size:
+                             fmSupportLib.py:104-106,178-189), so symbols are not dropped at block edges */
 } sdr_rds_config;
 
 typedef struct {

@@ -184,15 +184,19 @@ static int symbol_to_bit(const double *pair) {
   return 0;
 }
 
-/* fmSupportLib.py:103-201, driven as at fmRDS.py:257-268 */
-int rdo_cdr(const double *x, int n, int sps, int block_count, uint8_t *bits, int cap) {
-  double pair[2] = {0.0, 0.0};
-  const int start_init = 158; /* fmRDS.py:259 */
-  const int prev_size = 0;    /* fmRDS.py:258 */
+/* fmSupportLib.py:103-201 with an explicit to_pass_on_state = {pair[0], pair[1], start,
+ * prev_size} (:104-106), updated on return as at :178-189.  fmRDS.py:257-260 re-creates the
+ * state {0, 0, 158, 0} for every block (rdo_cdr below); carried from block to block it is
+ * what the function was written for: an odd number of sampling points leaves one symbol that
+ * is paired with the first point of the next block (:117-125). */
+int rdo_cdr_state(const double *x, int n, int sps, int block_count, double *state, uint8_t *bits, int cap) {
+  double pair[2] = {state[0], state[1]};
+  const int start_init = (int)state[2];
+  const int prev_size = (int)state[3];
   int start = start_init;
   const double limit = 0.3;
-  int n_prefix = 0; /* bits appended by restarts (:160-166) */
-  const int max_samples = n / sps + 2;
+  int n_prefix = 0; /* bits appended by the pairing branch (:117-125) and by restarts (:160-166) */
+  const int max_samples = n / sps + 3;
   double *spa = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
   double *samples = (double *)calloc((size_t)max_samples, sizeof(double));
   int size = 0;
@@ -202,7 +206,7 @@ int rdo_cdr(const double *x, int n, int sps, int block_count, uint8_t *bits, int
     size = 0;
     const int loop_start = start;
     for (int i = loop_start; i < n; i += sps) {
-      /* :117-125 -- dead with prev_size == 0, kept for fidelity */
+      /* :117-125 the last symbol of the previous block meets the first of this one */
       if (i == start && start == start_init && (prev_size % 2 == 1)) {
         pair[1] = x[i];
         if (n_prefix < cap) bits[n_prefix] = (uint8_t)symbol_to_bit(pair);
@@ -252,6 +256,16 @@ int rdo_cdr(const double *x, int n, int sps, int block_count, uint8_t *bits, int
     (void)any_good;
     unpaired = restarted;
   }
+  /* :178-189 state for the next block (with no sampling point left the reference would fail
+   * on samples[-1]; the symbol in hand is kept) */
+  if (size > 0) pair[0] = samples[size - 1];
+  state[0] = pair[0];
+  state[1] = pair[1];
+  {
+    const int last_index = ((size - 1) * sps) + start;
+    state[2] = (double)(sps - (n - last_index));
+  }
+  state[3] = (double)size;
   /* :192 manchestering (fmSupportLib.py:203-222) */
   int nb = n_prefix;
   for (int i = 0; i < size; i += 2) {
@@ -266,6 +280,12 @@ int rdo_cdr(const double *x, int n, int sps, int block_count, uint8_t *bits, int
   free(spa);
   free(samples);
   return nb;
+}
+
+/* fmSupportLib.py:103-201 driven as at fmRDS.py:257-268: fresh state for every block */
+int rdo_cdr(const double *x, int n, int sps, int block_count, uint8_t *bits, int cap) {
+  double state[4] = {0.0, 0.0, 158.0, 0.0}; /* fmRDS.py:257-260 */
+  return rdo_cdr_state(x, n, sps, block_count, state, bits, cap);
 }
 
 /* fmSupportLib.py:241-249 */
@@ -348,6 +368,8 @@ struct rdo_chain {
   int n_decoded, cap_decoded;
   char offset;
   int block_count;
+  int cdr_carry;       /* keep the CDR state from block to block instead of fmRDS.py:257-260 */
+  double cdr_state[4];
 };
 
 static double *dz(size_t n) { return (double *)calloc(n ? n : 1, sizeof(double)); }
@@ -390,6 +412,7 @@ rdo_chain *rdo_chain_create(int mode, int block_if) {
   c->diff_bits = (uint8_t *)calloc((size_t)cap, 1);
   c->cap_decoded = 0;
   c->decoded = NULL;
+  c->cdr_state[2] = 158.0; /* fmRDS.py:259 */
   return c;
 }
 
@@ -419,7 +442,10 @@ void rdo_chain_block(rdo_chain *c, const double *fm_demod) {
   rdo_resample(c->mixQ, n, c->h_rs, c->nh_rs, c->hist_rsQ, c->D, c->U, c->rsQ); /* :252 */
   rdo_fir(c->rsQ, (size_t)c->n_out, c->h_rrc, 101, c->hist_rrcQ, c->rrcQ);      /* :254 */
   const int cap = c->n_out / c->sps + 4;
-  c->n_bits = rdo_cdr(c->rrcI, c->n_out, c->sps, c->block_count, c->cdr_bits, cap); /* :268 */
+  if (c->cdr_carry)
+    c->n_bits = rdo_cdr_state(c->rrcI, c->n_out, c->sps, c->block_count, c->cdr_state, c->cdr_bits, cap);
+  else
+    c->n_bits = rdo_cdr(c->rrcI, c->n_out, c->sps, c->block_count, c->cdr_bits, cap); /* :268 */
   rdo_diff_decode(c->cdr_bits, c->n_bits, c->diff_bits);                             /* :271 */
   if (c->n_decoded + c->n_bits > c->cap_decoded) {
     c->cap_decoded = 2 * (c->n_decoded + c->n_bits) + 64;
@@ -434,6 +460,8 @@ void rdo_chain_block(rdo_chain *c, const double *fm_demod) {
   c->n_decoded -= used;
   c->block_count++;
 }
+
+void rdo_chain_set_cdr_carry(rdo_chain *c, int carry) { c->cdr_carry = carry; }
 
 const double *rdo_chain_tap(const rdo_chain *c, int stage, size_t *n) {
   const size_t ni = (size_t)c->n, no = (size_t)c->n_out;

@@ -57,6 +57,9 @@ void rdo_resample(const double *x, size_t n, const double *h, int nh, double *hi
  * written to bits (capacity cap).  Where the reference would loop forever (no pair with
  * opposite signs in a whole pass) the pass is accepted as it stands. */
 int rdo_cdr(const double *x, int n, int sps, int block_count, uint8_t *bits, int cap);
+/* The same function with its to_pass_on_state explicit and carried: state = {pair[0], pair[1],
+ * start, prev_size} (fmSupportLib.py:104-106), updated as at :178-189. */
+int rdo_cdr_state(const double *x, int n, int sps, int block_count, double *state, uint8_t *bits, int cap);
 /* fmSupportLib.py:241-249 */
 void rdo_diff_decode(const uint8_t *in, int n, uint8_t *out);
 /* fmSupportLib.py:14-27 with the parity matrix of :32-57; d has 26 bits, s gets 10. */
@@ -71,6 +74,9 @@ typedef struct rdo_chain rdo_chain;
  * by 2*rf_decim): 9600 in mode 0, 1536000 in mode 2; any multiple of 960 / 1920 works. */
 rdo_chain *rdo_chain_create(int mode, int block_if);
 void rdo_chain_destroy(rdo_chain *c);
+/* Keep the CDR state from block to block (what fmSupportLib.py's CDR was written for) instead of
+ * re-creating it per block as fmRDS.py:257-260 does.  Off by default. */
+void rdo_chain_set_cdr_carry(rdo_chain *c, int carry);
 /* One block of fm_demod in; every intermediate is kept until the next call. */
 void rdo_chain_block(rdo_chain *c, const double *fm_demod);
 /* stage: 0 channel_filt, 1 carrier_filt, 2 PLL I (n+1), 3 PLL Q (n+1), 4 mixer I, 5 mixer Q,

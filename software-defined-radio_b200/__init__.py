@@ -44,7 +44,8 @@ class ModeInfo(C.Structure):
 
 
 class RdsConfig(C.Structure):
-    _fields_ = [("block_if", C.c_int), ("max_pending_blocks", C.c_int), ("keep_nco", C.c_int)]
+    _fields_ = [("block_if", C.c_int), ("max_pending_blocks", C.c_int), ("keep_nco", C.c_int),
+                ("cdr_carry", C.c_int)]
 
 
 class RdsInfo(C.Structure):
@@ -340,10 +341,11 @@ class Rds:
     """RDS receiver attached to a :class:`Pipeline` (modes 0 and 2): it runs at the end of every
     process call of that pipeline, on the same stream."""
 
-    def __init__(self, pipeline: Pipeline, block_if=0, max_pending_blocks=0, keep_nco=False):
+    def __init__(self, pipeline: Pipeline, block_if=0, max_pending_blocks=0, keep_nco=False,
+                 cdr_carry=False):
         self.pipeline = pipeline
         self._h = _vp()
-        cfg = RdsConfig(block_if, max_pending_blocks, 1 if keep_nco else 0)
+        cfg = RdsConfig(block_if, max_pending_blocks, 1 if keep_nco else 0, 1 if cdr_carry else 0)
         _check(lib().sdr_rds_create(pipeline._h, C.byref(cfg), C.byref(self._h)))
         self.info = RdsInfo()
         _check(lib().sdr_rds_info(self._h, C.byref(self.info)))

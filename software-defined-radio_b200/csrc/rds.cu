@@ -469,6 +469,73 @@ struct RdsCdrArgs {
 constexpr int RDS_CDR_WARPS = 4;
 constexpr int RDS_CDR_PTS = 512;  // sampling points per block kept in shared memory (else read in place)
 
+// The walk over one block's grid of sampling points pts[i * step], i < n_pts (lane 0 only).
+// pair0 is the model's pair[0]; on return `size` is the number of points of the accepted pass,
+// `first_pt` the index of its first point and `last` the model's samples[-1] (after repairs).
+struct RdsCdrWalk {
+  int nb, size, first_pt;
+  double pair0, last;
+};
+
+static __device__ RdsCdrWalk rds_cdr_walk(const double *pts, int step, int n_pts, bool first_ever, double pair0,
+                                          int n_prefix, uint8_t *out, int bits_cap) {
+  const double limit = 0.3;
+  int first_pt = 0;  // restarts so far: the pass starts `first_pt` symbols later
+  int nb = 0;
+  double last = 0.0;
+  for (;;) {
+    double p1 = 0.0, p2 = 0.0;  // the two previous sampling points (before pair repairs)
+    double first = 0.0, s0 = 0.0;
+    bool restart = false;
+    nb = n_prefix;
+    for (int k = 0; first_pt + k < n_pts; ++k) {
+      const double xi = pts[(size_t)(first_pt + k) * step];
+      double s = xi;
+      // :128-136 a third consecutive high (or low) is inverted
+      if (k >= 2 && ((p2 > 0 && p1 > 0 && xi > 0) || (p2 < 0 && p1 < 0 && xi < 0))) s = -xi;
+      p2 = p1;
+      p1 = s;
+      if ((k & 1) == 0) {
+        first = s;
+        last = s;
+        if (k == 0) s0 = s;
+        continue;
+      }
+      double u = first, v = s;
+      if ((u < 0 && v < 0) || (u > 0 && v > 0)) {  // :147
+        if (fabs(u) < limit) u = -u;                // :151-153
+        else if (fabs(v) < limit) v = -v;           // :154-156
+        else {                                      // :158-172
+          restart = true;
+          break;
+        }
+      }
+      if (k == 1) s0 = u;  // samples[0] as the model sees it at a later restart
+      last = v;
+      // manchestering, :203-222
+      uint8_t bit = 0;
+      if (u > 0 && v < 0) bit = 1;
+      if (nb < bits_cap) out[nb] = bit;
+      ++nb;
+    }
+    if (!restart) break;
+    first_pt += 1;
+    if (!first_ever) {  // :160-167: symbolToBit looks at pair[0] only (:228-236)
+      const uint8_t bit = pair0 > 0 ? 1 : 0;
+      if (n_prefix < bits_cap) out[n_prefix] = bit;
+      ++n_prefix;
+      pair0 = s0;
+    }
+  }
+  RdsCdrWalk w;
+  w.nb = nb;
+  w.size = max(n_pts - first_pt, 0);
+  w.first_pt = first_pt;
+  w.pair0 = pair0;
+  w.last = last;
+  return w;
+}
+
 static __global__ void __launch_bounds__(32 * RDS_CDR_WARPS) k_rds_cdr(const RdsCdrArgs a) {
   __shared__ double pts_sm[RDS_CDR_WARPS][RDS_CDR_PTS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -488,55 +555,63 @@ static __global__ void __launch_bounds__(32 * RDS_CDR_WARPS) k_rds_cdr(const Rds
   }
   if (lane != 0) return;
   uint8_t *out = a.bits + ((size_t)b * a.blocks_cap + a.cursor + blk) * a.bits_cap;
-  const bool first_ever = (a.first_block + blk) == 0;
-  const double limit = 0.3;
-  int first_pt = 0;  // start = 158 + first_pt * sps
-  int n_prefix = 0;
-  double pair0 = 0.0;
-  int nb = 0;
-  for (;;) {
-    double p1 = 0.0, p2 = 0.0;  // the two previous sampling points (before pair repairs)
-    double first = 0.0, s0 = 0.0;
-    bool restart = false;
-    nb = n_prefix;
-    for (int k = 0; first_pt + k < n_pts; ++k) {
-      const double xi = pts[(size_t)(first_pt + k) * step];
-      double s = xi;
-      // :128-136 a third consecutive high (or low) is inverted
-      if (k >= 2 && ((p2 > 0 && p1 > 0 && xi > 0) || (p2 < 0 && p1 < 0 && xi < 0))) s = -xi;
-      p2 = p1;
-      p1 = s;
-      if ((k & 1) == 0) {
-        first = s;
-        if (k == 0) s0 = s;
-        continue;
-      }
-      double u = first, v = s;
-      if ((u < 0 && v < 0) || (u > 0 && v > 0)) {  // :147
-        if (fabs(u) < limit) u = -u;                // :151-153
-        else if (fabs(v) < limit) v = -v;           // :154-156
-        else {                                      // :158-172
-          restart = true;
-          break;
-        }
-      }
-      if (k == 1) s0 = u;  // samples[0] as the model sees it at a later restart
-      // manchestering, :203-222
-      uint8_t bit = 0;
-      if (u > 0 && v < 0) bit = 1;
-      if (nb < a.bits_cap) out[nb] = bit;
-      ++nb;
+  const RdsCdrWalk w = rds_cdr_walk(pts, step, n_pts, (a.first_block + blk) == 0, 0.0, 0, out, a.bits_cap);
+  a.counts[(size_t)b * a.blocks_cap + a.cursor + blk] = min(w.nb, a.bits_cap);
+}
+
+// The same with the model's to_pass_on_state {pair[0], start, prev_size} carried from block to
+// block (fmSupportLib.py:104-106,178-189) instead of re-created per block: one warp per capture
+// walks its blocks in order.  An odd number of points in the previous block leaves one symbol
+// that is paired with the first point of this block (:117-125).  cdr_state: [B][4] doubles =
+// pair[0], start, prev_size, unused.
+static __global__ void __launch_bounds__(32 * RDS_CDR_WARPS) k_rds_cdr_carry(const RdsCdrArgs a, double *cdr_state) {
+  __shared__ double pts_sm[RDS_CDR_WARPS][RDS_CDR_PTS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * RDS_CDR_WARPS + warp;
+  if (b >= a.batch) return;
+  double *st = cdr_state + (size_t)b * 4;
+  double pair0 = st[0];
+  int start = (int)st[1], prev_size = (int)st[2];
+  const int sps = a.sps, n = a.block_out;
+  for (int blk = 0; blk < a.n_blocks; ++blk) {
+    const double *x = a.rrc + (size_t)b * a.rrc_stride + (size_t)blk * n;
+    uint8_t *out = a.bits + ((size_t)b * a.blocks_cap + a.cursor + blk) * a.bits_cap;
+    int n_prefix = 0;
+    if ((prev_size & 1) && start < n) {  // :117-125
+      if (lane == 0 && a.bits_cap > 0) out[0] = pair0 > 0 ? 1 : 0;
+      n_prefix = 1;
+      pair0 = x[start];
+      start += sps;
     }
-    if (!restart) break;
-    first_pt += 1;
-    if (!first_ever) {  // :160-167: symbolToBit looks at pair[0] only (:228-236)
-      const uint8_t bit = pair0 > 0 ? 1 : 0;
-      if (n_prefix < a.bits_cap) out[n_prefix] = bit;
-      ++n_prefix;
-      pair0 = s0;
+    const int n_pts = start < n ? (n - start + sps - 1) / sps : 0;
+    const double *pts = x + start;
+    int step = sps;
+    __syncwarp();
+    if (n_pts <= RDS_CDR_PTS) {
+      for (int i = lane; i < n_pts; i += 32) pts_sm[warp][i] = pts[(size_t)i * sps];
+      __syncwarp();
+      pts = pts_sm[warp];
+      step = 1;
     }
+    RdsCdrWalk w{};
+    if (lane == 0) {
+      w = rds_cdr_walk(pts, step, n_pts, (a.first_block + blk) == 0, pair0, n_prefix, out, a.bits_cap);
+      a.counts[(size_t)b * a.blocks_cap + a.cursor + blk] = min(w.nb, a.bits_cap);
+    }
+    // :178-189 state for the next block, computed by lane 0 and shared with the warp
+    const int size = __shfl_sync(0xffffffffu, w.size, 0);
+    const int first_pt = __shfl_sync(0xffffffffu, w.first_pt, 0);
+    const double p0 = __shfl_sync(0xffffffffu, w.pair0, 0), last = __shfl_sync(0xffffffffu, w.last, 0);
+    pair0 = size > 0 ? last : p0;
+    const int last_index = (size - 1) * sps + (start + first_pt * sps);
+    start = sps - (n - last_index);
+    prev_size = size;
   }
-  a.counts[(size_t)b * a.blocks_cap + a.cursor + blk] = min(nb, a.bits_cap);
+  if (lane == 0) {
+    st[0] = pair0;
+    st[1] = (double)start;
+    st[2] = (double)prev_size;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -672,11 +747,12 @@ struct sdr_rds {
   size_t chan_stride = 0, carr_stride = 0, theta_stride = 0, mix_stride = 0, rs_stride = 0, rrc_stride = 0, nco_stride = 0;
   DTaps<RDS_T> h_chan{}, h_carr{};
   DTaps<RDS_TP> h_rrc{};
-  RBuf<double> quad, chan, carr, theta, mixI, mixQ, rsI, rsQ, rrcI, rrcQ, ncoI, ncoQ, pll;
+  RBuf<double> cdr_state, quad, chan, carr, theta, mixI, mixQ, rsI, rsQ, rrcI, rrcQ, ncoI, ncoQ, pll;
   RBuf<float> hist32;
   RBuf<uint8_t> bits;
   RBuf<int> counts;
   bool keep_nco = false;
+  bool cdr_carry = false;
   int cursor = 0;             // blocks waiting in bits/counts
   long long blocks_done = 0;  // since reset
   size_t last_n_if = 0;
@@ -705,6 +781,11 @@ static int rds_reset_device(sdr_rds *r) {
   std::vector<double> nans(B, nan);
   SDR_CUDA(cudaMemcpy2D(r->theta.p, r->theta_stride * sizeof(double), nans.data(), sizeof(double),
                         sizeof(double), B, cudaMemcpyHostToDevice));
+  {  // fmRDS.py:257-260: pair = (0, 0), start = 158, prev_size = 0
+    std::vector<double> cs(B * 4, 0.0);
+    for (size_t b = 0; b < B; ++b) cs[b * 4 + 1] = (double)RDS_CDR_START;
+    SDR_CUDA(cudaMemcpy(r->cdr_state.p, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   r->cursor = 0;
   r->blocks_done = 0;
   r->last_n_if = 0;
@@ -874,7 +955,10 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     a.batch = B;
     const int total = B * n_blocks;
     sdr_prof_begin(p, "k_rds_cdr", s);
-    k_rds_cdr<<<(total + RDS_CDR_WARPS - 1) / RDS_CDR_WARPS, 32 * RDS_CDR_WARPS, 0, s>>>(a);
+    if (r->cdr_carry)
+      k_rds_cdr_carry<<<(B + RDS_CDR_WARPS - 1) / RDS_CDR_WARPS, 32 * RDS_CDR_WARPS, 0, s>>>(a, r->cdr_state.p);
+    else
+      k_rds_cdr<<<(total + RDS_CDR_WARPS - 1) / RDS_CDR_WARPS, 32 * RDS_CDR_WARPS, 0, s>>>(a);
     if ((rc = sdr_check_launch(p, "k_rds_cdr"))) return rc;
   }
   {  // R7
@@ -1030,8 +1114,9 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
   const int blocks_per_call = (int)(r->cap_if / (size_t)r->block_if);
   r->blocks_cap = (cfg && cfg->max_pending_blocks > 0) ? cfg->max_pending_blocks : std::max(16, 2 * blocks_per_call);
   r->blocks_cap = std::max(r->blocks_cap, blocks_per_call);
-  r->bits_cap = r->block_out / r->sps + 4;
+  r->bits_cap = r->block_out / r->sps + 4;  // >= prefix bits + pairs, also with a carried start of 0
   r->keep_nco = cfg && cfg->keep_nco;
+  r->cdr_carry = cfg && cfg->cdr_carry;
   auto up = [](size_t v) { return (v + 3) / 4 * 4; };
   r->chan_stride = up(RDS_HC + r->cap_if);
   r->carr_stride = up(r->cap_if);
@@ -1066,7 +1151,7 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
             !r->carr.alloc(B * r->carr_stride) && !r->theta.alloc(B * r->theta_stride) && !r->mixI.alloc(B * r->mix_stride) &&
             !r->mixQ.alloc(B * r->mix_stride) && !r->rsI.alloc(B * r->rs_stride) &&
             !r->rsQ.alloc(B * r->rs_stride) && !r->rrcI.alloc(B * r->rrc_stride) &&
-            !r->rrcQ.alloc(B * r->rrc_stride) && !r->pll.alloc(B * 8) &&
+            !r->rrcQ.alloc(B * r->rrc_stride) && !r->pll.alloc(B * 8) && !r->cdr_state.alloc(B * 4) &&
             !r->hist32.alloc(B * (RDS_T - 1)) &&
             !r->bits.alloc(B * (size_t)r->blocks_cap * (size_t)r->bits_cap) &&
             !r->counts.alloc(B * (size_t)r->blocks_cap);

@@ -58,7 +58,7 @@ def model_chain(fm_demod, mode, block_if):
     st_rs = np.zeros(101 * p["U"] - 1); st_rs2 = np.zeros(101 * p["U"] - 1)
     st_rrc = np.zeros(100); st_rrc2 = np.zeros(100)
     decoded = np.array([])
-    out = dict(rrc_i=[], rrc_q=[], cdr=[], diff=[], offsets="", last={})
+    out = dict(rrc_i=[], rrc_q=[], cdr=[], diff=[], offsets="", last={}, sps=p["sps"])
     for bc in range(fm_demod.size // block_if):
         x = fm_demod[bc * block_if:(bc + 1) * block_if]
         chan, st_chan = signal.lfilter(c["chan"], 1.0, x, zi=st_chan)
@@ -96,6 +96,19 @@ def demod_of(mode, n_ref_blocks):
     return taps["demod"].astype(np.float64)
 
 
+def carried_cdr(rrc_blocks, sps):
+    """The model's CDR with its to_pass_on_state kept from block to block (what the function's
+    state arguments are for; fmRDS.py:257-260 re-creates the state instead)."""
+    state = [np.zeros(2), 158, 0]
+    bits_all, counts = [], []
+    for bc, rrc in enumerate(rrc_blocks):
+        bits, state = M.CDR(rrc, sps, state, bc)
+        bits_all.append(bits.astype(np.uint8))
+        counts.append(bits.size)
+    return dict(carry_bits=np.concatenate(bits_all), carry_counts=np.array(counts),
+                carry_state=np.array([state[0][0], state[0][1], state[1], state[2]], dtype=np.float64))
+
+
 def pack(res):
     d = dict(rrc_i=np.concatenate(res["rrc_i"]), rrc_q=np.concatenate(res["rrc_q"]),
              offsets=np.array(res["offsets"]),
@@ -103,6 +116,7 @@ def pack(res):
              cdr_bits=np.concatenate(res["cdr"]), diff_bits=np.concatenate(res["diff"]))
     for k, v in res["last"].items():
         d["last16_" + k] = v[::16].copy()
+    d.update(carried_cdr(res["rrc_i"], res["sps"]))
     return d
 
 
@@ -130,6 +144,14 @@ def bit_layer_cases():
             bits, _ = M.CDR(x, sps, st, bc)
             out[f"cdr_in_{k}"] = x
             out[f"cdr_out_{k}_bc{bc}"] = bits.astype(np.uint8)
+    # the same inputs with a carried state: an odd number of points left over (pairing branch,
+    # fmSupportLib.py:117-125), other start offsets
+    for k, x in enumerate(cases):
+        for j, (p0, start, prev) in enumerate([(0.7, 5, 3), (-0.4, 20, 4), (0.0, 0, 1)]):
+            st = [np.array([p0, 0.0]), start, prev]
+            bits, st = M.CDR(x, sps, st, 2)
+            out[f"cdrs_out_{k}_{j}"] = bits.astype(np.uint8)
+            out[f"cdrs_state_{k}_{j}"] = np.array([st[0][0], st[0][1], st[1], st[2]], dtype=np.float64)
     # differential decoding
     mb = rng.integers(0, 2, 64).astype(np.float64)
     out["diff_in"] = mb.astype(np.uint8)

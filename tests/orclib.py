@@ -190,6 +190,10 @@ class RdsOracle:
         L.rdo_resample.argtypes = [f64p, C.c_size_t, f64p, C.c_int, f64p, C.c_int, C.c_int, f64p]
         L.rdo_cdr.restype = C.c_int
         L.rdo_cdr.argtypes = [f64p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.rdo_cdr_state.restype = C.c_int
+        L.rdo_cdr_state.argtypes = [f64p, C.c_int, C.c_int, C.c_int, f64p, u8p, C.c_int]
+        L.rdo_chain_set_cdr_carry.restype = None
+        L.rdo_chain_set_cdr_carry.argtypes = [C.c_void_p, C.c_int]
         L.rdo_diff_decode.restype = None
         L.rdo_diff_decode.argtypes = [u8p, C.c_int, u8p]
         L.rdo_syndrome.restype = None
@@ -233,6 +237,13 @@ class RdsOracle:
         n = self.lib.rdo_cdr(x, x.size, sps, block_count, bits, bits.size)
         return bits[:n].copy()
 
+    def cdr_state(self, x, sps, block_count, state):
+        """state: float64[4] = pair[0], pair[1], start, prev_size; updated in place."""
+        x = np.ascontiguousarray(x, np.float64)
+        bits = np.zeros(x.size // sps + 4, np.uint8)
+        n = self.lib.rdo_cdr_state(x, x.size, sps, block_count, state, bits, bits.size)
+        return bits[:n].copy()
+
     def diff_decode(self, bits):
         bits = np.ascontiguousarray(bits, np.uint8)
         out = np.zeros_like(bits)
@@ -253,7 +264,7 @@ class RdsOracle:
         return o.decode(), idx.value
 
     # -- chain -----------------------------------------------------------------
-    def run_chain(self, fm_demod, mode, block_if=None, keep=("rrc_i", "rrc_q")):
+    def run_chain(self, fm_demod, mode, block_if=None, keep=("rrc_i", "rrc_q"), cdr_carry=False):
         """fm_demod: float array, a whole number of blocks.  Returns a dict with the kept
         stages concatenated over blocks, 'cdr_bits' / 'diff_bits' (lists per block) and
         'offsets' (one character per block)."""
@@ -263,6 +274,7 @@ class RdsOracle:
         h = self.lib.rdo_chain_create(mode, block_if)
         if not h:
             raise ValueError("RDS is defined for modes 0 and 2 only")
+        self.lib.rdo_chain_set_cdr_carry(h, 1 if cdr_carry else 0)
         out = {k: [] for k in keep}
         out.update(cdr_bits=[], diff_bits=[], offsets="")
         try:

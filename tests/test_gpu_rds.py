@@ -219,3 +219,38 @@ def test_rds_wide_batch(sdr, orc):
         want = oracle_chain(R, orc, iq[c], mode, block_if)
         parts = {(k, c): [first[c][k], second[c][k]] for k in STAGES}
         compare(parts, {c: reads[c]}, want, c, n_blocks, block_if)
+
+
+@pytest.mark.parametrize("mode,n_ref,kind", [(0, 15, "rds"), (0, 30, "rds_groups"), (2, 24, "rds_groups")])
+def test_rds_cdr_carried_state(sdr, orc, mode, n_ref, kind):
+    """cdr_carry=1: the model's CDR with its to_pass_on_state kept from block to block
+    (fmSupportLib.py:104-106,178-189) -- across blocks of one call and across calls."""
+    R = orclib.RDS()
+    block_if = 9600
+    full = [siggen.make_capture(5 + c, mode, n_ref, kind) for c in range(3)]
+    n_blocks = full[0].size // 192000
+    nbytes = n_blocks * 192000
+    iq = np.stack([f[:nbytes] for f in full])
+    with sdr.Pipeline(mode=mode, channels=1, batch=3, max_bytes_per_channel=nbytes) as p:
+        with sdr.Rds(p, block_if=block_if, cdr_carry=True, max_pending_blocks=n_blocks) as r:
+            cut = (n_blocks // 3) * 192000
+            p.process_host(np.ascontiguousarray(iq[:, :cut]))
+            p.process_host(np.ascontiguousarray(iq[:, cut:]))
+            reads = [r.read(c) for c in range(3)]
+    for c in range(3):
+        _, taps = orc.run_chain(full[c], mode, 1)
+        fm = taps["demod"][:n_blocks * block_if].astype(np.float64)
+        want = R.run_chain(fm, mode, block_if, keep=(), cdr_carry=True)
+        assert list(reads[c]["bit_counts"]) == [b.size for b in want["cdr_bits"]]
+        assert np.array_equal(reads[c]["cdr_bits"], np.concatenate(want["cdr_bits"]))
+        assert np.array_equal(reads[c]["diff_bits"], np.concatenate(want["diff_bits"]))
+        assert reads[c]["offsets"] == want["offsets"]
+    if mode == 0 and kind == "rds":
+        g = np.load(os.path.join(GOLD, "rds_mode0.npz"))   # the reference model itself, capture 200
+        iq1 = siggen.make_capture(200, 0, 15, "rds")[None, :8 * 192000]
+        with sdr.Pipeline(mode=0, channels=1, batch=1, max_bytes_per_channel=iq1.shape[1]) as p:
+            with sdr.Rds(p, block_if=9600, cdr_carry=True) as r:
+                p.process_host(iq1)
+                rd = r.read(0)
+        assert list(rd["bit_counts"]) == list(g["carry_counts"])
+        assert np.array_equal(rd["cdr_bits"], g["carry_bits"])

@@ -80,6 +80,26 @@ def test_bit_layer_matches_model():
         assert np.array_equal(R.syndrome(g[f"synd_in_{name}"]), g[f"synd_out_{name}"])
 
 
+def test_cdr_with_carried_state_matches_model():
+    """The model's CDR with its to_pass_on_state kept from block to block (fmSupportLib.py:104-106,
+    :178-189), on hand-made inputs (odd leftover -> pairing branch :117-125) and on the RRC output
+    of the golden capture."""
+    R = orclib.RDS()
+    g = np.load(os.path.join(GOLD, "rds_bits.npz"))
+    for k in range(6):
+        for j, (p0, start, prev) in enumerate([(0.7, 5, 3), (-0.4, 20, 4), (0.0, 0, 1)]):
+            st = np.array([p0, 0.0, start, prev], np.float64)
+            got = R.cdr_state(g[f"cdr_in_{k}"], 26, 2, st)
+            assert np.array_equal(got, g[f"cdrs_out_{k}_{j}"]), (k, j)
+            assert np.array_equal(st, g[f"cdrs_state_{k}_{j}"]), (k, j, st, g[f"cdrs_state_{k}_{j}"])
+    for mode, n_ref, block_if, n_blocks in ((0, 15, 9600, 8), (2, 12, 19200, 2)):
+        gm = np.load(os.path.join(GOLD, f"rds_mode{mode}.npz"))
+        fm = fm_demod_of(mode, n_ref)[:block_if * n_blocks]
+        r = R.run_chain(fm, mode, block_if, keep=(), cdr_carry=True)
+        assert [b.size for b in r["cdr_bits"]] == list(gm["carry_counts"])
+        assert np.array_equal(np.concatenate(r["cdr_bits"]), gm["carry_bits"])
+
+
 def test_offset_word_syndromes():
     """Known answers of the RDS standard (the reference's doc/3dy4-project-2022.pdf p.21 and
     fmSupportLib.py:62-91): a block of zero information bits whose check bits are the offset
