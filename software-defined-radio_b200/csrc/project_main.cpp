@@ -22,6 +22,8 @@
 //                                     differentially decoded bits.  Input is then consumed in
 //                                     units of 15 (mode 0) / 12 (mode 2) reference blocks, the
 //                                     smallest span that is whole in both block sizes.
+//            --rds-carry              with --rds: carry the clock-recovery state from block to block
+//                                     (sdr_rds_config.cdr_carry) instead of re-creating it per block
 //
 // The reference's two threads and bounded std::queue (project.cpp:141-149,181-189,471-496)
 // become: a reader thread filling two page-locked buffers, and the main thread handing
@@ -56,7 +58,7 @@ int die(const char *what) {
 
 void usage(const char *argv0) {
   std::fprintf(stderr,
-               "Usage: %s\nor\nUsage: %s <mode> [<channels>] [--taps rf,audio,stereo] [--blocks N] [--device D] [--rds FILE]\n"
+               "Usage: %s\nor\nUsage: %s <mode> [<channels>] [--taps rf,audio,stereo] [--blocks N] [--device D] [--rds FILE [--rds-carry]]\n"
                "\t\t <mode> is a value from 0 to 3, <channels> is 1 (mono) or 2 (stereo)\n",
                argv0, argv0);
 }
@@ -68,6 +70,7 @@ int main(int argc, char *argv[]) {
   int rf_taps = 151, audio_taps = 101, stereo_taps = 151;
   std::vector<std::string> pos;
   std::string rds_path;
+  bool rds_carry = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "--taps" && i + 1 < argc) {
@@ -81,6 +84,8 @@ int main(int argc, char *argv[]) {
       device = std::atoi(argv[++i]);
     } else if (a == "--rds" && i + 1 < argc) {
       rds_path = argv[++i];
+    } else if (a == "--rds-carry") {
+      rds_carry = true;
     } else if (a == "-h" || a == "--help") {
       usage(argv[0]);
       return 0;
@@ -139,6 +144,7 @@ int main(int argc, char *argv[]) {
   if (!rds_path.empty()) {
     sdr_rds_config rc{};
     rc.block_if = 9600;
+    rc.cdr_carry = rds_carry ? 1 : 0;
     if (sdr_rds_create(pipe, &rc, &rds) || sdr_rds_info(rds, &ri)) return die("sdr_rds_create");
     rds_out = std::fopen(rds_path.c_str(), "w");
     if (!rds_out) {
