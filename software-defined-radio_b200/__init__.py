@@ -239,6 +239,9 @@ class Pipeline:
         _check(lib().sdr_pipeline_create(C.byref(self.cfg), C.byref(self._h)))
 
     def close(self):
+        # a follower stage (Rds) holds a pointer to this handle: it goes first
+        for f in list(getattr(self, "_followers", [])):
+            f.close()
         if self._h:
             lib().sdr_pipeline_destroy(self._h)
             self._h = _vp()
@@ -349,11 +352,16 @@ class Rds:
         _check(lib().sdr_rds_create(pipeline._h, C.byref(cfg), C.byref(self._h)))
         self.info = RdsInfo()
         _check(lib().sdr_rds_info(self._h, C.byref(self.info)))
+        if not hasattr(pipeline, "_followers"):
+            pipeline._followers = []
+        pipeline._followers.append(self)
 
     def close(self):
         if self._h:
             lib().sdr_rds_destroy(self._h)
             self._h = _vp()
+            if self in getattr(self.pipeline, "_followers", []):
+                self.pipeline._followers.remove(self)
 
     def __del__(self):
         try:

@@ -199,6 +199,12 @@ def test_rds_reset_and_errors(sdr):
     with sdr.Pipeline(mode=1, batch=1, max_bytes_per_channel=1 << 20) as p:
         with pytest.raises(sdr.SdrError):
             sdr.Rds(p)
+    # closing the pipeline first takes its follower with it (no dangling handle)
+    p = sdr.Pipeline(mode=0, batch=1, max_bytes_per_channel=192000)
+    r = sdr.Rds(p)
+    p.close()
+    assert not r._h
+    r.close()
 
 
 def test_rds_wide_batch(sdr, orc):
