@@ -7,7 +7,8 @@
 //
 //   R1  k_rds_fir<151, float in>     channel band-pass 54-60 kHz            fmRDS.py:223
 //   R2  k_rds_fir<151, squared in>   x^2, carrier band-pass 113.5-114.5 kHz fmRDS.py:230-233
-//   R3a k_rds_pll                    PLL at 114 kHz (sequential, one lane per capture)  fmRDS.py:236
+//   R3a k_rds_pll_warp / k_rds_pll   PLL at 114 kHz: a warp per capture solving 32 samples at a time
+//                                    (up to 4096 captures), or one lane per capture  fmRDS.py:236
 //   R3b k_rds_mix                    NCO I and Q (scale 0.5, 3pi/8), all-pass delay (75)
 //                                    and both mixers                       fmRDS.py:227,241,251
 //   R4  k_rds_resample               rational resampler U/D, 101 taps per phase, gain U
@@ -1019,7 +1020,11 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     a.freq = 114e3;
     a.Fs = (double)r->view.if_Fs;
     a.normBandwidth = 0.002;
-    static const bool one_lane = std::getenv("SDR_RDS_PLL_LANE") != nullptr;  // the one-lane chain, for A/B runs
+    // Warp form below ~4096 captures (latency: 1.8 ms per 76 800 samples, flat up to ~1024
+    // captures, then ~0.95 ms per 1024 captures); one lane per capture above (4.7 ms, flat up to
+    // ~19 k captures): measured 8192 captures 7.9 vs 4.8 ms.  SDR_RDS_PLL=lane|warp forces one.
+    const char *force = std::getenv("SDR_RDS_PLL");
+    const bool one_lane = force ? force[0] == 'l' : B > 4096;
     sdr_prof_begin(p, "k_rds_pll", s);
     if (one_lane) k_rds_pll<<<(B + 31) / 32, 32, 0, s>>>(a);
     else k_rds_pll_warp<<<(B + RDS_PLLW_WARPS - 1) / RDS_PLLW_WARPS, 32 * RDS_PLLW_WARPS, 0, s>>>(a);

@@ -260,3 +260,25 @@ def test_rds_cdr_carried_state(sdr, orc, mode, n_ref, kind):
                 rd = r.read(0)
         assert list(rd["bit_counts"]) == list(g["carry_counts"])
         assert np.array_equal(rd["cdr_bits"], g["carry_bits"])
+
+
+def test_rds_pll_forms_agree(sdr, orc, monkeypatch):
+    """The two forms of the PLL kernel (a warp per capture solving 32 samples at a time, one
+    lane per capture walking them) against the oracle and against each other."""
+    R = orclib.RDS()
+    mode, block_if, n_blocks = 0, 9600, 8
+    nbytes = n_blocks * block_if * 20
+    iq = np.stack([siggen.make_capture(200 + c, mode, 15, k)[:nbytes]
+                   for c, k in enumerate(("rds", "stereo", "silence", "clipped", "rds_groups"))])
+    outs = {}
+    for form in ("warp", "lane"):
+        monkeypatch.setenv("SDR_RDS_PLL", form)
+        parts, reads = run_gpu(sdr, iq, mode, block_if, n_calls=2)
+        outs[form] = (parts, reads)
+        for c in range(iq.shape[0]):
+            want = oracle_chain(R, orc, iq[c], mode, block_if)
+            compare(parts, reads, want, c, n_blocks, block_if)
+    for c in range(iq.shape[0]):
+        a = np.concatenate(outs["warp"][0][("rrc_i", c)])
+        b = np.concatenate(outs["lane"][0][("rrc_i", c)])
+        close(a, b, 1e-9, "warp vs lane")
