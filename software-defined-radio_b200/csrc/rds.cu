@@ -297,8 +297,8 @@ static __global__ void __launch_bounds__(32) k_rds_pll(const RdsPllArgs a) {
 // choices are re-derived from the solved trajectory, and the tile is solved again until they
 // stop changing -- every pass fixes at least the first sample whose choice was wrong, two
 // passes are the rule, and a final solve with the converged choices makes the rounding of t
-// consistent too.  About 25 cycles per sample instead of the 119 of the one-lane chain, and
-// coalesced loads and stores.  Same model, same parity bound (1e-9 at every later stage).
+// consistent too.  Coalesced loads and stores.  (Described for one sample per lane; the kernel
+// below puts two on a lane.)  Same model, same parity bound (1e-9 at every later stage).
 // ---------------------------------------------------------------------------
 struct RdsM2 {
   double a, b, c, d;  // [[a, b], [c, d]]
@@ -309,6 +309,10 @@ __device__ __forceinline__ RdsM2 rds_mm(const RdsM2 &x, const RdsM2 &y) {
 
 constexpr int RDS_PLLW_WARPS = 4;
 
+// Two consecutive samples per lane, 64 per tile: a lane composes its two steps locally
+// (A*b0 + b1 under A^2), the prefix sum runs over A^2, A^4, .. A^32, and the state between a
+// lane's two samples is A times the previous lane's result plus b0.  Half the shuffle rounds
+// per sample of a 32-sample tile.
 static __global__ void __launch_bounds__(32 * RDS_PLLW_WARPS) k_rds_pll_warp(const RdsPllArgs a) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * RDS_PLLW_WARPS + (threadIdx.x >> 5);
@@ -318,15 +322,16 @@ static __global__ void __launch_bounds__(32 * RDS_PLLW_WARPS) k_rds_pll_warp(con
   const double Ki = __dmul_rn(__dmul_rn(a.normBandwidth, a.normBandwidth), 3.555);
   const double w = __dmul_rn(__dmul_rn(2.0, RDS_PI), __ddiv_rn(a.freq, a.Fs));          // fmSupportLib.py:340
   const double gI = Ki, gP = Kp + Ki;
-  // powers of A: pw[t] = A^(2^t); this lane's M = A^(lane+1)
-  RdsM2 pw[6];
+  // pw[t] = A^(2^t); this lane's M = A^(2*(lane+1))
+  RdsM2 pw[7];
   pw[0] = {1.0, -Ki, 1.0, 1.0 - Kp - Ki};
 #pragma unroll
-  for (int t = 1; t < 6; ++t) pw[t] = rds_mm(pw[t - 1], pw[t - 1]);
+  for (int t = 1; t < 7; ++t) pw[t] = rds_mm(pw[t - 1], pw[t - 1]);
+  const RdsM2 A = pw[0];
   RdsM2 M = {1.0, 0.0, 0.0, 1.0};
 #pragma unroll
-  for (int t = 0; t < 6; ++t)
-    if (((lane + 1) >> t) & 1) M = rds_mm(pw[t], M);
+  for (int t = 1; t < 7; ++t)
+    if (((2 * (lane + 1)) >> t) & 1) M = rds_mm(pw[t], M);
   double *st = a.state + (size_t)b * 8;
   double I0 = st[0], P0 = st[1], r0 = st[2];
   const double n0 = st[5];
@@ -335,22 +340,25 @@ static __global__ void __launch_bounds__(32 * RDS_PLLW_WARPS) k_rds_pll_warp(con
   constexpr int HALF_PI_HI = 0x3ff921fb;
   constexpr unsigned HALF_PI_LO = 0x54442d18u;
   constexpr double ROUND_MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-  double x_next = lane < a.n ? in[lane] : 0.0;
-  for (int k0 = 0; k0 < a.n; k0 += 32) {
-    const int kn = min(32, a.n - k0);
-    const double x = x_next;
-    x_next = (k0 + 32 + lane < a.n) ? in[k0 + 32 + lane] : 0.0;   // next tile, a tile ahead
-    // this lane's sample is k = k0 + lane; its step uses t of sample k-1 = w*(n0+k) + P_{k-1}
-    const double wn_prev = __dmul_rn(w, n0 + (double)(k0 + lane));
-    const double wn_this = __dmul_rn(w, n0 + (double)(k0 + lane + 1));
+  auto load2 = [&](int k, double &v0, double &v1) {
+    v0 = k < a.n ? in[k] : 1.0;          // (past the end: any non-zero value, never used)
+    v1 = k + 1 < a.n ? in[k + 1] : 1.0;
+  };
+  double xn0, xn1;
+  load2(2 * lane, xn0, xn1);
+  for (int k0 = 0; k0 < a.n; k0 += 64) {
+    const int kn = min(64, a.n - k0);
+    const double x0 = xn0, x1 = xn1;
+    load2(k0 + 64 + 2 * lane, xn0, xn1);   // next tile, a tile ahead
+    const bool v0 = 2 * lane < kn, v1 = 2 * lane + 1 < kn;
     // A tile with an exactly-zero sample (silence) is walked in order by every lane alike, with
     // the model's own sequence of operations: there the detector's output (0 or +-pi, atan2's
     // signed-zero cases) does not depend on the phase beyond its class, the phase estimate
     // grows without bound, and results become sensitive to the order of the roundings.
-    if (__any_sync(FULL, lane < kn && x == 0.0)) {
-      double I = I0, P = P0, r = r0, mine = 0.0;
+    if (__any_sync(FULL, (v0 && x0 == 0.0) || (v1 && x1 == 0.0))) {
+      double I = I0, P = P0, r = r0, mine0 = 0.0, mine1 = 0.0;
       for (int j = 0; j < kn; ++j) {
-        const double xj = __shfl_sync(FULL, x, j);
+        const double xj = __shfl_sync(FULL, (j & 1) ? x1 : x0, j >> 1);
         const bool r_neg = __double2hiint(r) < 0;
         double c = xj > 0.0 ? 0.0 : (r_neg ? -RDS_PI : RDS_PI);
         double rr = r;
@@ -364,60 +372,81 @@ static __global__ void __launch_bounds__(32 * RDS_PLLW_WARPS) k_rds_pll_warp(con
         I = fma(Ki, errorD, I);
         P = __dadd_rn(fma(Kp, errorD, P), I);
         const double t = __dadd_rn(__dmul_rn(w, n0 + (double)(k0 + j + 1)), P);
-        if (lane == j) mine = t;
+        if (lane == (j >> 1)) {
+          if (j & 1) mine1 = t;
+          else mine0 = t;
+        }
         const double turns = __dsub_rn(fma(t, RDS_INV_2PI, ROUND_MAGIC), ROUND_MAGIC);
         r = fma(-turns, RDS_2PI_LO, fma(-turns, RDS_2PI_HI, t));
       }
-      if (lane < kn) th[k0 + lane] = mine;
+      if (v0) th[k0 + 2 * lane] = mine0;
+      if (v1) th[k0 + 2 * lane + 1] = mine1;
       I0 = I;
       P0 = P;
       r0 = r;
       continue;
     }
-    double Pprev = lane == 0 ? P0 : fma((double)lane, I0, P0);     // first guess: the integrator's drift
-    double I = 0.0, P = 0.0;
-    double sig_turns = 0.0;
-    int sig_bits = -1;
-    for (int it = 0; it < 40; ++it) {
-      // ---- discrete choices and g from the guess ----
-      double r, turns = 0.0;
+    // this lane's samples are k = k0 + 2*lane and k + 1; a step uses t of the sample before it
+    const double wn_a = __dmul_rn(w, n0 + (double)(k0 + 2 * lane));       // t of sample k-1
+    const double wn_b = __dmul_rn(w, n0 + (double)(k0 + 2 * lane + 1));   // t of sample k
+    const double wn_c = __dmul_rn(w, n0 + (double)(k0 + 2 * lane + 2));   // t of sample k+1
+    double Pp0 = lane == 0 ? P0 : fma((double)(2 * lane), I0, P0);        // first guess: the integrator's drift
+    double Pp1 = fma((double)(2 * lane + 1), I0, P0);
+    double SI0 = 0.0, SP0 = 0.0, SI1 = 0.0, SP1 = 0.0;                    // state after sample k / k+1
+    double sg_t0 = 0.0, sg_t1 = 0.0;
+    int sg_b0 = -1, sg_b1 = -1;
+    for (int it = 0; it < 72; ++it) {
+      // ---- discrete choices and g = c - r + P^ from the guesses ----
+      double ra, tu0 = 0.0;
       if (lane == 0) {
-        r = r0;  // exact: carried from the previous tile / call
+        ra = r0;  // exact: carried from the previous tile / call
       } else {
-        const double t = __dadd_rn(wn_prev, Pprev);
-        turns = __dsub_rn(fma(t, RDS_INV_2PI, ROUND_MAGIC), ROUND_MAGIC);
-        r = fma(-turns, RDS_2PI_LO, fma(-turns, RDS_2PI_HI, t));
+        const double t = __dadd_rn(wn_a, Pp0);
+        tu0 = __dsub_rn(fma(t, RDS_INV_2PI, ROUND_MAGIC), ROUND_MAGIC);
+        ra = fma(-tu0, RDS_2PI_LO, fma(-tu0, RDS_2PI_HI, t));
       }
-      const bool r_neg = __double2hiint(r) < 0;
-      const double c = x > 0.0 ? 0.0 : (r_neg ? -RDS_PI : RDS_PI);
-      const bool same = it > 0 && (int)r_neg == sig_bits && turns == sig_turns;
-      const bool converged = __all_sync(FULL, same || lane >= kn);
-      sig_bits = (int)r_neg;
-      sig_turns = turns;
-      // ---- solve the tile: (I, P)_j = A (I, P)_{j-1} + g_j (Ki, Kp + Ki), g_j = (c - r)_j + Pprev_j ----
-      const double g = lane < kn ? __dadd_rn(__dsub_rn(c, r), Pprev) : 0.0;
-      double vI = g * gI, vP = g * gP;
+      const double tb = __dadd_rn(wn_b, Pp1);
+      const double tu1 = __dsub_rn(fma(tb, RDS_INV_2PI, ROUND_MAGIC), ROUND_MAGIC);
+      const double rb = fma(-tu1, RDS_2PI_LO, fma(-tu1, RDS_2PI_HI, tb));
+      const int n0b = __double2hiint(ra) < 0, n1b = __double2hiint(rb) < 0;
+      const double c0 = x0 > 0.0 ? 0.0 : (n0b ? -RDS_PI : RDS_PI);
+      const double c1 = x1 > 0.0 ? 0.0 : (n1b ? -RDS_PI : RDS_PI);
+      const bool same = it > 0 && (!v0 || (n0b == sg_b0 && tu0 == sg_t0)) && (!v1 || (n1b == sg_b1 && tu1 == sg_t1));
+      const bool converged = __all_sync(FULL, same);
+      sg_b0 = n0b; sg_b1 = n1b; sg_t0 = tu0; sg_t1 = tu1;
+      const double g0 = v0 ? __dadd_rn(__dsub_rn(c0, ra), Pp0) : 0.0;
+      const double g1 = v1 ? __dadd_rn(__dsub_rn(c1, rb), Pp1) : 0.0;
+      // ---- solve: per lane (I, P) -> A^2 (I, P) + (A b0 + b1), b = g (Ki, Kp + Ki) ----
+      const double b0I = g0 * gI, b0P = g0 * gP;
+      double vI = fma(A.a, b0I, fma(A.b, b0P, g1 * gI));
+      double vP = fma(A.c, b0I, fma(A.d, b0P, g1 * gP));
 #pragma unroll
       for (int t = 0; t < 5; ++t) {
         const double uI = __shfl_up_sync(FULL, vI, 1 << t), uP = __shfl_up_sync(FULL, vP, 1 << t);
         if (lane >= (1 << t)) {
-          vI = fma(pw[t].a, uI, fma(pw[t].b, uP, vI));
-          vP = fma(pw[t].c, uI, fma(pw[t].d, uP, vP));
+          vI = fma(pw[t + 1].a, uI, fma(pw[t + 1].b, uP, vI));
+          vP = fma(pw[t + 1].c, uI, fma(pw[t + 1].d, uP, vP));
         }
       }
-      I = fma(M.a, I0, fma(M.b, P0, vI));
-      P = fma(M.c, I0, fma(M.d, P0, vP));
-      const double Pup = __shfl_up_sync(FULL, P, 1);
-      Pprev = lane == 0 ? P0 : Pup;
+      SI1 = fma(M.a, I0, fma(M.b, P0, vI));
+      SP1 = fma(M.c, I0, fma(M.d, P0, vP));
+      double pI = __shfl_up_sync(FULL, SI1, 1), pP = __shfl_up_sync(FULL, SP1, 1);
+      if (lane == 0) { pI = I0; pP = P0; }
+      SI0 = fma(A.a, pI, fma(A.b, pP, b0I));
+      SP0 = fma(A.c, pI, fma(A.d, pP, b0P));
+      Pp0 = pP;    // P of the sample before this lane's first
+      Pp1 = SP0;   // P of this lane's first sample
       if (converged) break;  // this pass was solved with settled choices and a settled guess
     }
     // ---- this tile's NCO phases; state for the next tile ----
-    const double trigArg = __dadd_rn(wn_this, P);
-    if (lane < kn) th[k0 + lane] = trigArg;
-    const int last = kn - 1;
-    I0 = __shfl_sync(FULL, I, last);
-    P0 = __shfl_sync(FULL, P, last);
-    const double tl = __shfl_sync(FULL, trigArg, last);
+    const double t0 = __dadd_rn(wn_b, SP0), t1 = __dadd_rn(wn_c, SP1);
+    if (v0) th[k0 + 2 * lane] = t0;
+    if (v1) th[k0 + 2 * lane + 1] = t1;
+    const int last = kn - 1, ll = last >> 1;
+    const bool odd = last & 1;
+    I0 = __shfl_sync(FULL, odd ? SI1 : SI0, ll);
+    P0 = __shfl_sync(FULL, odd ? SP1 : SP0, ll);
+    const double tl = __shfl_sync(FULL, odd ? t1 : t0, ll);
     const double turns_l = __dsub_rn(fma(tl, RDS_INV_2PI, ROUND_MAGIC), ROUND_MAGIC);
     r0 = fma(-turns_l, RDS_2PI_LO, fma(-turns_l, RDS_2PI_HI, tl));
   }
