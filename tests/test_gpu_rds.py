@@ -282,3 +282,29 @@ def test_rds_pll_forms_agree(sdr, orc, monkeypatch):
         a = np.concatenate(outs["warp"][0][("rrc_i", c)])
         b = np.concatenate(outs["lane"][0][("rrc_i", c)])
         close(a, b, 1e-9, "warp vs lane")
+
+
+def test_rds_mode2_model_block(sdr, orc):
+    """The model's own mode-2 block (fmRDS.py:152: 10*800*1920*2 = 30 720 000 bytes = 1 536 000 IF
+    samples, 653 600 symbol-rate samples, ~15 200 sampling points for the CDR): one capture, one
+    block.  At this length the NCO phase reaches 4.6e6 rad, where one ulp is 9e-10: the NCO
+    outputs get twice the usual bound."""
+    R = orclib.RDS()
+    mode, block_if = 2, 1536000
+    nbytes = block_if * 20
+    full = siggen.make_capture(200, mode, 275, "rds_groups")
+    iq = full[None, :nbytes]
+    with sdr.Pipeline(mode=mode, channels=1, batch=1, max_bytes_per_channel=nbytes) as p:
+        with sdr.Rds(p) as r:   # block_if = 0: the model's
+            assert r.info.block_if == block_if and r.info.block_bytes == nbytes
+            p.process_host(iq)
+            got = {k: r.tap(k, 0) for k in ("channel_filt", "carrier_filt", "mixer_i", "resampler_i", "rrc_i", "rrc_q")}
+            rd = r.read(0)
+    _, taps = orc.run_chain(full, mode, 1)
+    want = R.run_chain(taps["demod"][:block_if].astype(np.float64), mode, block_if, keep=tuple(got))
+    for k in got:
+        close(got[k], want[k], 1e-12 if k in ("channel_filt", "carrier_filt") else 2e-9, k)
+    assert np.array_equal(rd["cdr_bits"], want["cdr_bits"][0])
+    assert np.array_equal(rd["diff_bits"], want["diff_bits"][0])
+    assert rd["offsets"] == want["offsets"]
+    assert rd["cdr_bits"].size > 7000
