@@ -11,6 +11,7 @@ the 147/800 polyphase resampler), 1024 batched captures on one B200, functional 
 GPU (captures are independent: no collective on the data path, weak scaling).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
+      (also times, with short runs, the other BASELINE.json configs -> "other_configs"; --no-others skips them)
   python bench.py --impl reference [...]                       the reference's CPU path
   torchrun ... bench.py --gpus N ...                           one rank per GPU (driver-launched)
 """
@@ -180,7 +181,8 @@ def workload_config(args):
             "blocks_per_capture": args.blocks, "l2_policy": "input batch larger than L2 (no flush needed)",
             "variant": ("fast (tensor-core RF front end; PCM within +-1 LSB of the reference)"
                         if args.variant == "fast" and args.audio_channels == 1
-                        else "exact (bit-identical to the reference)")}
+                        else "mixed (bit-exact in front of the PLL, contracted multiply-adds elsewhere; PCM +-1 LSB)"
+                        if args.variant == "mixed" else "exact (bit-identical to the reference)")}
 
 
 BLOCK_BYTES = {0: 102400, 1: 61440, 2: 112000, 3: 134400}
@@ -210,19 +212,81 @@ def make_host_batch(mode, batch, blocks, kind, out=None):
 
 
 def make_device_batch(torch, mode, batch, blocks, kind, device):
-    """Built on the host and uploaded once (not timed), so that no torch kernels run."""
-    return torch.from_numpy(make_host_batch(mode, batch, blocks, kind)).to(device)
+    """A few distinct captures are built on the host; the batch is tiled from them on the device
+    with the same per-row circular shift as make_host_batch (outside every timed region)."""
+    from sdr_b200 import siggen
+    distinct = min(batch, 8)
+    base = torch.from_numpy(np.stack([siggen.make_capture(c, mode, blocks, kind) for c in range(distinct)])).to(device)
+    n = base.shape[1]
+    out = torch.empty((batch, n), dtype=torch.uint8, device=device)
+    for g in range((batch + distinct - 1) // distinct):
+        rot = 2 * (g * 977 % (n // 2))
+        rows = min(distinct, batch - g * distinct)
+        out[g * distinct:g * distinct + rows] = torch.roll(base[:rows], shifts=rot, dims=1) if rot else base[:rows]
+    return out
+
+
+def parity_rows(torch, orc_mod, groups, d_iq, nbytes, mode, rows_per_group=4):
+    """After the timed region: reset every pipeline handle, run ONE call on the bench's own device
+    batch and compare a few rows of its PCM with the CPU oracle fed with the same bytes (the
+    oracle is test infrastructure; nothing of it runs inside a timed region).  Exact variant:
+    bit-identical; fast / mixed: within +-1 LSB."""
+    orc = orc_mod.ORC()
+    worst, checked, ok = 0, 0, True
+    per = groups[0][2].shape[0]
+    for gi, (p, rds, rows, d_pcm, stream, vname) in enumerate(groups):
+        if rds is not None:
+            rds.discard()
+        p.reset()
+        d_pcm.zero_()
+        torch.cuda.synchronize()
+        p.process_device(rows.data_ptr(), rows.stride(0), nbytes, d_pcm.data_ptr(), d_pcm.stride(0), stream.cuda_stream)
+        torch.cuda.synchronize()
+        ch = p.cfg.channels
+        pick = sorted({0, 1, per // 2, per - 1})[:rows_per_group]
+        for r in pick:
+            want, _ = orc.run_chain(rows[r].cpu().numpy(), mode, ch, TAPS["rf_taps"], TAPS["audio_taps"],
+                                    TAPS["stereo_taps"], keep_taps=False)
+            got = d_pcm[r].cpu().numpy()
+            d = int(np.abs(got.astype(np.int32) - want.astype(np.int32)).max()) if got.size == want.size else 1 << 30
+            worst = max(worst, d)
+            ok = ok and d <= (0 if vname == "exact" else 1)
+            checked += 1
+    return {"parity_checked": bool(ok), "rows": checked, "max_abs_lsb": worst,
+            "bar": "bit-identical (exact) / +-1 LSB (fast, mixed) vs the CPU oracle on the bench's own input"}
 
 
 def pick_variant(sdr, args, mode, audio_channels):
-    """FAST exists for mono (all modes); stereo needs the bit-exact path (PLL parity)."""
+    """FAST exists for mono (all modes); stereo needs the bit-exact chain in front of the PLL:
+    EXACT (everything bit-identical) or MIXED (only what feeds the PLL is exact)."""
     if args.variant == "fast" and audio_channels == 1:
         return sdr.VARIANT_FAST, "fast"
+    if args.variant == "mixed":
+        return sdr.VARIANT_MIXED, "mixed"
     return sdr.VARIANT_EXACT, "exact"
 
 
+def fp32_ceiling_msps(mode, audio_channels, variant, sm_mhz):
+    """What the CUDA-core (exact / mixed) chains are bounded by: FP32-pipe instructions per input
+    sample of the FIR kernels alone (PLL, discriminator, staging, PCM packing counted as free) over
+    148 SMs x 128 lanes x clock.  The reference's multiply-add is two instructions (separately
+    rounded FMUL + FADD); a contracted one is one."""
+    D = {0: 10, 1: 5, 2: 10, 3: 3}[mode]
+    Da_over_U = {0: 5.0, 1: 6.0, 2: 800.0 / 147.0, 3: 3200.0 / 441.0}[mode]
+    exact, fma = 2.0, 1.0
+    rf = 2 * TAPS["rf_taps"] / D * (exact if variant != "fast" else 0.0)      # I and Q (fast: tensor cores)
+    audio_cost = exact if variant == "exact" else fma
+    audio = TAPS["audio_taps"] / (D * Da_over_U) * audio_cost * (2 if audio_channels == 2 else 1)
+    bpf = 0.0
+    if audio_channels == 2:
+        bpf = TAPS["stereo_taps"] / D * (exact + (exact if variant == "exact" else fma))   # pilot (always exact) + 22-54 kHz band
+    instr = rf + audio + bpf
+    rate = 148 * 128 * (sm_mhz or 1965.0) * 1e6
+    return {"fp32_instr_per_sample": instr, "ceiling_msps": rate / instr / 1e6 if instr else None}
+
+
 def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, world, profile=True,
-                force_exact=False):
+                force_exact=False, check_parity=False):
     """Device-resident timing of one configuration.  Returns dict with ms/step (max over ranks),
     per-kernel times and launches.
 
@@ -316,6 +380,11 @@ def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, wor
         rd = groups[0][1].read(0)
         rds_info = {"blocks": int(rd["bit_counts"].size), "bits_capture0": int(rd["cdr_bits"].size),
                     "offsets_capture0_tail": rd["offsets"][-16:]}
+    parity = None
+    if check_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import orclib
+        parity = parity_rows(torch, orclib, groups, d_iq, nbytes, mode)
     for g in groups:
         if g[1] is not None:
             g[1].close()
@@ -326,47 +395,91 @@ def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, wor
     torch.cuda.empty_cache()
     return {"ms_per_step": ms / steps, "samples_per_step": samples_per_step, "launches": launches,
             "kernels": ktimes, "nbytes": nbytes, "n_pcm": n_pcm_total // args.batch, "checksum": checksum,
-            "variant": vname, "rds": rds_info, "pcm_values_per_step": n_pcm_total}
+            "variant": vname, "rds": rds_info, "pcm_values_per_step": n_pcm_total, "parity": parity}
 
 
-def time_e2e(torch, sdr, args, steps, dist, world):
-    """Same metric through the public host-buffer call (sdr_pipeline_process_host): pinned host
-    input -> H2D -> kernels -> D2H PCM, all inside the timed region, every step."""
-    from sdr_b200 import siggen
-    dev_index = torch.cuda.current_device()
+def copy_ceiling(torch, devices, bytes_per_device, reps=3):
+    """Plain pinned host -> device copies, one cudaMemcpyAsync per device and repetition, all
+    devices concurrently: what the box's host memory system and PCIe links deliver with no
+    pipeline behind them.  Returns aggregate GB/s (the best of `reps` rounds)."""
+    bufs = []
+    for d in devices:
+        h = torch.empty(bytes_per_device, dtype=torch.uint8).pin_memory()
+        h.fill_(1)
+        with torch.cuda.device(d):
+            bufs.append((h, torch.empty(bytes_per_device, dtype=torch.uint8, device=f"cuda:{d}"),
+                         torch.cuda.Stream(device=d)))
+    best = 0.0
+    for _ in range(reps + 1):
+        for d in devices:
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        for (h, g, st) in bufs:
+            with torch.cuda.stream(st):
+                g.copy_(h, non_blocking=True)
+        for d in devices:
+            torch.cuda.synchronize(d)
+        dt = time.perf_counter() - t0
+        best = max(best, len(devices) * bytes_per_device / dt / 1e9)
+    del bufs
+    return best
+
+
+def time_e2e(torch, sdr, args, steps, world, rank, barrier):
+    """Same metric through the public host-buffer API, host buffers in, host PCM out, every copy
+    inside the timed region.  One GPU: sdr_pipeline_process_host.  N GPUs: ONE process (rank 0)
+    hands the whole batch of N x `batch` captures to sdr_multi_process_host, which spreads it over
+    the N devices with one host thread each and gathers the PCM into one host array -- the final
+    host gather is therefore inside the timed region; the other ranks only wait."""
     blocks = min(args.blocks, args.e2e_blocks)
     nbytes = blocks * BLOCK_BYTES[args.mode]
-    h_iq = torch.empty((args.batch, nbytes), dtype=torch.uint8).pin_memory()
-    make_host_batch(args.mode, args.batch, blocks, "stereo", out=h_iq.numpy())
-    p = sdr.Pipeline(mode=args.mode, channels=args.audio_channels, batch=args.batch, device=dev_index,
-                     max_bytes_per_channel=nbytes, variant=pick_variant(sdr, args, args.mode, args.audio_channels)[0],
-                     **TAPS)
+    if rank != 0:
+        barrier()
+        return None
+    total = args.batch * world
+    os.sched_setaffinity(0, range(os.cpu_count()))   # worker threads inherit: let them use every core
+    h_iq = torch.empty((total, nbytes), dtype=torch.uint8).pin_memory()
+    make_host_batch(args.mode, args.batch, blocks, "stereo", out=h_iq.numpy()[:args.batch])
+    for r in range(1, world):   # the other devices' ranges: the same captures, rotated by one row
+        h_iq[r * args.batch:(r + 1) * args.batch] = torch.roll(h_iq[:args.batch], shifts=r, dims=0)
+    variant = pick_variant(sdr, args, args.mode, args.audio_channels)[0]
+    if world == 1:
+        p = sdr.Pipeline(mode=args.mode, channels=args.audio_channels, batch=total, device=torch.cuda.current_device(),
+                         max_bytes_per_channel=nbytes, variant=variant, **TAPS)
+        api = "sdr_pipeline_process_host (pinned host buffers, 3 streams, double-buffered slices)"
+    else:
+        p = sdr.MultiPipeline(mode=args.mode, channels=args.audio_channels, batch=total, devices=world,
+                              max_bytes_per_channel=nbytes, variant=variant, **TAPS)
+        api = (f"sdr_multi_process_host: one process, {world} devices, one host thread per device, contiguous "
+               "capture ranges, PCM gathered into one pinned host array")
     n_pcm = p.pcm_count(nbytes)
-    h_pcm = torch.empty((args.batch, n_pcm), dtype=torch.int16).pin_memory()
+    h_pcm = torch.empty((total, n_pcm), dtype=torch.int16).pin_memory()
 
     def step():
         p.process_host_ptr(h_iq.data_ptr(), h_iq.stride(0), nbytes, h_pcm.data_ptr(), h_pcm.stride(0))
 
     step()  # warm-up: allocates the staging buffers
     step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        step()
-    torch.cuda.synchronize()
+        step()          # returns when the whole batch's PCM is in h_pcm
     sec = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([sec], dtype=torch.float64, device=torch.device("cuda", dev_index))
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
     p.close()
-    samples = args.batch * (nbytes // 2) * steps * world
-    return {"value": samples / sec / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(args.batch * nbytes),
-            "d2h_bytes_per_step": int(args.batch * n_pcm * 2), "blocks_per_capture": blocks,
-            "ms_per_step": sec / steps * 1e3,
-            "api": "sdr_pipeline_process_host (pinned host buffers, 3 streams, double-buffered slices)"}
+    ceiling = copy_ceiling(torch, list(range(world)), args.batch * nbytes)
+    del h_iq, h_pcm
+    barrier()
+    samples = total * (nbytes // 2) * steps
+    h2d = int(total * nbytes)
+    return {"value": samples / sec / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": int(total * n_pcm * 2), "blocks_per_capture": blocks,
+            "ms_per_step": sec / steps * 1e3, "api": api,
+            "h2d_gbs": h2d * steps / sec / 1e9,
+            "copy_ceiling_gbs": ceiling,
+            "frac_of_copy_ceiling": h2d * steps / sec / 1e9 / ceiling if ceiling else None,
+            "copy_ceiling_how": f"{world} concurrent pinned cudaMemcpyAsync H2D of {args.batch * nbytes} B each, best of 3 "
+                                "(tools/h2d_ceiling.cu is the stand-alone probe)",
+            "host_gather_in_timed_region": True}
 
 
 def bind_to_gpu_numa_node(index: int):
@@ -389,6 +502,41 @@ def bind_to_gpu_numa_node(index: int):
     return before  # the caller restores it before the CPU-baseline leg forks its workers
 
 
+def with_args(args, **kw):
+    d = dict(vars(args))
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def other_config_list(args, world):
+    """The BASELINE.json configs that are not the headline one, as short runs (3 warm-up + 3 timed
+    steps).  Per GPU; under torchrun only the sharded mixed config (configs[3]) and the stereo
+    shapes are repeated on every rank."""
+    base = dict(streams=1, mixed=False, rds=False, variant="fast", batch=1024, blocks=16)
+    lst = []
+    if world == 1:
+        lst += [("mono_mode0", "configs[1]: mono, mode 0 (48 kS/s, plain decimating audio filter)",
+                 dict(base, mode=0, audio_channels=1)),
+                ("mono_mode1", "configs[1]: mono, mode 1 (1.44 MS/s, rf_decim 5)", dict(base, mode=1, audio_channels=1)),
+                ("mono_mode3", "configs[1]: mono custom-rate mode 3 (960 kS/s -> 44.1 kS/s, 441/3200)",
+                 dict(base, mode=3, audio_channels=1)),
+                ("mono_mode2_exact", "headline shape on the bit-exact CUDA-core path",
+                 dict(base, mode=2, audio_channels=1, variant="exact")),
+                ("stereo_mode0_1024", "configs[2]: stereo, 1024 captures (the PLL's 32 warps cannot fill the GPU)",
+                 dict(base, mode=0, audio_channels=2, variant="exact"))]
+    lst += [("stereo_mode0_fill", "configs[2] shaped to fill the GPU: 16384 captures x 4 blocks, bit-exact",
+             dict(base, mode=0, audio_channels=2, variant="exact", batch=16384, blocks=4)),
+            ("stereo_mode0_fill_mixed", "same shape, SDR_VARIANT_MIXED (PLL chain exact, other filters contracted, PCM +-1 LSB)",
+             dict(base, mode=0, audio_channels=2, variant="mixed", batch=16384, blocks=4)),
+            ("mixed_8192", f"configs[3]: 8192 captures (half mono fast, half stereo exact) over {world} GPU(s), "
+                           f"{8192 // world} per GPU, two pipeline handles on two streams",
+             dict(base, mode=0, audio_channels=1, mixed=True, streams=2, batch=8192 // world, blocks=4))]
+    if world == 1:
+        lst += [("stereo_rds_mode0", "configs[4]: stereo + RDS chain (BPF, squaring PLL, RRC, clock recovery), 1024 captures x 15 blocks",
+                 dict(base, mode=0, audio_channels=2, variant="exact", rds=True, blocks=15))]
+    return lst
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -401,42 +549,75 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200 (sm_100) GPU: the product has no CPU fallback")
     torch.cuda.set_device(local)
     affinity_before = bind_to_gpu_numa_node(local)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")   # host-side waits that keep the GPUs idle
+
+    def cpu_barrier():
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
 
-    main = time_config(torch, sdr, args, args.mode, args.audio_channels, args.steps, args.warmup, dist, world)
+    main = time_config(torch, sdr, args, args.mode, args.audio_channels, args.steps, args.warmup, dist, world,
+                       check_parity=(rank == 0 and not args.no_parity))
     clocks = None
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=3)
         clocks = sampler.summary()
-
-    e2e = None if (args.rds or args.mixed or args.streams > 1) else \
-        time_e2e(torch, sdr, args, max(2, min(args.steps, 5)), dist, world)
-    os.sched_setaffinity(0, affinity_before)
+    peak, peak_src = measured_peak()
+    sm_mhz = (clocks or {}).get("sm_mhz")
 
     others = {}
-    if args.others and world == 1:
-        for name, (m, ch, ex) in {"mono_mode0": (0, 1, False), "mono_mode2_exact": (2, 1, True),
-                                  "mono_mode0_exact": (0, 1, True), "stereo_mode0": (0, 2, False),
-                                  "stereo_mode2": (2, 2, False)}.items():
-            r = time_config(torch, sdr, args, m, ch, max(2, args.steps // 4), 3, dist, world, profile=True,
-                            force_exact=ex)
-            msps = r["samples_per_step"] / (r["ms_per_step"] * 1e-3) / 1e6
-            peak, _ = measured_peak()
-            others[name] = {"value": msps, "unit": UNIT, "variant": r["variant"], "ms_per_step": r["ms_per_step"],
-                            "hbm_frac": msps * 1e6 * algorithmic_bytes_per_sample(m, ch) / 1e9 / peak,
-                            "kernel_ms_per_step": {k: v[0] / max(1, v[1]) * (v[1] / max(2, args.steps // 4))
-                                                   for k, v in r["kernels"].items()}}
+    if not args.no_others:
+        for name, what, kw in other_config_list(args, world):
+            a = with_args(args, **kw)
+            try:
+                r = time_config(torch, sdr, a, a.mode, a.audio_channels, 3, 3, dist, world, profile=True,
+                                check_parity=(rank == 0 and not args.no_parity))
+            except Exception as e:   # an optional line must not take the headline down with it
+                others[name] = {"what": what, "error": str(e)[:300]}
+                if world > 1:
+                    raise
+                continue
+            msps = r["samples_per_step"] * world / (r["ms_per_step"] * 1e-3) / 1e6
+            bps = algorithmic_bytes_per_sample(a.mode, a.audio_channels)
+            if a.mixed:
+                bps = 0.5 * (algorithmic_bytes_per_sample(a.mode, 1) + algorithmic_bytes_per_sample(a.mode, 2))
+            kms = {k: v[0] / 3 for k, v in r["kernels"].items()}
+            dom = max(kms, key=kms.get) if kms else None
+            o = {"what": what, "value": msps, "unit": UNIT, "n_gpus": world, "variant": r["variant"],
+                 "ms_per_step": r["ms_per_step"], "steps": 3, "warmup": 3,
+                 "workload": workload_config(a)["workload"],
+                 "whole_step_frac": msps * 1e6 * bps / 1e9 / peak / world,
+                 "dominant_kernel": dom, "kernel_ms_per_step": kms, "gpu_launches": r["launches"],
+                 "parity": r["parity"]}
+            if a.audio_channels == 2 and not a.mixed:
+                c = fp32_ceiling_msps(a.mode, 2, r["variant"], sm_mhz)
+                o["fp32_pipe_ceiling"] = dict(c, frac_of_ceiling=msps / world / c["ceiling_msps"],
+                                              note="FIR kernels' FP32-pipe instructions only (the reference's "
+                                                   "multiply-add = FMUL + FADD), 148 SMs x 128 lanes x SM clock; "
+                                                   "the bit-exact chain cannot reach the HBM roofline")
+            if r.get("rds"):
+                o["rds"] = r["rds"]
+            others[name] = o
+
+    e2e = None
+    if not (args.rds or args.mixed or args.streams > 1):
+        os.sched_setaffinity(0, affinity_before)
+        if world == 1:
+            bind_to_gpu_numa_node(local)
+        e2e = time_e2e(torch, sdr, args, max(2, min(args.steps, 5)), world, rank, cpu_barrier)
+    os.sched_setaffinity(0, affinity_before)
 
     if rank == 0:
         total_samples = main["samples_per_step"] * world
         value = total_samples / (main["ms_per_step"] * 1e-3) / 1e6
-        peak, peak_src = measured_peak()
         bps = algorithmic_bytes_per_sample(args.mode, args.audio_channels)
         if args.mixed:  # 2 B in + the PCM both halves write
             bps = 0.5 * (algorithmic_bytes_per_sample(args.mode, 1) + algorithmic_bytes_per_sample(args.mode, 2))
@@ -449,17 +630,19 @@ def run_ours(args):
             dom_ms = kt[dom][0] / kt[dom][1]
             alg_bytes = main["samples_per_step"] * bps  # per launch: one launch covers the whole batch
             achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-            traffic = None
-            try:  # measured DRAM bytes per launch of this kernel (ncu --set full), default workload only
+            traffic, traffic_src = None, None
+            try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture
                 tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
                 w = tj["workload"]
                 if (w["mode"], w["audio_channels"], w["batch_per_gpu"], w["blocks_per_capture"]) == \
                         (args.mode, args.audio_channels, args.batch, args.blocks) and dom in tj:
                     traffic = tj[dom]["dram_bytes_per_launch"]
+                    traffic_src = ("not measured in this run: " + tj[dom]["source"])
             except Exception:
                 pass
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
                         "kernel_share_of_step": kt[dom][0] / args.steps / step_kernel_ms,
                         "whole_step_frac": value * 1e6 * bps / 1e9 / peak / world,
@@ -478,10 +661,17 @@ def run_ours(args):
             "config": workload_config(args), "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
             "gpu_launches": main["launches"], "clocks": clocks, "pcm_checksum": main["checksum"],
         }
+        if main.get("parity"):
+            line["parity_checked"] = main["parity"]["parity_checked"]
+            line["parity"] = main["parity"]
         if main.get("rds"):
             line["rds"] = main["rds"]
         if others:
             line["other_configs"] = others
+            for k in ("stereo_mode0_fill", "stereo_mode0_1024"):   # stable top-level key for the stereo result
+                if k in others and "value" in others[k]:
+                    line["stereo"] = dict(others[k], config_key=k)
+                    break
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -499,7 +689,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="captures per GPU")
     ap.add_argument("--blocks", type=int, default=16, help="reference blocks per capture per step")
     ap.add_argument("--e2e-blocks", type=int, default=8)
-    ap.add_argument("--others", action="store_true", help="also time mono mode 0 / stereo configs")
+    ap.add_argument("--no-others", action="store_true",
+                    help="skip the short runs of the other BASELINE.json configs (other_configs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run PCM check against the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=1,
                     help="pipeline handles per GPU, each with batch/streams captures on its own CUDA stream")
@@ -507,8 +699,9 @@ def main():
                     help="half of the handles mono, half stereo (BASELINE configs[3]); needs --streams >= 2")
     ap.add_argument("--rds", action="store_true",
                     help="also run the RDS chain (modes 0/2) behind every step; not the default workload")
-    ap.add_argument("--variant", default="fast", choices=["fast", "exact"],
-                    help="fast: tensor-core RF front end (mono, +-1 LSB PCM); exact: bit-identical CUDA-core path")
+    ap.add_argument("--variant", default="fast", choices=["fast", "exact", "mixed"],
+                    help="fast: tensor-core RF front end (mono, +-1 LSB PCM); exact: bit-identical CUDA-core path; "
+                         "mixed: exact in front of the PLL, contracted multiply-adds elsewhere (+-1 LSB PCM)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.mixed and args.streams < 2:

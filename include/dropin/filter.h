@@ -14,6 +14,9 @@
  *   - convolveBlockFastFIR does not perform the reference's one-past-the-end
  *     iteration (src/filter.cpp:166), so it neither reads x[x.size()] nor writes
  *     y[x.size()/decim]; every in-range output is identical;
+ *   - a `state` vector whose size is not h.size()-1 (6 for fmPLL) throws
+ *     std::invalid_argument: the reference would index it by state.size() and treat
+ *     that as the tap count (filter.cpp:144,174,207); the C ABI below takes a bare pointer;
  *   - the device is picked by the SDR_B200_DEVICE environment variable (default 0).
  */
 #ifndef SDR_B200_DROPIN_FILTER_H

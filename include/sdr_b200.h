@@ -50,6 +50,12 @@ extern "C" {
  * intermediates agree to >= 100 dB SNR and PCM to +-1 LSB, not bit for bit.
  * Stereo is refused: the PLL amplifies 1-ulp differences beyond the parity bound. */
 #define SDR_VARIANT_FAST 1
+/* Mono or stereo.  Everything that feeds the stereo PLL -- RF front end, discriminator, pilot
+ * band-pass, the PLL itself -- keeps the reference's arithmetic bit for bit (so the NCO is the
+ * reference's NCO); the filters that do NOT feed it (22-54 kHz band-pass, both audio low-pass /
+ * resampling filters) contract each multiply-add into one FMA.  fm_demod, carrier_filt and the
+ * NCO are bit-identical, the other float intermediates agree to >= 100 dB and PCM to +-1 LSB. */
+#define SDR_VARIANT_MIXED 2
 
 /* Intermediate signals that sdr_pipeline_tap can return (same numbering as the
  * oracle, oracle/fm_oracle.h).  Names follow src/project.cpp's variables. */
@@ -189,6 +195,36 @@ int sdr_pipeline_kernel_times(sdr_pipeline *p, int index, char *name, size_t nam
                               double *total_ms, uint64_t *count, int reset);
 
 /* ------------------------------------------------------------------------ */
+/* One process, several devices.  Replaces the thread set-up of              */
+/* src/project.cpp:471-496 (one producer + one consumer around a queue) at    */
+/* the scale of a batch: `cfg.batch` captures are cut into contiguous ranges, */
+/* one per device, each driven by its own host thread through                 */
+/* sdr_pipeline_process_host.  Captures never interact, so there is no        */
+/* collective; every device writes its PCM rows straight into the caller's    */
+/* buffer (the final host gather).  Results are identical to one pipeline     */
+/* processing the whole batch.  cfg.device is ignored.                        */
+/* ------------------------------------------------------------------------ */
+typedef struct sdr_multi sdr_multi;
+typedef struct {
+  sdr_config cfg;     /* cfg.batch = captures over all devices */
+  int n_devices;      /* 0 = every usable sm_100 device; clipped to cfg.batch */
+  const int *devices; /* optional CUDA ordinals (n_devices entries); NULL = 0..n_devices-1 */
+} sdr_multi_config;
+
+int sdr_multi_create(const sdr_multi_config *cfg, sdr_multi **out);
+int sdr_multi_destroy(sdr_multi *m);
+int sdr_multi_reset(sdr_multi *m);
+/* Devices in use and the first capture of each device's range (up to `cap` entries each). */
+int sdr_multi_layout(const sdr_multi *m, int *n_devices, int *devices, int *first_capture, int cap);
+int sdr_multi_pcm_count(const sdr_multi *m, size_t nbytes_per_channel, size_t *n_pcm);
+int sdr_multi_launch_count(sdr_multi *m, uint64_t *count, int reset);
+/* iq [batch][iq_stride_bytes], pcm [batch][pcm_stride] in host memory (page-locked memory from
+ * sdr_host_alloc is copied from / to directly; pageable memory is staged by the worker threads).
+ * Returns when the whole batch's PCM is in `pcm`. */
+int sdr_multi_process_host(sdr_multi *m, const uint8_t *iq, size_t iq_stride_bytes,
+                           size_t nbytes_per_channel, int16_t *pcm, size_t pcm_stride);
+
+/* ------------------------------------------------------------------------ */
 /* RDS receiver chain (modes 0 and 2), attached to a batched pipeline.       */
 /* The reference has no C++ RDS path: these entry points replace the block    */
 /* loop of its Python model, model/fmRDS.py:222-276 (functions in             */
@@ -210,7 +246,13 @@ typedef struct {
   int cdr_carry;          /* 0: the CDR state is re-created for every block, as fmRDS.py:257-260 does;
                              1: it is carried from block to block (pair, start, prev_size:
                              fmSupportLib.py:104-106,178-189), so symbols are not dropped at block edges */
+  int pll_form;           /* which form of the 114 kHz PLL kernel runs: SDR_RDS_PLL_AUTO picks by batch
+                             size (a warp per capture up to 4096 captures, one lane per capture above);
+                             both give the same result to 1e-9 (tests) */
 } sdr_rds_config;
+#define SDR_RDS_PLL_AUTO 0
+#define SDR_RDS_PLL_LANE 1
+#define SDR_RDS_PLL_WARP 2
 
 typedef struct {
   int upsamp, decim;        /* fmRDS.py:57-58 / :69-70 */

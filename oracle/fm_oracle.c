@@ -34,7 +34,7 @@
 /*                  polynomial), in the x86_64 FMA ifunc variant that every */
 /*                  AVX2+FMA host selects; the fma() placement below is the */
 /*                  one found in that variant's machine code.               */
-/* tests/test_oracle_libm.py pins them against the host libm.               */
+/* tests/test_oracle.py pins them against the host libm.                    */
 /* ======================================================================== */
 
 static inline uint32_t f2u(float f) {

@@ -23,6 +23,7 @@ TAP_NAMES = ["i_filt", "q_filt", "demod", "allpass", "stereo_filt", "carrier_fil
 
 VARIANT_EXACT = 0
 VARIANT_FAST = 1
+VARIANT_MIXED = 2
 
 
 class SdrError(RuntimeError):
@@ -43,9 +44,13 @@ class ModeInfo(C.Structure):
                 ("block_bytes", C.c_int), ("granule_bytes", C.c_int), ("pcm_per_granule", C.c_int)]
 
 
+class MultiConfig(C.Structure):
+    _fields_ = [("cfg", Config), ("n_devices", C.c_int), ("devices", C.POINTER(C.c_int))]
+
+
 class RdsConfig(C.Structure):
     _fields_ = [("block_if", C.c_int), ("max_pending_blocks", C.c_int), ("keep_nco", C.c_int),
-                ("cdr_carry", C.c_int)]
+                ("cdr_carry", C.c_int), ("pll_form", C.c_int)]
 
 
 class RdsInfo(C.Structure):
@@ -96,6 +101,13 @@ ABI = {
     "sdr_pipeline_profile": (C.c_int, [_vp, C.c_int]),
     "sdr_pipeline_kernel_times": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_size_t,
                                             C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
+    "sdr_multi_create": (C.c_int, [C.POINTER(MultiConfig), C.POINTER(_vp)]),
+    "sdr_multi_destroy": (C.c_int, [_vp]),
+    "sdr_multi_reset": (C.c_int, [_vp]),
+    "sdr_multi_layout": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
+    "sdr_multi_pcm_count": (C.c_int, [_vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sdr_multi_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
+    "sdr_multi_process_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_size_t]),
     "sdr_rds_design": (C.c_int, [C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sdr_rds_create": (C.c_int, [_vp, C.POINTER(RdsConfig), C.POINTER(_vp)]),
     "sdr_rds_destroy": (C.c_int, [_vp]),
@@ -329,6 +341,76 @@ class Pipeline:
         return out
 
 
+class MultiPipeline:
+    """``batch`` captures spread over several GPUs by one process (sdr_multi_*): contiguous capture
+    ranges, one host thread per device, PCM gathered into one host array."""
+
+    def __init__(self, mode=0, channels=1, rf_taps=151, audio_taps=101, stereo_taps=151, batch=1,
+                 devices=None, variant=VARIANT_EXACT, max_bytes_per_channel=0):
+        cfg = Config(mode, channels, rf_taps, audio_taps, stereo_taps, batch, 0, variant,
+                     max_bytes_per_channel)
+        self.batch = batch
+        if devices is None:
+            mc = MultiConfig(cfg, 0, None)
+        elif isinstance(devices, int):
+            mc = MultiConfig(cfg, devices, None)
+        else:
+            self._devs = (C.c_int * len(devices))(*devices)
+            mc = MultiConfig(cfg, len(devices), self._devs)
+        self._h = _vp()
+        _check(lib().sdr_multi_create(C.byref(mc), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sdr_multi_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def layout(self):
+        """[(device, first capture), ...]"""
+        n = C.c_int(0)
+        devs, first = (C.c_int * 64)(), (C.c_int * 64)()
+        _check(lib().sdr_multi_layout(self._h, C.byref(n), devs, first, 64))
+        return [(devs[i], first[i]) for i in range(n.value)]
+
+    def reset(self):
+        _check(lib().sdr_multi_reset(self._h))
+
+    def pcm_count(self, nbytes: int) -> int:
+        n = C.c_size_t(0)
+        _check(lib().sdr_multi_pcm_count(self._h, nbytes, C.byref(n)))
+        return n.value
+
+    def launch_count(self, reset=False) -> int:
+        n = C.c_uint64(0)
+        _check(lib().sdr_multi_launch_count(self._h, C.byref(n), 1 if reset else 0))
+        return n.value
+
+    def process_host(self, iq: np.ndarray, pcm: np.ndarray | None = None) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, np.uint8)
+        assert iq.ndim == 2 and iq.shape[0] == self.batch, "iq must be [batch, nbytes]"
+        nbytes = iq.shape[1]
+        if pcm is None:
+            pcm = np.zeros((self.batch, self.pcm_count(nbytes)), np.int16)
+        _check(lib().sdr_multi_process_host(self._h, iq.ctypes.data, iq.strides[0], nbytes,
+                                            pcm.ctypes.data, pcm.strides[0] // 2))
+        return pcm
+
+    def process_host_ptr(self, iq_ptr: int, iq_stride: int, nbytes: int, pcm_ptr: int, pcm_stride: int):
+        _check(lib().sdr_multi_process_host(self._h, iq_ptr, iq_stride, nbytes, pcm_ptr, pcm_stride))
+
+
 # ---- RDS chain (model/fmRDS.py:222-276) ----------------------------------------------------------
 def rds_design(which: str, mode: int) -> np.ndarray:
     """The model's coefficient sets: 'channel', 'carrier', 'resampler', 'rrc' (float64)."""
@@ -345,10 +427,11 @@ class Rds:
     process call of that pipeline, on the same stream."""
 
     def __init__(self, pipeline: Pipeline, block_if=0, max_pending_blocks=0, keep_nco=False,
-                 cdr_carry=False):
+                 cdr_carry=False, pll_form="auto"):
         self.pipeline = pipeline
         self._h = _vp()
-        cfg = RdsConfig(block_if, max_pending_blocks, 1 if keep_nco else 0, 1 if cdr_carry else 0)
+        cfg = RdsConfig(block_if, max_pending_blocks, 1 if keep_nco else 0, 1 if cdr_carry else 0,
+                        {"auto": 0, "lane": 1, "warp": 2}[pll_form])
         _check(lib().sdr_rds_create(pipeline._h, C.byref(cfg), C.byref(self._h)))
         self.info = RdsInfo()
         _check(lib().sdr_rds_info(self._h, C.byref(self.info)))

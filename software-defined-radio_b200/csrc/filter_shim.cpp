@@ -30,6 +30,16 @@ auto ptr(V &v) -> decltype(v.data()) {
   return v.empty() ? dummy : v.data();
 }
 
+// The C ABI takes the state as a bare pointer whose length is implied by the tap count
+// (nh-1 floats; the zero-stuffed nh-1 for the resampler; 6 for the PLL).  The reference
+// indexes by state.size() instead (filter.cpp:144,174,207), so a vector of another size would
+// be read and written out of bounds below the ABI: refuse it here.
+void need_state(const std::vector<float> &state, size_t want, const char *what) {
+  if (state.size() != want)
+    throw std::invalid_argument(std::string(what) + ": state must hold " + std::to_string(want) +
+                                " floats (got " + std::to_string(state.size()) + ")");
+}
+
 }  // namespace
 
 void impulseResponseLPF(float Fs, float Fc, unsigned short int num_taps, std::vector<float> &h) {
@@ -52,6 +62,7 @@ void convolveBlockFIR(std::vector<float> &y, const std::vector<float> &x,
                       const std::vector<float> &h, std::vector<float> &state) {
   y.assign(x.size(), 0.0f);
   if (x.empty()) return;
+  need_state(state, h.empty() ? 0 : h.size() - 1, "convolveBlockFIR");
   must(sdr_fir_block(device(), y.data(), x.data(), x.size(), h.data(), h.size(), ptr(state)),
        "convolveBlockFIR");
 }
@@ -61,6 +72,7 @@ void convolveBlockFastFIR(std::vector<float> &y, const std::vector<float> &x,
                           const unsigned int decim, const bool) {
   y.assign(x.size() / decim, 0.0f);
   if (x.empty()) return;
+  need_state(state, h.empty() ? 0 : h.size() - 1, "convolveBlockFastFIR");
   must(sdr_fir_decim(device(), ptr(y), x.data(), x.size(), h.data(), h.size(), ptr(state), decim),
        "convolveBlockFastFIR");
 }
@@ -70,6 +82,7 @@ void convolveBlockResampleFIR(std::vector<float> &y, const std::vector<float> &x
                               const unsigned int audio_decim, const unsigned int audio_upsamp, bool) {
   y.assign((x.size() * audio_upsamp) / audio_decim, 0.0f);
   if (x.empty()) return;
+  need_state(state, h.empty() ? 0 : h.size() - 1, "convolveBlockResampleFIR");
   must(sdr_fir_resample(device(), ptr(y), x.data(), x.size(), h.data(), h.size(), ptr(state),
                         audio_decim, audio_upsamp),
        "convolveBlockResampleFIR");
@@ -99,6 +112,7 @@ void fmDemod(std::vector<float> &fm_demod, const std::vector<float> &I, const st
 void fmPLL(const std::vector<float> &PLLIn, std::vector<float> &ncoOut, std::vector<float> &state,
            float freq, float Fs, float ncoScale, float phaseAdjust, float normBandwidth) {
   ncoOut.assign(PLLIn.size() + 1, 0.0f);
+  need_state(state, 6, "fmPLL");
   must(sdr_pll(device(), ptr(PLLIn), PLLIn.size(), ncoOut.data(), state.data(), freq, Fs, ncoScale,
                phaseAdjust, normBandwidth),
        "fmPLL");

@@ -150,7 +150,9 @@ __device__ __forceinline__ void fir_groups(const float *__restrict__ w,
 
 // Two filters over the same input window (the stereo and pilot band-pass filters read
 // the same demodulated samples): identical walk, two tap sets, two accumulator sets.
-template <int T, int D, int R>
+// FMA_A = true contracts the multiply-adds of filter A only (SDR_VARIANT_MIXED: the stereo band
+// does not feed the PLL); filter B stays in the reference's two-rounding form.
+template <int T, int D, int R, bool FMA_A = false>
 __device__ __forceinline__ void fir_groups2(const float *__restrict__ w,
                                             const TapArray<taps_groups(T, D, R)> &taps_a,
                                             const TapArray<taps_groups(T, D, R)> &taps_b,
@@ -196,7 +198,8 @@ __device__ __forceinline__ void fir_groups2(const float *__restrict__ w,
       for (int j = 0; j < D; ++j)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          acc_a[r] = xmac(acc_a[r], ha[D * c + j], xb[(r - c + R) % R][j]);
+          acc_a[r] = FMA_A ? __fmaf_rn(ha[D * c + j], xb[(r - c + R) % R][j], acc_a[r])
+                           : xmac(acc_a[r], ha[D * c + j], xb[(r - c + R) % R][j]);
           acc_b[r] = xmac(acc_b[r], hb[D * c + j], xb[(r - c + R) % R][j]);
         }
     }
@@ -608,53 +611,21 @@ struct ResampleArgs {
   int U, D, TA;
 };
 
-template <bool STEREO>
-static __global__ void k_audio_resample(const ResampleArgs g) {
-  const AudioArgs &a = g.a;
-  const int b = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.n_out) return;
-  const long long m = (long long)j * g.D;
-  const int p = (int)(m % g.U);
-  const long long i0 = m / g.U;
-  const float *hp = g.hp + (size_t)p * g.TA;
-  const float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off - a.delay + i0;
-  float am = 0.0f, as = 0.0f;
-  if (STEREO) {
-    const float *srow = a.stf + (size_t)b * a.stf_stride + a.hist_off + i0;
-    const float *nrow = a.nco + (size_t)b * a.nco_stride + a.hist_off + i0;
-    for (int k = 0; k < g.TA; ++k) {
-      const float h = __ldg(hp + k);
-      am = xmac(am, h, drow[-k]);
-      as = xmac(as, h, xmul(xmul(srow[-k], nrow[-k]), 2.0f));
-    }
-    const float fu = (float)g.U;
-    am = xadd(am, xmul(am, fu));
-    as = xadd(as, xmul(as, fu));
-    const float L = xadd(as, am), R = xsub(am, as);
-    int16_t *q = a.pcm + (size_t)b * a.pcm_stride + 2 * (size_t)j;
-    q[0] = pcm16(L);
-    q[1] = pcm16(R);
-    if (a.stereo_final) a.stereo_final[(size_t)b * a.tap_stride + j] = as;
-  } else {
-    for (int k = 0; k < g.TA; ++k) am = xmac(am, __ldg(hp + k), drow[-k]);
-    am = xadd(am, xmul(am, (float)g.U));
-    a.pcm[(size_t)b * a.pcm_stride + j] = pcm16(am);
-  }
-  if (a.audio_filt) a.audio_filt[(size_t)b * a.tap_stride + j] = am;
-}
-
 // K6r, throughput form: one LANE per capture.  Consecutive outputs of one capture use
 // different polyphase rows and input offsets that are not multiples of anything useful,
 // so with lanes along time every shared-memory access conflicts.  With 32 captures across
 // the lanes instead, the tap is the same for the whole warp (one broadcast LDS.128 brings
 // four taps) and the 32 inputs x[c][i] sit in 32 different banks of a transposed tile.
 // CTA = 32 captures x RS_J outputs; warp w computes outputs w, w+NW, ... of the tile.
+template <bool FMA>
+__device__ __forceinline__ float rs_mac(float acc, float h, float x) {
+  return FMA ? __fmaf_rn(h, x, acc) : xmac(acc, h, x);
+}
 constexpr int RS_J = 32;    // outputs per tile
 constexpr int RS_NW = 8;    // warps per CTA
 constexpr int RS_PITCH = 33;
 
-template <bool STEREO>
+template <bool STEREO, bool FMA = false>
 static __global__ void __launch_bounds__(RS_NW * 32)
 k_audio_resample_v2(const ResampleArgs g, int batch, int rows_cap) {
   const AudioArgs &a = g.a;
@@ -716,20 +687,20 @@ k_audio_resample_v2(const ResampleArgs g, int batch, int rows_cap) {
     int k = 0;
     for (; k + 4 <= g.TA; k += 4) {
       const float4 hv = *reinterpret_cast<const float4 *>(h + k);
-      am = xmac(am, hv.x, x[-(k + 0) * RS_PITCH]);
-      am = xmac(am, hv.y, x[-(k + 1) * RS_PITCH]);
-      am = xmac(am, hv.z, x[-(k + 2) * RS_PITCH]);
-      am = xmac(am, hv.w, x[-(k + 3) * RS_PITCH]);
+      am = rs_mac<FMA>(am, hv.x, x[-(k + 0) * RS_PITCH]);
+      am = rs_mac<FMA>(am, hv.y, x[-(k + 1) * RS_PITCH]);
+      am = rs_mac<FMA>(am, hv.z, x[-(k + 2) * RS_PITCH]);
+      am = rs_mac<FMA>(am, hv.w, x[-(k + 3) * RS_PITCH]);
       if (STEREO) {
-        as = xmac(as, hv.x, x2[-(k + 0) * RS_PITCH]);
-        as = xmac(as, hv.y, x2[-(k + 1) * RS_PITCH]);
-        as = xmac(as, hv.z, x2[-(k + 2) * RS_PITCH]);
-        as = xmac(as, hv.w, x2[-(k + 3) * RS_PITCH]);
+        as = rs_mac<FMA>(as, hv.x, x2[-(k + 0) * RS_PITCH]);
+        as = rs_mac<FMA>(as, hv.y, x2[-(k + 1) * RS_PITCH]);
+        as = rs_mac<FMA>(as, hv.z, x2[-(k + 2) * RS_PITCH]);
+        as = rs_mac<FMA>(as, hv.w, x2[-(k + 3) * RS_PITCH]);
       }
     }
     for (; k < g.TA; ++k) {
-      am = xmac(am, h[k], x[-k * RS_PITCH]);
-      if (STEREO) as = xmac(as, h[k], x2[-k * RS_PITCH]);
+      am = rs_mac<FMA>(am, h[k], x[-k * RS_PITCH]);
+      if (STEREO) as = rs_mac<FMA>(as, h[k], x2[-k * RS_PITCH]);
     }
     am = xadd(am, xmul(am, fu));  // filter.cpp:213
     if (STEREO) as = xadd(as, xmul(as, fu));
@@ -756,137 +727,13 @@ k_audio_resample_v2(const ResampleArgs g, int batch, int rows_cap) {
   }
 }
 
-// Same kernel with the per-phase tap count known at compile time (101 functional, 13 as shipped):
-// the tap loop is straight-line code with immediate shared-memory offsets, each warp works on two
-// outputs at a time (two independent accumulator chains), and the staging loops carry no
-// multiplications or 64-bit index arithmetic.
-template <bool STEREO, int TA>
-static __global__ void __launch_bounds__(RS_NW * 32)
-k_audio_resample_v3(const ResampleArgs g, int batch, int rows_cap) {
-  const AudioArgs &a = g.a;
-  constexpr int TA4 = (TA + 3) & ~3;
-  constexpr int PER = STEREO ? 2 : 1;
-  constexpr int PSP = RS_J * PER + 2;                // padded PCM row (int16) -> fewer bank conflicts
-  extern __shared__ __align__(16) float smem[];
-  float *hs = smem;                                  // [RS_J][TA4]
-  float *xs = hs + RS_J * TA4;                       // [rows_cap][33]
-  float *xs2 = xs + (size_t)rows_cap * RS_PITCH;
-  int16_t *ps = reinterpret_cast<int16_t *>(xs + (size_t)rows_cap * RS_PITCH * PER);
-  __shared__ int s_phase[RS_J], s_top[RS_J];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j0 = blockIdx.x * RS_J;
-  const int jn = min(RS_J, a.n_out - j0);
-  const int c0 = blockIdx.y * 32;
-  const unsigned U = (unsigned)g.U, D = (unsigned)g.D;
-  const int i_lo = (int)(((unsigned)j0 * D) / U) - (TA - 1);
-  const int i_hi = (int)(((unsigned)(j0 + jn - 1) * D) / U);
-  const int rows = i_hi - i_lo + 1;
-  if (threadIdx.x < RS_J) {
-    const unsigned m = (unsigned)(j0 + threadIdx.x) * D;
-    const unsigned q = m / U;
-    s_phase[threadIdx.x] = (int)(m - q * U);
-    s_top[threadIdx.x] = (threadIdx.x < jn) ? (int)q - i_lo : TA - 1;  // padded outputs read valid rows
-  }
-  // ---- transposed input tile: warp w streams the rows of captures w, w+8, ... ----
-#pragma unroll
-  for (int cc = 0; cc < 32 / RS_NW; ++cc) {
-    const int c = warp + cc * RS_NW;
-    const int ch = min(c0 + c, batch - 1);           // lanes past the batch re-read the last capture
-    const float *drow = a.demod + (size_t)ch * a.demod_stride + (a.demod_off - a.delay + i_lo);
-    float *dst = xs + c + lane * RS_PITCH;
-    if (STEREO) {
-      const float *srow = a.stf + (size_t)ch * a.stf_stride + (a.hist_off + i_lo);
-      const float *nrow = a.nco + (size_t)ch * a.nco_stride + (a.hist_off + i_lo);
-      float *dst2 = xs2 + c + lane * RS_PITCH;
-      for (int i = lane; i < rows; i += 32, dst += 32 * RS_PITCH, dst2 += 32 * RS_PITCH) {
-        *dst = drow[i];
-        *dst2 = xmul(xmul(srow[i], nrow[i]), 2.0f);
-      }
-    } else {
-      int i = lane;
-      for (; i + 96 < rows; i += 128, dst += 128 * RS_PITCH) {  // four loads in flight
-        const float v0 = drow[i], v1 = drow[i + 32], v2 = drow[i + 64], v3 = drow[i + 96];
-        dst[0] = v0; dst[32 * RS_PITCH] = v1; dst[64 * RS_PITCH] = v2; dst[96 * RS_PITCH] = v3;
-      }
-      for (; i < rows; i += 32, dst += 32 * RS_PITCH) *dst = drow[i];
-    }
-  }
-  __syncthreads();   // s_phase visible
-  // ---- taps of the tile's phases (zero padded to TA4) ----
-  for (int jj = warp; jj < RS_J; jj += RS_NW) {
-    const float *src = g.hp + (size_t)s_phase[jj] * TA;
-#pragma unroll
-    for (int k0 = 0; k0 < TA4; k0 += 32) {
-      const int k = k0 + lane;
-      if (k < TA4) hs[jj * TA4 + k] = (k < TA) ? __ldg(src + k) : 0.0f;
-    }
-  }
-  __syncthreads();
-  const float fu = (float)g.U;
-  // ---- each warp: outputs (jj, jj + RS_NW) together, 32 captures across the lanes ----
-  for (int jj = warp; jj < RS_J; jj += 2 * RS_NW) {
-    const int jb = jj + RS_NW;
-    const float *ha = hs + jj * TA4, *hb = hs + jb * TA4;
-    const float *xa = xs + s_top[jj] * RS_PITCH + lane, *xb = xs + s_top[jb] * RS_PITCH + lane;
-    const float *ya = xs2 + s_top[jj] * RS_PITCH + lane, *yb = xs2 + s_top[jb] * RS_PITCH + lane;
-    float ma = 0.0f, mb = 0.0f, sa = 0.0f, sb = 0.0f;
-#pragma unroll
-    for (int k = 0; k < TA4; k += 4) {
-      const float4 va = *reinterpret_cast<const float4 *>(ha + k);
-      const float4 vb = *reinterpret_cast<const float4 *>(hb + k);
-      const float ta[4] = {va.x, va.y, va.z, va.w}, tb[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (k + u < TA) {
-          ma = xmac(ma, ta[u], xa[-(k + u) * RS_PITCH]);
-          mb = xmac(mb, tb[u], xb[-(k + u) * RS_PITCH]);
-          if (STEREO) {
-            sa = xmac(sa, ta[u], ya[-(k + u) * RS_PITCH]);
-            sb = xmac(sb, tb[u], yb[-(k + u) * RS_PITCH]);
-          }
-        }
-      }
-    }
-    ma = xadd(ma, xmul(ma, fu));  // filter.cpp:213
-    mb = xadd(mb, xmul(mb, fu));
-    if (STEREO) {
-      sa = xadd(sa, xmul(sa, fu));
-      sb = xadd(sb, xmul(sb, fu));
-      ps[lane * PSP + 2 * jj] = pcm16(xadd(sa, ma));
-      ps[lane * PSP + 2 * jj + 1] = pcm16(xsub(ma, sa));
-      ps[lane * PSP + 2 * jb] = pcm16(xadd(sb, mb));
-      ps[lane * PSP + 2 * jb + 1] = pcm16(xsub(mb, sb));
-    } else {
-      ps[lane * PSP + jj] = pcm16(ma);
-      ps[lane * PSP + jb] = pcm16(mb);
-    }
-    const int ch = c0 + lane;
-    if (ch < batch && a.audio_filt) {
-      if (jj < jn) a.audio_filt[(size_t)ch * a.tap_stride + j0 + jj] = ma;
-      if (jb < jn) a.audio_filt[(size_t)ch * a.tap_stride + j0 + jb] = mb;
-      if (STEREO && a.stereo_final) {
-        if (jj < jn) a.stereo_final[(size_t)ch * a.tap_stride + j0 + jj] = sa;
-        if (jb < jn) a.stereo_final[(size_t)ch * a.tap_stride + j0 + jb] = sb;
-      }
-    }
-  }
-  __syncthreads();
-  // ---- PCM rows out: one capture per warp pass, contiguous int16 along time ----
-  for (int c = warp; c < 32; c += RS_NW) {
-    const int ch = c0 + c;
-    if (ch >= batch) continue;
-    int16_t *dst = a.pcm + (size_t)ch * a.pcm_stride + (size_t)j0 * PER;
-    for (int q = lane; q < jn * PER; q += 32) dst[q] = ps[c * PSP + q];
-  }
-}
-
-// Pair form (the default): v3 sits at 79 % of the shared-memory wavefront peak (profiles/r1f) because
-// every multiply-add reads its own input word.  Two CONSECUTIVE outputs use input windows that are
+// Pair form (stereo, 101 taps per phase): the generic form above sits at 79 % of the shared-memory
+// wavefront peak (profiles/r1f) because every multiply-add reads its own input word.  Two CONSECUTIVE outputs use input windows that are
 // only DU0 or DU0+1 = floor(D/U) (+1) rows apart, so a warp that computes them together loads each
 // input row once and feeds both accumulators: 0.79 instead of 1.25 shared-memory wavefronts per
 // multiply-add.  The row walk is unrolled for both possible offsets (a warp-uniform branch picks
 // one); every accumulator still sees its taps in ascending order.
-template <bool STEREO, int TA, int DELTA>
+template <bool STEREO, int TA, int DELTA, bool FMA>
 __device__ __forceinline__ void rs_pair(const float *__restrict__ ha, const float *__restrict__ hb,
                                         const float *__restrict__ xtop, const float *__restrict__ ytop,
                                         float &ma, float &mb, float &sa, float &sb) {
@@ -901,18 +748,18 @@ __device__ __forceinline__ void rs_pair(const float *__restrict__ ha, const floa
     const float y = STEREO ? ytop[-kb * RS_PITCH] : 0.0f;
     if (kb < TA) {
       const float t = (kb & 3) == 0 ? vb.x : (kb & 3) == 1 ? vb.y : (kb & 3) == 2 ? vb.z : vb.w;
-      mb = xmac(mb, t, x);
-      if (STEREO) sb = xmac(sb, t, y);
+      mb = rs_mac<FMA>(mb, t, x);
+      if (STEREO) sb = rs_mac<FMA>(sb, t, y);
     }
     if (ka >= 0 && ka < TA) {
       const float t = (ka & 3) == 0 ? va.x : (ka & 3) == 1 ? va.y : (ka & 3) == 2 ? va.z : va.w;
-      ma = xmac(ma, t, x);
-      if (STEREO) sa = xmac(sa, t, y);
+      ma = rs_mac<FMA>(ma, t, x);
+      if (STEREO) sa = rs_mac<FMA>(sa, t, y);
     }
   }
 }
 
-template <bool STEREO, int TA, int DU0>
+template <bool STEREO, int TA, int DU0, bool FMA = false>
 static __global__ void __launch_bounds__(RS_NW * 32)
 k_audio_resample_v4(const ResampleArgs g, int batch, int rows_cap) {
   const AudioArgs &a = g.a;
@@ -982,8 +829,8 @@ k_audio_resample_v4(const ResampleArgs g, int batch, int rows_cap) {
     const int top_b = s_top[jb], delta = top_b - s_top[jj];
     const float *xtop = xs + top_b * RS_PITCH + lane, *ytop = xs2 + top_b * RS_PITCH + lane;
     float ma = 0.0f, mb = 0.0f, sa = 0.0f, sb = 0.0f;
-    if (delta == DU0) rs_pair<STEREO, TA, DU0>(ha, hb, xtop, ytop, ma, mb, sa, sb);
-    else rs_pair<STEREO, TA, DU0 + 1>(ha, hb, xtop, ytop, ma, mb, sa, sb);
+    if (delta == DU0) rs_pair<STEREO, TA, DU0, FMA>(ha, hb, xtop, ytop, ma, mb, sa, sb);
+    else rs_pair<STEREO, TA, DU0 + 1, FMA>(ha, hb, xtop, ytop, ma, mb, sa, sb);
     ma = xadd(ma, xmul(ma, fu));  // filter.cpp:213
     mb = xadd(mb, xmul(mb, fu));
     if (STEREO) {
@@ -1240,7 +1087,7 @@ struct BpfArgs {
   int outs_per_seg;
 };
 
-template <int T, int R, int NT>
+template <int T, int R, int NT, bool FMA_STEREO = false>
 __global__ void __launch_bounds__(NT)
 k_bpf_dual(const BpfArgs a, const __grid_constant__ TapArray<taps_groups(T, 1, R)> h_stereo,
            const __grid_constant__ TapArray<taps_groups(T, 1, R)> h_pilot) {
@@ -1265,7 +1112,7 @@ k_bpf_dual(const BpfArgs a, const __grid_constant__ TapArray<taps_groups(T, 1, R
     float as[R], ap[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) as[r] = ap[r] = 0.0f;
-    fir_groups2<T, 1, R>(xs + Geom::thread_base(t), h_stereo, h_pilot, as, ap);
+    fir_groups2<T, 1, R, FMA_STEREO>(xs + Geom::thread_base(t), h_stereo, h_pilot, as, ap);
     const int o = o0 + t * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -1301,9 +1148,12 @@ struct PllArgs {
   float freq, Fs, ncoScale, phaseAdjust, normBandwidth;
 };
 
-static __global__ void k_pll(const PllArgs a) {
-  // lanes past the batch shadow the last capture (same loads, same stores of the same values):
-  // the tile copies below are warp-collective
+constexpr int PLL_MAX_WARPS = 4;   // warps per block at large batches (each warp: 32 captures, own tiles)
+static __global__ void __launch_bounds__(32 * PLL_MAX_WARPS) k_pll(const PllArgs a) {
+  // lanes past the batch shadow the last capture (same loads, same stores of the same values, in
+  // lockstep with its owner): the tile copies below are warp-collective.  A whole warp past the
+  // batch has nothing to shadow.
+  if ((int)((blockIdx.x * blockDim.x + threadIdx.x) & ~31u) >= a.batch) return;
   const int b = min((int)(blockIdx.x * blockDim.x + threadIdx.x), a.batch - 1);
   // filter.cpp:35-39
   const float Kp = xmul(a.normBandwidth, 2.666f);
@@ -1317,7 +1167,8 @@ static __global__ void k_pll(const PllArgs a) {
   // Input: the warp copies tiles of 32 captures x 32 samples into shared memory with
   // asynchronous copies (32 coalesced 128-byte rows per tile, no register in between), one
   // tile ahead of the one being consumed, so no global-load latency meets the recurrence.
-  __shared__ float tile[2][32][33];
+  __shared__ float tiles[PLL_MAX_WARPS][2][32][33];
+  float (*tile)[32][33] = tiles[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int b_first = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
   auto fetch = [&](int buf, int k0) {

@@ -208,6 +208,10 @@ extern "C" int sdr_pll(int device, const float *in, size_t n, float *out, float 
   if (!in || !out || !state) return bad("null argument");
   int rc = select_device(device);
   if (rc) return rc;
+  if (n == 0) {  // empty PLLIn: ncoOut = {state[4]}, state unchanged (filter.cpp:41-46,73-79)
+    out[0] = state[4];
+    return SDR_OK;
+  }
   Tmp din, dout, dst;
   if ((rc = dalloc(din, n * 4)) || (rc = dalloc(dout, (n + 1) * 4)) || (rc = dalloc(dst, 8 * 4))) return rc;
   float st8[8] = {state[0], state[1], state[2], state[3], state[4], state[5], 0, 0};
@@ -218,7 +222,7 @@ extern "C" int sdr_pll(int device, const float *in, size_t n, float *out, float 
             freq, Fs, ncoScale, phaseAdjust, normBandwidth};
   k_pll<<<1, 32>>>(a);
   if ((rc = launch_ok("k_pll"))) return rc;
-  if (n) k_nco_cos<<<dim3(((unsigned)n + 1023) / 1024, 1), 256>>>(a);
+  k_nco_cos<<<dim3(((unsigned)n + 1023) / 1024, 1), 256>>>(a);
   if ((rc = launch_ok("k_nco_cos"))) return rc;
   SDR_CUDA(cudaMemcpy(out, dout.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
   SDR_CUDA(cudaMemcpy(st8, dst.p, sizeof st8, cudaMemcpyDeviceToHost));

@@ -106,6 +106,14 @@ struct sdr_pipeline {
   int HA;     // stf/nco history prefix
   int delay;  // all-pass delay (stereo), project.cpp:457
   int granule_bytes, if_per_granule, pcm_per_granule;
+  int base_granule_bytes, base_if_per_granule, base_pcm_per_granule;  // without a follower stage
+  // which audio kernel runs (decided once, at create): modes 0/1 specialised FIR or generic FIRs;
+  // modes 2/3 quad resampler (mono), pair resampler (stereo, 101 taps per phase) or the generic one
+  enum AudioKernel { AK_FIR, AK_FIR_GENERIC, AK_RS_QUAD, AK_RS_PAIR, AK_RS_GENERIC } audio_kernel = AK_FIR_GENERIC;
+  int rs_pitch = 0, rs_rows_cap = 0;   // tile geometry of the chosen resampler
+  size_t rs_smem = 0;
+  bool fma_aux = false;                // contract the multiply-adds that do not feed the PLL (FAST, MIXED)
+  int n_sm = 148;
   size_t cap_if, cap_audio;  // per-capture capacities of one call
   size_t demod_stride, stf_stride, nco_stride, car_stride, tap_if_stride, tap_audio_stride;
   bool rf_fast, audio_fast, bpf_fast;  // specialised kernels available for these tap counts
@@ -218,9 +226,8 @@ template <int T, int D, int R, int NT, bool MERGE, int ALGO = 0>
 static int launch_rf(sdr_pipeline *p, RfArgs a, cudaStream_t s) {
   using Cfg = RfCfg<T, D, R, NT, ALGO>;
   auto kern = k_rf_demod<T, D, R, NT, MERGE, ALGO>;
-  static std::once_flag once[16];
-  int dev = p->cfg.device;
-  std::call_once(once[dev & 15], [&] {
+  static std::once_flag once[16];   // raised once per device, not per launch
+  std::call_once(once[p->cfg.device & 15], [&] {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   });
   int segs = pick_segments(a.n_if, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
@@ -228,16 +235,6 @@ static int launch_rf(sdr_pipeline *p, RfArgs a, cudaStream_t s) {
   prof_begin(p, "k_rf_demod", s);
   kern<<<grid, NT, Cfg::SMEM, s>>>(a, make_taps<Cfg::NTAPS>(p->h_rf));
   return check_launch(p, "k_rf_demod");
-}
-
-// Tuning knob for experiments (profiles/): SDR_RF_VARIANT selects the tile shape of the
-// 151-tap, decimate-by-10 front end.  Every variant produces identical bits.
-static int rf_variant() {
-  static const int v = [] {
-    const char *e = std::getenv("SDR_RF_VARIANT");
-    return e ? std::atoi(e) : -1;
-  }();
-  return v;
 }
 
 static bool rf_fast_available(int T, int D) {
@@ -256,12 +253,8 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     // Long segments first (a segment start costs an extra barrier and the integer predecessor),
     // a few short ones at the end of every capture so that the last items handed out are small.
     const int n_tiles = (a.n_if + TC_TILE_OUT - 1) / TC_TILE_OUT;
-    int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->cfg.device);
-    const int n_cta = 2 * n_sm;
-    static const int items_per_cta = std::getenv("SDR_TC_ITEMS") ? std::atoi(std::getenv("SDR_TC_ITEMS")) : 6;
-    static const int tail_tiles = std::getenv("SDR_TC_TAIL") ? std::atoi(std::getenv("SDR_TC_TAIL")) : 8;
-    static const int small_tiles = std::getenv("SDR_TC_SMALL") ? std::atoi(std::getenv("SDR_TC_SMALL")) : 4;
+    const int n_cta = 2 * p->n_sm;
+    constexpr int items_per_cta = 6, tail_tiles = 8, small_tiles = 4;   // measured on the bench workload
     const int tail = n_tiles >= 4 * tail_tiles ? tail_tiles : 0;          // tiles covered by short segments
     const int n_small = tail ? (tail + small_tiles - 1) / small_tiles : 0;
     const int head = n_tiles - tail;
@@ -273,12 +266,6 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     for (int t = head; t < n_tiles; t += small_tiles) g.seg_begin[g.segs++] = t;
     g.seg_begin[g.segs] = n_tiles;
     g.batch = p->cfg.batch;
-    static std::once_flag once[16];
-    std::call_once(once[p->cfg.device & 15], [&] {
-      cudaFuncSetAttribute(k_rf_demod_tc<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<10>::SMEM);
-      cudaFuncSetAttribute(k_rf_demod_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<5>::SMEM);
-      cudaFuncSetAttribute(k_rf_demod_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<3>::SMEM);
-    });
     dim3 grid(std::min(n_cta, g.segs * g.batch));
     g.next_item = p->tc_next_item.p;
     if (!p->tc_counter_armed &&   // first call, or the previous call failed before its k_carry
@@ -292,23 +279,8 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
     return check_launch(p, "k_rf_demod_tc");
   }
   if (p->rf_fast) {
-    if (T == 151 && D == 10) {
-      switch (rf_variant()) {
-        case 0: return launch_rf<151, 10, 6, 128, false>(p, a, s);
-        case 1: return launch_rf<151, 10, 6, 128, true>(p, a, s);
-        case 2: return launch_rf<151, 10, 6, 64, true>(p, a, s);
-        case 3: return launch_rf<151, 10, 4, 128, true>(p, a, s);
-        case 4: return launch_rf<151, 10, 4, 64, true>(p, a, s);
-        case 5: return launch_rf<151, 10, 2, 128, true>(p, a, s);
-        case 10: return launch_rf<151, 10, 4, 128, true, 1>(p, a, s);
-        case 11: return launch_rf<151, 10, 4, 64, true, 1>(p, a, s);
-        case 12: return launch_rf<151, 10, 8, 64, true, 1>(p, a, s);
-        case 13: return launch_rf<151, 10, 8, 128, true, 1>(p, a, s);
-        case 14: return launch_rf<151, 10, 4, 128, false, 1>(p, a, s);
-        case 15: return launch_rf<151, 10, 4, 256, true, 1>(p, a, s);
-        default: return launch_rf<151, 10, 2, 128, true>(p, a, s);
-      }
-    }
+    // tile shapes from the sweep in DESIGN.md section 4 (two outputs per thread, one merged I/Q loop)
+    if (T == 151 && D == 10) return launch_rf<151, 10, 2, 128, true>(p, a, s);
     if (T == 151 && D == 5) return launch_rf<151, 5, 4, 128, true>(p, a, s);
     if (T == 151 && D == 3) return launch_rf<151, 3, 4, 128, true>(p, a, s);
     if (T == 13 && D == 10) return launch_rf<13, 10, 6, 128, false>(p, a, s);
@@ -337,10 +309,13 @@ static int launch_audio(sdr_pipeline *p, AudioArgs a, cudaStream_t s) {
   constexpr int NT = 128;
   using Cfg = AudioCfg<T, D, R, NT>;
   constexpr size_t SMEM = (size_t)Cfg::ROW * (STEREO ? 2 : 1) * sizeof(float);
-  // the fast variant (mono only) contracts the multiply-adds
-  const bool fma = !STEREO && p->cfg.variant == SDR_VARIANT_FAST;
-  auto kern = fma ? k_audio_fir<T, D, R, NT, STEREO, !STEREO> : k_audio_fir<T, D, R, NT, STEREO, false>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  // FAST / MIXED contract the multiply-adds (the audio filters do not feed the PLL)
+  auto kern = p->fma_aux ? k_audio_fir<T, D, R, NT, STEREO, true> : k_audio_fir<T, D, R, NT, STEREO, false>;
+  static std::once_flag once[16];   // raised once per device, not per launch
+  std::call_once(once[p->cfg.device & 15], [&] {
+    cudaFuncSetAttribute(k_audio_fir<T, D, R, NT, STEREO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    cudaFuncSetAttribute(k_audio_fir<T, D, R, NT, STEREO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  });
   int segs = pick_segments(a.n_out, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
   prof_begin(p, "k_audio_fir", s);
@@ -367,8 +342,11 @@ static int launch_bpf(sdr_pipeline *p, BpfArgs a, cudaStream_t s) {
   int segs = pick_segments(a.n_if, NT * R, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
   prof_begin(p, "k_bpf_dual", s);
-  k_bpf_dual<T, R, NT><<<grid, NT, 0, s>>>(a, make_taps<taps_groups(T, 1, R)>(p->h_stereo),
-                                           make_taps<taps_groups(T, 1, R)>(p->h_pilot));
+  // MIXED: the 22-54 kHz band only reaches the mixer, so its multiply-adds may be contracted; the
+  // pilot band feeds the PLL and keeps the reference's two roundings
+  auto kern = p->fma_aux ? k_bpf_dual<T, R, NT, true> : k_bpf_dual<T, R, NT, false>;
+  kern<<<grid, NT, 0, s>>>(a, make_taps<taps_groups(T, 1, R)>(p->h_stereo),
+                           make_taps<taps_groups(T, 1, R)>(p->h_pilot));
   return check_launch(p, "k_bpf_dual");
 }
 
@@ -477,6 +455,10 @@ int sdr::pipeline_view(sdr_pipeline *p, DemodView *v) {
 int sdr::pipeline_set_hook(sdr_pipeline *p, PipelineHook fn, void *ctx, int granule_bytes) {
   if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
   if (fn && p->hook && p->hook_ctx != ctx) return fail(SDR_ERR_INVALID, "pipeline already has a follower stage");
+  // the granule is recomputed from the pipeline's own on every attach and detach
+  p->granule_bytes = p->base_granule_bytes;
+  p->if_per_granule = p->base_if_per_granule;
+  p->pcm_per_granule = p->base_pcm_per_granule;
   if (fn && granule_bytes > 0) {
     long long a = p->granule_bytes, b = granule_bytes;
     while (b) { const long long t = a % b; a = b; b = t; }
@@ -518,7 +500,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   if (cfg->rf_taps < 2 || cfg->rf_taps > 1024 || cfg->audio_taps < 2 || cfg->audio_taps > 1024 ||
       cfg->stereo_taps < 3 || cfg->stereo_taps > 1024)
     return fail(SDR_ERR_INVALID, "tap counts out of range");
-  if (cfg->variant != SDR_VARIANT_EXACT && cfg->variant != SDR_VARIANT_FAST)
+  if (cfg->variant != SDR_VARIANT_EXACT && cfg->variant != SDR_VARIANT_FAST && cfg->variant != SDR_VARIANT_MIXED)
     return fail(SDR_ERR_INVALID, "unknown variant");
   const ModeRow &m = kModes[cfg->mode];
   if (cfg->variant == SDR_VARIANT_FAST) {
@@ -546,9 +528,11 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   p->HD = round_up(std::max(p->stereo ? cfg->stereo_taps - 1 : 0, p->TA - 1 + p->delay), 8);  // 32-byte aligned sample 0
   sdr_mode_info mi;
   sdr_mode_lookup(cfg->mode, cfg->channels, &mi);
-  p->granule_bytes = mi.granule_bytes;
-  p->if_per_granule = mi.granule_bytes / 2 / m.rf_decim;
-  p->pcm_per_granule = mi.pcm_per_granule;
+  p->granule_bytes = p->base_granule_bytes = mi.granule_bytes;
+  p->if_per_granule = p->base_if_per_granule = mi.granule_bytes / 2 / m.rf_decim;
+  p->pcm_per_granule = p->base_pcm_per_granule = mi.pcm_per_granule;
+  p->fma_aux = cfg->variant != SDR_VARIANT_EXACT;
+  cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
   uint64_t cap_bytes = cfg->max_bytes_per_channel ? cfg->max_bytes_per_channel : (uint64_t)m.block_bytes;
   cap_bytes = (cap_bytes + mi.granule_bytes - 1) / mi.granule_bytes * mi.granule_bytes;
   p->cap_if = cap_bytes / 2 / m.rf_decim;
@@ -560,6 +544,62 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   p->rf_fast = rf_fast_available(cfg->rf_taps, m.rf_decim);
   p->audio_fast = !p->resample && audio_fast_available(p->TA, m.audio_decim);
   p->bpf_fast = cfg->stereo_taps == 151 || cfg->stereo_taps == 13;
+  // ---- kernels are chosen, and their shared-memory limits raised, once per handle ----
+  constexpr size_t kSmemCap = 200 * 1024;
+  if (!p->resample) {
+    p->audio_kernel = p->audio_fast ? sdr_pipeline::AK_FIR : sdr_pipeline::AK_FIR_GENERIC;
+  } else {
+    const int U = m.audio_upsamp, D = m.audio_decim;
+    // quad form (mono): rows of a tile = inputs spanned by RQ_J outputs + the table (KB + 4 rows) + alignment slack
+    const int KB = round_up(p->TA + (U - 1 + 3 * D) / U, 4);
+    int pitch = round_up((int)(((long long)(RQ_J - 1) * D) / U) + KB + 4 + 8, 4);
+    if ((pitch / 4) % 2 == 0) pitch += 4;  // pitch/4 odd: conflict-free LDS.128 across lanes
+    const size_t quad_smem = ((size_t)8 * (KB + 4) * 4 + (size_t)64 * pitch) * sizeof(float) +
+                             (size_t)64 * (RQ_J + 2) * sizeof(int16_t);
+    // pair / generic forms: rows of the transposed tile = inputs spanned by RS_J outputs + the filter history
+    const int rows_cap = (int)(((long long)RS_J * D) / U) + p->TA + 2;
+    const int TA4 = (p->TA + 3) & ~3;
+    const size_t gen_smem = ((size_t)RS_J * TA4 + (size_t)rows_cap * RS_PITCH * (p->stereo ? 2 : 1)) * sizeof(float) +
+                            (size_t)32 * RS_J * (p->stereo ? 2 : 1) * sizeof(int16_t);
+    const int du0 = D / U;   // rows between consecutive outputs (floor)
+    if (!p->stereo && quad_smem <= kSmemCap) {
+      p->audio_kernel = sdr_pipeline::AK_RS_QUAD;
+      p->rs_pitch = pitch;
+      p->rs_smem = quad_smem;
+    } else if (p->stereo && p->TA == 101 && (du0 == 5 || du0 == 7) && gen_smem + 128 <= kSmemCap) {
+      p->audio_kernel = sdr_pipeline::AK_RS_PAIR;
+      p->rs_rows_cap = rows_cap;
+      p->rs_smem = gen_smem + 32 * 2 * sizeof(int16_t);   // padded PCM rows
+    } else if (gen_smem <= kSmemCap) {
+      p->audio_kernel = sdr_pipeline::AK_RS_GENERIC;
+      p->rs_rows_cap = rows_cap;
+      p->rs_smem = gen_smem;
+    } else {
+      delete p;
+      return fail(SDR_ERR_INVALID, "audio_taps too large for this mode: no resampler tile fits in shared memory");
+    }
+  }
+  {
+    const int big = (int)kSmemCap;
+    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaFuncSetAttribute(k_rf_demod_tc<10>, at, (int)TcCfg<10>::SMEM);
+    cudaFuncSetAttribute(k_rf_demod_tc<5>, at, (int)TcCfg<5>::SMEM);
+    cudaFuncSetAttribute(k_rf_demod_tc<3>, at, (int)TcCfg<3>::SMEM);
+    cudaFuncSetAttribute(k_audio_resample_v5<true, 2>, at, big);
+    cudaFuncSetAttribute(k_audio_resample_v5<false, 2>, at, big);
+    cudaFuncSetAttribute(k_audio_resample_v4<true, 101, 5, true>, at, big);
+    cudaFuncSetAttribute(k_audio_resample_v4<true, 101, 5, false>, at, big);
+    cudaFuncSetAttribute(k_audio_resample_v4<true, 101, 7, true>, at, big);
+    cudaFuncSetAttribute(k_audio_resample_v4<true, 101, 7, false>, at, big);
+    cudaFuncSetAttribute(k_audio_resample_v2<true, true>, at, big);
+    cudaFuncSetAttribute(k_audio_resample_v2<true, false>, at, big);
+    cudaFuncSetAttribute(k_audio_resample_v2<false, true>, at, big);
+    cudaFuncSetAttribute(k_audio_resample_v2<false, false>, at, big);
+    if (cudaGetLastError() != cudaSuccess) {
+      delete p;
+      return fail(SDR_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+    }
+  }
 
   // ---- filter design (host, same arithmetic as the reference; design.cpp) ----
   p->h_rf.resize(cfg->rf_taps);
@@ -885,7 +925,10 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
     pa.phaseAdjust = (float)0.0;
     pa.normBandwidth = (float)0.01;
     prof_begin(p, "k_pll", s);
-    k_pll<<<(B + 31) / 32, 32, 0, s>>>(pa);
+    // one lane per capture; up to one warp per scheduler the warps are spread over the SMs (one-warp
+    // blocks), beyond that four warps share a block
+    const int pll_threads = B > p->n_sm * 4 * 32 ? 32 * PLL_MAX_WARPS : 32;
+    k_pll<<<(B + pll_threads - 1) / pll_threads, pll_threads, 0, s>>>(pa);
     if ((rc = check_launch(p, "k_pll"))) return rc;
     prof_begin(p, "k_nco_cos", s);
     k_nco_cos<<<dim3(((unsigned)n_if + 1023) / 1024, B), 256, 0, s>>>(pa);
@@ -911,68 +954,26 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   aa.n_out = (int)n_audio;
   if (p->resample) {
     ResampleArgs g{aa, p->d_h_poly.p, p->m.audio_upsamp, p->m.audio_decim, p->TA};
-    static const bool use_v1 = std::getenv("SDR_RESAMPLE_V1") != nullptr;
-    static const bool no_quads = std::getenv("SDR_RESAMPLE_V4") != nullptr;
-    if (!p->stereo && !no_quads && !use_v1) {
+    const bool fma = p->fma_aux;
+    prof_begin(p, "k_audio_resample", s);
+    if (p->audio_kernel == sdr_pipeline::AK_RS_QUAD) {
       ResampleQuadArgs q{aa, p->d_h_quad.p, p->m.audio_upsamp, p->m.audio_decim, p->TA, p->quad_kb, (int)n_if};
-      const int KB = p->quad_kb;
-      static const int nc = std::getenv("SDR_RESAMPLE_NC") ? std::atoi(std::getenv("SDR_RESAMPLE_NC")) : 2;
-      const int caps = 32 * nc;
-      // rows of a tile: inputs spanned by RQ_J outputs + the table (KB + 4 rows) + alignment slack
-      int pitch = round_up((int)(((long long)(RQ_J - 1) * p->m.audio_decim) / p->m.audio_upsamp) + KB + 4 + 8, 4);
-      if ((pitch / 4) % 2 == 0) pitch += 4;  // pitch/4 odd: conflict-free LDS.128 across lanes
-      const size_t smem = ((size_t)8 * (KB + 4) * 4 + (size_t)caps * pitch) * sizeof(float) +
-                          (size_t)caps * (RQ_J + 2) * sizeof(int16_t);
-      if (smem > 200 * 1024) return fail(SDR_ERR_INVALID, "resampler tile does not fit in shared memory");
-      dim3 grid(((int)n_audio + RQ_J - 1) / RQ_J, (B + caps - 1) / caps);
-      using QuadKernel = void (*)(const ResampleQuadArgs, int, int);
-      const bool fma = p->cfg.variant == SDR_VARIANT_FAST;
-      QuadKernel kern = nc == 2 ? (fma ? k_audio_resample_v5<true, 2> : k_audio_resample_v5<false, 2>)
-                                : (fma ? k_audio_resample_v5<true, 1> : k_audio_resample_v5<false, 1>);
-      prof_begin(p, "k_audio_resample", s);
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      kern<<<grid, 256, smem, s>>>(q, (int)B, pitch);
-      if ((rc = check_launch(p, "k_audio_resample_v5"))) return rc;
-    } else if (use_v1) {
-      dim3 grid(((int)n_audio + 127) / 128, B);
-      prof_begin(p, "k_audio_resample", s);
-      if (p->stereo) k_audio_resample<true><<<grid, 128, 0, s>>>(g);
-      else k_audio_resample<false><<<grid, 128, 0, s>>>(g);
-      if ((rc = check_launch(p, "k_audio_resample"))) return rc;
+      dim3 grid(((int)n_audio + RQ_J - 1) / RQ_J, (B + 63) / 64);
+      if (fma) k_audio_resample_v5<true, 2><<<grid, 256, p->rs_smem, s>>>(q, (int)B, p->rs_pitch);
+      else k_audio_resample_v5<false, 2><<<grid, 256, p->rs_smem, s>>>(q, (int)B, p->rs_pitch);
     } else {
-      // rows of the transposed tile: inputs spanned by RS_J outputs plus the filter history
-      const int rows_cap = (int)(((long long)RS_J * p->m.audio_decim) / p->m.audio_upsamp) + p->TA + 2;
-      const int TA4 = (p->TA + 3) & ~3;
-      const size_t smem = ((size_t)RS_J * TA4 + (size_t)rows_cap * RS_PITCH * (p->stereo ? 2 : 1)) * sizeof(float) +
-                          (size_t)32 * RS_J * (p->stereo ? 2 : 1) * sizeof(int16_t);
       dim3 grid(((int)n_audio + RS_J - 1) / RS_J, (B + 31) / 32);
-      static std::once_flag once[16];
-      std::call_once(once[p->cfg.device & 15], [&] {
-        cudaFuncSetAttribute(k_audio_resample_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_audio_resample_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      });
-      if (smem > 200 * 1024) return fail(SDR_ERR_INVALID, "resampler tile does not fit in shared memory");
-      const size_t smem3 = smem + 32 * 2 * sizeof(int16_t);  // padded PCM rows
+      const int du0 = p->m.audio_decim / p->m.audio_upsamp;
       using ResKernel = void (*)(const ResampleArgs, int, int);
-      ResKernel kern = nullptr;
-      const int du0 = p->m.audio_decim / p->m.audio_upsamp;   // rows between consecutive outputs (floor)
-      static const bool no_pairs = std::getenv("SDR_RESAMPLE_V3") != nullptr;
-      if (p->TA == 101 && du0 == 5 && !no_pairs) kern = p->stereo ? k_audio_resample_v4<true, 101, 5> : k_audio_resample_v4<false, 101, 5>;
-      else if (p->TA == 101 && du0 == 7 && !no_pairs) kern = p->stereo ? k_audio_resample_v4<true, 101, 7> : k_audio_resample_v4<false, 101, 7>;
-      else if (p->TA == 101) kern = p->stereo ? k_audio_resample_v3<true, 101> : k_audio_resample_v3<false, 101>;
-      else if (p->TA == 13) kern = p->stereo ? k_audio_resample_v3<true, 13> : k_audio_resample_v3<false, 13>;
-      prof_begin(p, "k_audio_resample", s);
-      if (kern) {
-        // (attribute set per launch: cheap, and correct for every instantiation and device)
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        kern<<<grid, RS_NW * 32, smem3, s>>>(g, B, rows_cap);
-      } else if (p->stereo) {
-        k_audio_resample_v2<true><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
-      } else {
-        k_audio_resample_v2<false><<<grid, RS_NW * 32, smem, s>>>(g, B, rows_cap);
-      }
-      if ((rc = check_launch(p, "k_audio_resample_v2"))) return rc;
+      ResKernel kern;
+      if (p->audio_kernel == sdr_pipeline::AK_RS_PAIR)
+        kern = du0 == 5 ? (fma ? k_audio_resample_v4<true, 101, 5, true> : k_audio_resample_v4<true, 101, 5, false>)
+                        : (fma ? k_audio_resample_v4<true, 101, 7, true> : k_audio_resample_v4<true, 101, 7, false>);
+      else if (p->stereo) kern = fma ? k_audio_resample_v2<true, true> : k_audio_resample_v2<true, false>;
+      else kern = fma ? k_audio_resample_v2<false, true> : k_audio_resample_v2<false, false>;
+      kern<<<grid, RS_NW * 32, p->rs_smem, s>>>(g, B, p->rs_rows_cap);
     }
+    if ((rc = check_launch(p, "k_audio_resample"))) return rc;
   } else if (p->audio_fast) {
     rc = p->stereo ? run_audio_fir_fast<true>(p, aa, s) : run_audio_fir_fast<false>(p, aa, s);
     if (rc) return rc;
@@ -1125,6 +1126,8 @@ extern "C" int sdr_pipeline_copy_state(sdr_pipeline *p, int dst, int src) {
     return fail(SDR_ERR_INVALID, "channel out of range");
   if (dst == src) return SDR_OK;
   SDR_CUDA(cudaSetDevice(p->cfg.device));
+  // the copies below run on the default stream: wait for whatever stream the last process call used
+  SDR_CUDA(cudaDeviceSynchronize());
   auto cp = [&](void *base, size_t row_bytes) -> int {
     if (!base) return SDR_OK;
     SDR_CUDA(cudaMemcpy((char *)base + (size_t)dst * row_bytes, (char *)base + (size_t)src * row_bytes,
@@ -1134,7 +1137,6 @@ extern "C" int sdr_pipeline_copy_state(sdr_pipeline *p, int dst, int src) {
   int rc;
   if ((rc = cp(p->rf_hist.p, 2 * (size_t)p->HR))) return rc;
   if ((rc = cp(p->prev.p, 2 * sizeof(float)))) return rc;
-  if ((rc = cp(p->demod.p, (size_t)p->HD * sizeof(float)))) return rc;
   // rows are strided: only the prefixes matter, but they sit at row starts
   auto cprow = [&](float *base, size_t stride, size_t len) -> int {
     if (!base) return SDR_OK;
@@ -1160,6 +1162,7 @@ static int ensure_host_staging(sdr_pipeline *p, size_t slice_bytes) {
   const size_t B = (size_t)p->cfg.batch;
   size_t n_pcm;
   sdr_pipeline_pcm_count(p, slice_bytes, &n_pcm);
+  p->slice_bytes = 0;   // nothing usable until every buffer below exists
   for (int i = 0; i < 2; ++i) {
     if (p->pin_in[i]) cudaFreeHost(p->pin_in[i]);
     if (p->pin_out[i]) cudaFreeHost(p->pin_out[i]);

@@ -24,6 +24,10 @@
 //                                     smallest span that is whole in both block sizes.
 //            --rds-carry              with --rds: carry the clock-recovery state from block to block
 //                                     (sdr_rds_config.cdr_carry) instead of re-creating it per block
+//            --batch B [--devices N]  B independent captures at once, spread over N devices (default:
+//                                     all) by sdr_multi_*.  stdin then carries, per device call, B
+//                                     consecutive chunks of (--blocks x block_size) bytes, one per
+//                                     capture; stdout carries the B PCM chunks in the same order.
 //
 // The reference's two threads and bounded std::queue (project.cpp:141-149,181-189,471-496)
 // become: a reader thread filling two page-locked buffers, and the main thread handing
@@ -58,7 +62,7 @@ int die(const char *what) {
 
 void usage(const char *argv0) {
   std::fprintf(stderr,
-               "Usage: %s\nor\nUsage: %s <mode> [<channels>] [--taps rf,audio,stereo] [--blocks N] [--device D] [--rds FILE [--rds-carry]]\n"
+               "Usage: %s\nor\nUsage: %s <mode> [<channels>] [--taps rf,audio,stereo] [--blocks N] [--device D] [--rds FILE [--rds-carry]] [--batch B [--devices N]]\n"
                "\t\t <mode> is a value from 0 to 3, <channels> is 1 (mono) or 2 (stereo)\n",
                argv0, argv0);
 }
@@ -66,7 +70,7 @@ void usage(const char *argv0) {
 }  // namespace
 
 int main(int argc, char *argv[]) {
-  int mode = 0, channels = 1, device = 0, blocks = 1;
+  int mode = 0, channels = 1, device = 0, blocks = 1, batch = 1, devices = 0;
   int rf_taps = 151, audio_taps = 101, stereo_taps = 151;
   std::vector<std::string> pos;
   std::string rds_path;
@@ -82,6 +86,10 @@ int main(int argc, char *argv[]) {
       blocks = std::atoi(argv[++i]);
     } else if (a == "--device" && i + 1 < argc) {
       device = std::atoi(argv[++i]);
+    } else if (a == "--batch" && i + 1 < argc) {
+      batch = std::atoi(argv[++i]);
+    } else if (a == "--devices" && i + 1 < argc) {
+      devices = std::atoi(argv[++i]);
     } else if (a == "--rds" && i + 1 < argc) {
       rds_path = argv[++i];
     } else if (a == "--rds-carry") {
@@ -93,7 +101,7 @@ int main(int argc, char *argv[]) {
       pos.push_back(a);
     }
   }
-  if (pos.size() > 2 || blocks < 1) {
+  if (pos.size() > 2 || blocks < 1 || batch < 1 || devices < 0 || (batch > 1 && !rds_path.empty())) {
     usage(argv[0]);
     return 1;
   }
@@ -137,7 +145,20 @@ int main(int argc, char *argv[]) {
   cfg.variant = SDR_VARIANT_EXACT;
   cfg.max_bytes_per_channel = call_bytes;
   sdr_pipeline *pipe = nullptr;
-  if (sdr_pipeline_create(&cfg, &pipe)) return die("sdr_pipeline_create");
+  sdr_multi *multi = nullptr;
+  const bool batched = batch > 1 || devices > 0;
+  if (batched) {
+    sdr_multi_config mc{};
+    mc.cfg = cfg;
+    mc.cfg.batch = batch;
+    mc.n_devices = devices;
+    if (sdr_multi_create(&mc, &multi)) return die("sdr_multi_create");
+    int n_dev = 0;
+    sdr_multi_layout(multi, &n_dev, nullptr, nullptr, 0);
+    std::fprintf(stderr, "%d captures over %d device(s)\n", batch, n_dev);
+  } else if (sdr_pipeline_create(&cfg, &pipe)) {
+    return die("sdr_pipeline_create");
+  }
   sdr_rds *rds = nullptr;
   std::FILE *rds_out = nullptr;
   sdr_rds_info_t ri{};
@@ -157,13 +178,17 @@ int main(int argc, char *argv[]) {
   std::vector<char> rds_offsets((size_t)ri.max_pending_blocks + 1);
   size_t rds_block_index = 0;
   size_t pcm_per_call = 0;
-  if (sdr_pipeline_pcm_count(pipe, call_bytes, &pcm_per_call)) return die("sdr_pipeline_pcm_count");
+  if (batched ? sdr_multi_pcm_count(multi, call_bytes, &pcm_per_call)
+              : sdr_pipeline_pcm_count(pipe, call_bytes, &pcm_per_call))
+    return die("pcm_count");
+  const size_t B = (size_t)batch;
 
+  // A slot holds the B captures' chunks of one device call back to back: [capture][call_bytes].
   Slot slots[2];
   int16_t *pcm = nullptr;
   for (auto &s : slots)
-    if (sdr_host_alloc(call_bytes, reinterpret_cast<void **>(&s.data))) return die("sdr_host_alloc");
-  if (sdr_host_alloc(pcm_per_call * sizeof(int16_t), reinterpret_cast<void **>(&pcm)))
+    if (sdr_host_alloc(B * call_bytes, reinterpret_cast<void **>(&s.data))) return die("sdr_host_alloc");
+  if (sdr_host_alloc(B * pcm_per_call * sizeof(int16_t), reinterpret_cast<void **>(&pcm)))
     return die("sdr_host_alloc");
 
   std::mutex mu;
@@ -179,12 +204,14 @@ int main(int argc, char *argv[]) {
         cv.wait(lk, [&] { return !s.full; });
       }
       size_t got = 0;
-      while (got < call_bytes) {
-        size_t n = std::fread(s.data + got, 1, call_bytes - got, stdin);
+      while (got < B * call_bytes) {
+        size_t n = std::fread(s.data + got, 1, B * call_bytes - got, stdin);
         if (n == 0) break;
         got += n;
       }
-      const size_t whole = got / block_bytes * block_bytes;  // partial block is dropped
+      // single capture: a partial block is dropped; batch: only whole rounds of B chunks count
+      const size_t whole = B == 1 ? got / block_bytes * block_bytes : (got == B * call_bytes ? call_bytes : 0);
+      got = B == 1 ? got : (got == B * call_bytes ? call_bytes : 0);
       std::unique_lock<std::mutex> lk(mu);
       s.bytes = whole;
       s.full = true;
@@ -207,12 +234,20 @@ int main(int argc, char *argv[]) {
     }
     if (s.bytes) {
       size_t n_pcm = 0;
-      sdr_pipeline_pcm_count(pipe, s.bytes, &n_pcm);
-      if (sdr_pipeline_process_host(pipe, s.data, s.bytes, s.bytes, pcm, n_pcm)) {
-        rc = die("sdr_pipeline_process_host");
-        break;
+      if (batched) {
+        sdr_multi_pcm_count(multi, s.bytes, &n_pcm);
+        if (sdr_multi_process_host(multi, s.data, call_bytes, s.bytes, pcm, n_pcm)) {
+          rc = die("sdr_multi_process_host");
+          break;
+        }
+      } else {
+        sdr_pipeline_pcm_count(pipe, s.bytes, &n_pcm);
+        if (sdr_pipeline_process_host(pipe, s.data, s.bytes, s.bytes, pcm, n_pcm)) {
+          rc = die("sdr_pipeline_process_host");
+          break;
+        }
       }
-      std::fwrite(pcm, sizeof(int16_t), n_pcm, stdout);
+      std::fwrite(pcm, sizeof(int16_t), B * n_pcm, stdout);
       if (rds) {
         size_t n_bits = 0, n_blocks = 0;
         if (sdr_rds_read(rds, 0, nullptr, rds_bits.data(), rds_bits.size(), &n_bits, rds_counts.data(),
@@ -229,8 +264,8 @@ int main(int argc, char *argv[]) {
           at += (size_t)rds_counts[b];
         }
       }
-      total_in += s.bytes;
-      total_out += n_pcm;
+      total_in += B * s.bytes;
+      total_out += B * n_pcm;
     }
     const bool short_read = s.bytes < call_bytes;
     {
@@ -250,5 +285,6 @@ int main(int argc, char *argv[]) {
   if (rds_out) std::fclose(rds_out);
   sdr_rds_destroy(rds);
   sdr_pipeline_destroy(pipe);
+  sdr_multi_destroy(multi);
   return 0;
 }

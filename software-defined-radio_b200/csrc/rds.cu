@@ -929,6 +929,7 @@ struct sdr_rds {
   RBuf<int> counts;
   bool keep_nco = false;
   bool cdr_carry = false;
+  int pll_form = 0;   // SDR_RDS_PLL_AUTO / _LANE / _WARP
   int cursor = 0;             // blocks waiting in bits/counts
   long long blocks_done = 0;  // since reset
   size_t last_n_if = 0;
@@ -1051,9 +1052,8 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     a.normBandwidth = 0.002;
     // Warp form below ~4096 captures (latency: 1.8 ms per 76 800 samples, flat up to ~1024
     // captures, then ~0.95 ms per 1024 captures); one lane per capture above (4.7 ms, flat up to
-    // ~19 k captures): measured 8192 captures 7.9 vs 4.8 ms.  SDR_RDS_PLL=lane|warp forces one.
-    const char *force = std::getenv("SDR_RDS_PLL");
-    const bool one_lane = force ? force[0] == 'l' : B > 4096;
+    // ~19 k captures): measured 8192 captures 7.9 vs 4.8 ms.  sdr_rds_config.pll_form forces one.
+    const bool one_lane = r->pll_form ? r->pll_form == SDR_RDS_PLL_LANE : B > 4096;
     sdr_prof_begin(p, "k_rds_pll", s);
     if (one_lane) k_rds_pll<<<(B + 31) / 32, 32, 0, s>>>(a);
     else k_rds_pll_warp<<<(B + RDS_PLLW_WARPS - 1) / RDS_PLLW_WARPS, 32 * RDS_PLLW_WARPS, 0, s>>>(a);
@@ -1100,7 +1100,7 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
                          (size_t)4 * r->quad_rows * 4) * sizeof(double);
     dim3 grid((n_out + RDS_RS_J - 1) / RDS_RS_J, (B + 31) / 32);
     sdr_prof_begin(p, "k_rds_resample", s);
-    cudaFuncSetAttribute(k_rds_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 200 * 1024) return fail(SDR_ERR_INVALID, "RDS resampler tile does not fit in shared memory");
     k_rds_resample<<<grid, 256, smem, s>>>(a, B, rows_cap, n, r->quad_rows);
     if ((rc = sdr_check_launch(p, "k_rds_resample"))) return rc;
   }
@@ -1289,7 +1289,12 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
     return fail(SDR_ERR_CAPACITY, "pipeline max_bytes_per_channel is smaller than one RDS block");
   }
   if (r->block_out <= RDS_CDR_START) { delete r; return fail(SDR_ERR_INVALID, "RDS block too short for the CDR"); }
-  SDR_CUDA(cudaSetDevice(r->view.device));
+  {
+    const cudaError_t e = cudaSetDevice(r->view.device);
+    if (e != cudaSuccess) { delete r; return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__); }
+  }
+  // the resampler's tile is the only kernel of the chain above the default 48 KB of dynamic shared memory
+  cudaFuncSetAttribute(k_rds_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const size_t B = (size_t)r->view.batch;
   r->cap_if = r->view.cap_if / (size_t)r->block_if * (size_t)r->block_if;
   r->cap_out = r->cap_if * (size_t)r->U / (size_t)r->D;
@@ -1299,6 +1304,8 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
   r->bits_cap = r->block_out / r->sps + 4;  // >= prefix bits + pairs, also with a carried start of 0
   r->keep_nco = cfg && cfg->keep_nco;
   r->cdr_carry = cfg && cfg->cdr_carry;
+  r->pll_form = cfg ? cfg->pll_form : 0;
+  if (r->pll_form < 0 || r->pll_form > 2) { delete r; return fail(SDR_ERR_INVALID, "unknown sdr_rds_config.pll_form"); }
   auto up = [](size_t v) { return (v + 3) / 4 * 4; };
   r->chan_stride = up(RDS_HC + r->cap_if);
   r->carr_stride = up(r->cap_if);

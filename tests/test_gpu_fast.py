@@ -45,9 +45,12 @@ def test_fast_front_end(sdr, orc, mode, taps):
     with sdr.Pipeline(mode=mode, channels=1, rf_taps=taps[0], audio_taps=taps[1], batch=B,
                       variant=sdr.VARIANT_FAST, max_bytes_per_channel=nbytes) as p:
         p.keep_taps(True)
+        p.profile(True)
         pcm = p.process_host(iq)
         got = {n: [p.tap(n, c) for c in range(B)] for n in ("i_filt", "q_filt", "demod", "audio_filt")}
-        assert "k_rf_demod_tc" in p.kernel_times() or True
+        launched = p.kernel_times()
+        assert "k_rf_demod_tc" in launched and "k_rf_demod" not in launched, \
+            f"the fast variant must run the tensor-core front end, ran {sorted(launched)}"
     rf_Fs, decim = sdr.mode_info(mode).rf_Fs, sdr.mode_info(mode).rf_decim
     h = sdr.impulseResponseLPF(rf_Fs, 100000, taps[0])
     for c in range(B):

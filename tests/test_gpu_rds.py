@@ -31,12 +31,12 @@ def close(got, want, tol, what=""):
     assert err <= tol * scale, f"{what}: {err:.3e} > {tol * scale:.3e}"
 
 
-def run_gpu(sdr, iq, mode, block_if, n_calls=1, channels=1, variant=0):
+def run_gpu(sdr, iq, mode, block_if, n_calls=1, channels=1, variant=0, pll_form="auto"):
     """iq [B, nbytes] -> ({stage: [B] arrays}, [B] read() dicts)."""
     B, nbytes = iq.shape
     with sdr.Pipeline(mode=mode, channels=channels, batch=B, variant=variant,
                       max_bytes_per_channel=nbytes) as p:
-        with sdr.Rds(p, block_if=block_if, keep_nco=True, max_pending_blocks=64) as r:
+        with sdr.Rds(p, block_if=block_if, keep_nco=True, max_pending_blocks=64, pll_form=pll_form) as r:
             bb = r.info.block_bytes
             assert nbytes % bb == 0
             blocks = nbytes // bb
@@ -262,7 +262,7 @@ def test_rds_cdr_carried_state(sdr, orc, mode, n_ref, kind):
         assert np.array_equal(rd["cdr_bits"], g["carry_bits"])
 
 
-def test_rds_pll_forms_agree(sdr, orc, monkeypatch):
+def test_rds_pll_forms_agree(sdr, orc):
     """The two forms of the PLL kernel (a warp per capture solving 32 samples at a time, one
     lane per capture walking them) against the oracle and against each other."""
     R = orclib.RDS()
@@ -272,8 +272,7 @@ def test_rds_pll_forms_agree(sdr, orc, monkeypatch):
                    for c, k in enumerate(("rds", "stereo", "silence", "clipped", "rds_groups"))])
     outs = {}
     for form in ("warp", "lane"):
-        monkeypatch.setenv("SDR_RDS_PLL", form)
-        parts, reads = run_gpu(sdr, iq, mode, block_if, n_calls=2)
+        parts, reads = run_gpu(sdr, iq, mode, block_if, n_calls=2, pll_form=form)
         outs[form] = (parts, reads)
         for c in range(iq.shape[0]):
             want = oracle_chain(R, orc, iq[c], mode, block_if)
