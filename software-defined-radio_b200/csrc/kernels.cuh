@@ -245,6 +245,13 @@ struct RfArgs {
   long long n_rf;          // input pairs per capture in this call
   int n_if;                // outputs per capture in this call
   int outs_per_seg;        // multiple of the tile size
+  // tensor-core front end only: fm_demod also (or only) as two half-precision planes
+  // x = xh + xl (xh = fp16(x), xl = fp16(x - xh)): the operand format of the tensor-core
+  // resampler (resample_tc.cuh).  [B][pl_stride] halfs each, sample 0 at pl_off.
+  uint16_t *xh, *xl;
+  size_t pl_stride;
+  int pl_off;
+  int write_f32;           // 0: the planes replace the float row (nobody else reads fm_demod)
 };
 
 template <int T, int D>

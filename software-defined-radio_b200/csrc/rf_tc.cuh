@@ -460,8 +460,31 @@ k_rf_demod_tc(const RfTcArgs g) {
         pi = fi[k];
         pq = fq[k];
       }
+      if (a.xh && jrow + 8 <= a.n_if) {
+        // split planes for the tensor-core resampler: 16 bytes per plane and thread (pl_off and
+        // pl_stride are multiples of 8, jrow is a multiple of 8)
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint16_t h0, h1, l0, l1;
+          float f0, f1;
+          asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h0) : "f"(dm[2 * k]));
+          asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h1) : "f"(dm[2 * k + 1]));
+          asm("cvt.f32.f16 %0, %1;" : "=f"(f0) : "h"(h0));
+          asm("cvt.f32.f16 %0, %1;" : "=f"(f1) : "h"(h1));
+          asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l0) : "f"(__fsub_rn(dm[2 * k], f0)));
+          asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l1) : "f"(__fsub_rn(dm[2 * k + 1], f1)));
+          hw[k] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          lw[k] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+        const size_t at = (size_t)b * a.pl_stride + a.pl_off + jrow;
+        *reinterpret_cast<uint4 *>(a.xh + at) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4 *>(a.xl + at) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
       float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
-      if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 7) == 0) {
+      if (!a.write_f32) {
+        // the planes are the only consumer's input
+      } else if (jrow + 8 <= a.n_if && ((a.demod_stride | a.demod_off) & 7) == 0) {
         // one 256-bit store per thread: half the store wavefronts of two float4 (the L1 data pipe
         // is the busiest unit of this kernel, profiles/r1k)
         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(drow + jrow), "f"(dm[0]), "f"(dm[1]),
