@@ -31,6 +31,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "--expt-relaxed-constexpr"]
 if os.environ.get("SDR_TC_TRACE"):   # debug build for tools/tc_trace.py (clock stamps in the tensor-core kernel)
     NVCC_FLAGS.append("-DSDR_TC_TRACE")
+if os.environ.get("SDR_RT_TRACE"):   # debug build: per-role cycle totals of one CTA of the tensor-core resampler (printf)
+    NVCC_FLAGS.append("-DSDR_RT_TRACE")
 
 
 def _newer(target: str, sources: list[str]) -> bool:

@@ -1252,10 +1252,10 @@ static __global__ void __launch_bounds__(256) k_nco_cos(const PllArgs a) {
 // ---------------------------------------------------------------------------
 struct CarryArgs {
   // float rows: copy row[off_src .. off_src+len) -> row[0 .. len)
-  float *rows[3];
-  size_t strides[3];
-  int src_off[3];
-  int len[3];
+  float *rows[5];      // demod, stereo_filt, nco, and the two fp16 planes of the tensor-core resampler
+  size_t strides[5];   // (plane rows are moved as pairs of halfs: offsets and lengths in 32-bit words)
+  int src_off[5];
+  int len[5];
   // raw I/Q history
   const uint8_t *iq;
   size_t iq_stride;
@@ -1275,7 +1275,7 @@ static __global__ void k_carry(const CarryArgs c) {
   // 1. float tails.  Source and destination ranges may overlap when the call was
   //    shorter than the history, so go through shared memory.
   float *fstage = reinterpret_cast<float *>(stage);
-  for (int r = 0; r < 3; ++r) {
+  for (int r = 0; r < 5; ++r) {
     if (!c.rows[r]) continue;
     float *row = c.rows[r] + (size_t)b * c.strides[r];
     for (int i = t; i < c.len[r]; i += blockDim.x) fstage[i] = row[c.src_off[r] + i];

@@ -20,6 +20,8 @@
 #include "kernels.cuh"
 #include "pipeline_view.h"
 #include "rf_tc.cuh"
+#include "resample_tc.cuh"
+#include <cuda_fp16.h>
 
 namespace sdr {
 
@@ -109,7 +111,14 @@ struct sdr_pipeline {
   int base_granule_bytes, base_if_per_granule, base_pcm_per_granule;  // without a follower stage
   // which audio kernel runs (decided once, at create): modes 0/1 specialised FIR or generic FIRs;
   // modes 2/3 quad resampler (mono), pair resampler (stereo, 101 taps per phase) or the generic one
-  enum AudioKernel { AK_FIR, AK_FIR_GENERIC, AK_RS_QUAD, AK_RS_PAIR, AK_RS_GENERIC } audio_kernel = AK_FIR_GENERIC;
+  enum AudioKernel { AK_FIR, AK_FIR_GENERIC, AK_RS_QUAD, AK_RS_PAIR, AK_RS_GENERIC, AK_RS_TC } audio_kernel = AK_FIR_GENERIC;
+  // tensor-core resampler (resample_tc.cuh): period tables, tap tiles, fp16 planes of fm_demod
+  RtTables rt_tab{};
+  DevBuf<uint8_t> d_rt_tiles;
+  DevBuf<uint16_t> xh, xl;
+  size_t pl_stride = 0;
+  int pl_off = 0;
+  float rt_out_scale = 0.0f;
   int rs_pitch = 0, rs_rows_cap = 0;   // tile geometry of the chosen resampler
   size_t rs_smem = 0;
   bool fma_aux = false;                // contract the multiply-adds that do not feed the PLL (FAST, MIXED)
@@ -417,6 +426,7 @@ extern "C" int sdr_pipeline_reset(sdr_pipeline *p) {
   if ((rc = p->prev.zero())) return rc;
   if ((rc = p->prev_new.zero())) return rc;
   if ((rc = p->demod.zero())) return rc;
+  if ((rc = p->xh.zero()) || (rc = p->xl.zero())) return rc;
   if ((rc = p->stf.zero())) return rc;
   if ((rc = p->car.zero())) return rc;
   if ((rc = p->nco.zero())) return rc;
@@ -488,6 +498,87 @@ static int alloc_tap_buffers(sdr_pipeline *p) {
     }
   }
   return SDR_OK;
+}
+
+// Period tables and tap tiles of the tensor-core resampler (resample_tc.cuh).  Returns false when
+// the mode's geometry does not fit the kernel (the quad resampler then stays in charge).
+static bool build_resample_tc(sdr_pipeline *p, std::vector<uint8_t> &tiles) {
+  const int U = p->m.audio_upsamp, D = p->m.audio_decim, TA = p->TA;
+  int g = D, r = U;
+  while (r) { const int t = g % r; g = r; r = t; }
+  RtTables &t = p->rt_tab;
+  t.P_in = D / g;
+  t.P_out = U / g;
+  if (t.P_in % RT_SLAB) return false;
+  t.SP = t.P_in / RT_SLAB;
+  t.NBLK = (t.P_out + RT_NB - 1) / RT_NB;
+  if (t.SP > RT_MAX_SP || t.NBLK > RT_MAX_BLK) return false;
+  auto floordiv32 = [](int v) { return v >= 0 ? v / RT_SLAB : -((-v + RT_SLAB - 1) / RT_SLAB); };
+  int n_tiles = 0;
+  t.qmin = 0;
+  for (int b = 0; b < t.NBLK; ++b) {
+    const int j_lo = b * RT_NB, j_hi = std::min(j_lo + RT_NB - 1, t.P_out - 1);
+    const int lo = (int)(((long long)j_lo * D) / U) - (TA - 1), hi = (int)(((long long)j_hi * D) / U);
+    t.qs[b] = floordiv32(lo);
+    t.qe[b] = floordiv32(hi);
+    t.tile0[b] = n_tiles;
+    n_tiles += t.qe[b] - t.qs[b] + 1;
+    t.qmin = std::min(t.qmin, t.qs[b]);
+    if (b && t.qs[b] < t.qs[b - 1]) return false;
+  }
+  if (-t.qmin >= t.SP) return false;   // a block may only reach back into the previous period
+  // the schedule: which blocks meet slab position q (at most RT_NACT; a block has long finished when
+  // its accumulator slot comes round again: RT_SLOTS = 2 * RT_NACT)
+  std::memset(t.sched, 0, sizeof t.sched);
+  std::memset(t.tile, 0, sizeof t.tile);
+  std::memset(t.any_last, 0, sizeof t.any_last);
+  for (int q = 0; q < t.SP; ++q) {
+    int n = 0;
+    for (int dp = 0; dp < 2; ++dp)
+      for (int b = 0; b < t.NBLK; ++b) {
+        const int qq = q - dp * t.SP;
+        if (qq < t.qs[b] || qq > t.qe[b]) continue;
+        if (n == RT_NACT || t.qe[b] - t.qs[b] > 255) return false;
+        t.tile[q][n] = (uint32_t)(t.tile0[b] + qq - t.qs[b]);
+        if (qq == t.qe[b]) t.any_last[q] = 1;
+        t.sched[q][n++] = (uint32_t)b | ((uint32_t)(qq - t.qs[b]) << 8) | ((uint32_t)dp << 16) |
+                          ((uint32_t)(qq == t.qe[b]) << 17) | (1u << 18);
+      }
+  }
+  // taps with the reference's output gain (filter.cpp:213) and a power-of-two scale folded in
+  double hmax = 0.0;
+  for (float h : p->h_poly) hmax = std::max(hmax, std::fabs((double)h) * (1.0 + U));
+  if (!(hmax > 0.0)) return false;
+  int S = 0;
+  while (S < 40 && std::ldexp(hmax, S + 1) < 8192.0) ++S;
+  while (S > -40 && std::ldexp(hmax, S) >= 8192.0) --S;
+  p->rt_out_scale = (float)std::ldexp(1.0, -S);
+  tiles.assign((size_t)n_tiles * RT_TILE_BYTES, 0);
+  for (int b = 0; b < t.NBLK; ++b) {
+    for (int js = 0; js <= t.qe[b] - t.qs[b]; ++js) {
+      uint16_t *tile = reinterpret_cast<uint16_t *>(tiles.data() + (size_t)(t.tile0[b] + js) * RT_TILE_BYTES);
+      for (int o = 0; o < RT_NB; ++o) {
+        const int j = b * RT_NB + o;
+        if (j >= t.P_out) continue;
+        const long long m = (long long)j * D;
+        const int phase = (int)(m % U), i0 = (int)(m / U);
+        for (int k = 0; k < RT_SLAB; ++k) {
+          const int i = RT_SLAB * (t.qs[b] + js) + k, tap = i0 - i;
+          if (tap < 0 || tap >= TA) continue;
+          const double v = std::ldexp((double)p->h_poly[(size_t)phase * TA + tap] * (1.0 + U), S);
+          const __half hh = __float2half_rn((float)v);
+          const __half hl = __float2half_rn((float)(v - (double)__half2float(hh)));
+          // [half][chunk kc][output o][8 halfs]
+          const size_t at = ((size_t)(k / 8) * RT_NB + o) * 8 + (k % 8);
+          tile[at] = __half_as_ushort(hh);
+          tile[(size_t)(RT_SLAB / 8) * RT_NB * 8 + at] = __half_as_ushort(hl);
+        }
+      }
+    }
+  }
+  p->pl_off = -t.qmin * RT_SLAB;
+  p->pl_stride = (size_t)round_up((int)(p->pl_off + p->cap_if + RT_SLAB), 8);
+  return true;
 }
 
 extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
@@ -585,6 +676,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     cudaFuncSetAttribute(k_rf_demod_tc<10>, at, (int)TcCfg<10>::SMEM);
     cudaFuncSetAttribute(k_rf_demod_tc<5>, at, (int)TcCfg<5>::SMEM);
     cudaFuncSetAttribute(k_rf_demod_tc<3>, at, (int)TcCfg<3>::SMEM);
+    cudaFuncSetAttribute(k_audio_resample_tc<RT_NST, 2, true>, at, (int)rt_smem(RT_NST));
     cudaFuncSetAttribute(k_audio_resample_v5<true, 2>, at, big);
     cudaFuncSetAttribute(k_audio_resample_v5<false, 2>, at, big);
     cudaFuncSetAttribute(k_audio_resample_v4<true, 101, 5, true>, at, big);
@@ -644,6 +736,9 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     }
   }
 
+  std::vector<uint8_t> rt_tiles;
+  if (p->resample && !p->stereo && cfg->variant == SDR_VARIANT_FAST && build_resample_tc(p, rt_tiles))
+    p->audio_kernel = sdr_pipeline::AK_RS_TC;
   std::vector<int8_t> tc_b;
   std::vector<int32_t> tc_h;
   if (cfg->variant == SDR_VARIANT_FAST) {
@@ -723,6 +818,15 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     TRY(p->tc_next_item.alloc(1));   // zeroed before first use; k_carry re-arms it at the end of every call
     rc = cudaMemcpy(p->tc_bmat.p, tc_b.data(), tc_b.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
                  cudaMemcpy(p->tc_hq.p, tc_h.data(), tc_h.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess
+             ? SDR_OK
+             : SDR_ERR_CUDA;
+    TRY(rc);
+  }
+  if (p->audio_kernel == sdr_pipeline::AK_RS_TC) {
+    TRY(p->d_rt_tiles.alloc(rt_tiles.size()));
+    TRY(p->xh.alloc(B * p->pl_stride));
+    TRY(p->xl.alloc(B * p->pl_stride));
+    rc = cudaMemcpy(p->d_rt_tiles.p, rt_tiles.data(), rt_tiles.size(), cudaMemcpyHostToDevice) == cudaSuccess
              ? SDR_OK
              : SDR_ERR_CUDA;
     TRY(rc);
@@ -883,6 +987,15 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   ra.tap_stride = p->tap_if_stride;
   ra.n_rf = n_rf;
   ra.n_if = (int)n_if;
+  const bool rs_tc = p->audio_kernel == sdr_pipeline::AK_RS_TC;
+  ra.write_f32 = 1;
+  if (rs_tc) {   // the front end hands fm_demod to the tensor-core resampler as two fp16 planes
+    ra.xh = p->xh.p;
+    ra.xl = p->xl.p;
+    ra.pl_stride = p->pl_stride;
+    ra.pl_off = p->pl_off;
+    ra.write_f32 = (taps || p->hook) ? 1 : 0;   // the float row only when someone else reads it
+  }
   if ((rc = run_rf(p, ra, s))) return rc;
 
   // ---- stereo: K4 + K5 ----
@@ -956,7 +1069,25 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
     ResampleArgs g{aa, p->d_h_poly.p, p->m.audio_upsamp, p->m.audio_decim, p->TA};
     const bool fma = p->fma_aux;
     prof_begin(p, "k_audio_resample", s);
-    if (p->audio_kernel == sdr_pipeline::AK_RS_QUAD) {
+    if (rs_tc) {
+      ResampleTcArgs t{};
+      t.xh = p->xh.p;
+      t.xl = p->xl.p;
+      t.pl_stride = p->pl_stride;
+      t.pl_off = p->pl_off;
+      t.tiles = p->d_rt_tiles.p;
+      t.pcm = d_pcm;
+      t.pcm_stride = pcm_stride;
+      t.audio_filt = aa.audio_filt;
+      t.tap_stride = aa.tap_stride;
+      t.out_scale = p->rt_out_scale;
+      t.batch = B;
+      t.n_periods = (int)(n_if / (size_t)p->rt_tab.P_in);
+      const int row_tiles = (B + RT_ROWS - 1) / RT_ROWS;
+      const int total_blocks = t.n_periods * p->rt_tab.NBLK;
+      t.ctas_per_tile = std::max(1, std::min(total_blocks, (2 * p->n_sm) / row_tiles));
+      k_audio_resample_tc<RT_NST, 2, true><<<row_tiles * t.ctas_per_tile, RT_BLOCK, rt_smem(RT_NST), s>>>(t, p->rt_tab);
+    } else if (p->audio_kernel == sdr_pipeline::AK_RS_QUAD) {
       ResampleQuadArgs q{aa, p->d_h_quad.p, p->m.audio_upsamp, p->m.audio_decim, p->TA, p->quad_kb, (int)n_if};
       dim3 grid(((int)n_audio + RQ_J - 1) / RQ_J, (B + 63) / 64);
       if (fma) k_audio_resample_v5<true, 2><<<grid, 256, p->rs_smem, s>>>(q, (int)B, p->rs_pitch);
@@ -1036,6 +1167,13 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
     ca.src_off[2] = (int)n_if;
     ca.len[2] = p->HA + 1;
   }
+  if (rs_tc) {   // planes: rows of halfs moved as 32-bit words (every offset is even)
+    ca.rows[3] = reinterpret_cast<float *>(p->xh.p);
+    ca.rows[4] = reinterpret_cast<float *>(p->xl.p);
+    ca.strides[3] = ca.strides[4] = p->pl_stride / 2;
+    ca.src_off[3] = ca.src_off[4] = (int)(n_if / 2);
+    ca.len[3] = ca.len[4] = p->pl_off / 2;
+  }
   ca.iq = d_iq;
   ca.iq_stride = iq_stride;
   ca.hist = p->rf_hist.p;
@@ -1045,7 +1183,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   ca.prev_src = p->prev_new.p;
   // When taps are kept the carry would overwrite what sdr_pipeline_tap reads
   // (history-prefixed rows), so the tap accessor accounts for it via last_n_if.
-  size_t sh = std::max<size_t>((size_t)std::max(p->HD, p->HA + 1) * sizeof(float), (size_t)2 * p->HR);
+  size_t sh = std::max<size_t>((size_t)std::max({p->HD, p->HA + 1, p->pl_off / 2}) * sizeof(float), (size_t)2 * p->HR);
   ca.work_counter = p->tc_next_item.p;   // nullptr unless the fast variant allocated it
   prof_begin(p, "k_carry", s);
   k_carry<<<B, 128, sh, s>>>(ca);
@@ -1148,6 +1286,10 @@ extern "C" int sdr_pipeline_copy_state(sdr_pipeline *p, int dst, int src) {
   if ((rc = cprow(p->stf.p, p->stf_stride, p->HA))) return rc;
   if ((rc = cprow(p->nco.p, p->nco_stride, p->HA + 1))) return rc;
   if ((rc = cprow(p->pll_state.p, 8, 8))) return rc;
+  if (p->xh.p) {   // fp16 planes of the tensor-core resampler: history prefix, as 32-bit words
+    if ((rc = cprow(reinterpret_cast<float *>(p->xh.p), p->pl_stride / 2, (size_t)p->pl_off / 2))) return rc;
+    if ((rc = cprow(reinterpret_cast<float *>(p->xl.p), p->pl_stride / 2, (size_t)p->pl_off / 2))) return rc;
+  }
   return SDR_OK;
 }
 

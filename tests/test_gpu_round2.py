@@ -227,3 +227,31 @@ def test_level1_reference_project_cpp_runs_on_the_dropin():
     assert rc0 == 1 and rc1 == 1, (rc0, rc1, err1[-1500:])
     assert head1 == head0 and tail1 == tail0
     assert "End of input stream reached" in "".join(tail1)
+
+
+# ---- tensor-core resampler (csrc/resample_tc.cuh) -------------------------------------------------
+@pytest.mark.parametrize("mode", [2, 3])
+def test_tc_resampler_wide_batch_and_streaming(sdr, orc, mode):
+    """FAST mono, modes 2/3: 130 captures (a second, almost empty 128-capture tile), the capture cut
+    into three uneven calls (the fp16 planes' history is carried) must give the same bits as one
+    call; audio_filt >= 100 dB and PCM within +-1 LSB of the reference on sampled captures."""
+    B = 130
+    iq = siggen.make_batch(B, mode, 3, "stereo", distinct=6)
+    gran = sdr.mode_info(mode, 1).granule_bytes
+    n = iq.shape[1]
+    cuts = [0, gran * 2, gran * 9, n]
+    with sdr.Pipeline(mode=mode, channels=1, batch=B, variant=sdr.VARIANT_FAST, max_bytes_per_channel=n) as p:
+        p.keep_taps(True)
+        p.profile(True)
+        whole = p.process_host(iq)
+        audio = {c: p.tap("audio_filt", c) for c in (0, 5, 127, 128, 129)}
+        assert "k_audio_resample" in p.kernel_times()
+        p.keep_taps(False)
+        p.reset()
+        parts = [p.process_host(np.ascontiguousarray(iq[:, a:b])) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts, axis=1), whole), "result depends on how the capture is cut into calls"
+    for c, got in audio.items():
+        want_pcm, want = orc.run_chain(iq[c], mode, 1)
+        assert snr_db(got, want["audio_filt"]) >= 100.0, (c, snr_db(got, want["audio_filt"]))
+        d = np.abs(whole[c].astype(np.int32) - want_pcm.astype(np.int32))
+        assert int(d.max()) <= 1, f"capture {c}: PCM differs by {int(d.max())} LSB"
