@@ -737,7 +737,12 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   }
 
   std::vector<uint8_t> rt_tiles;
-  if (p->resample && !p->stereo && cfg->variant == SDR_VARIANT_FAST && build_resample_tc(p, rt_tiles))
+  // The tensor-core resampler's cost follows the INPUT rate (one pipeline step per 32-sample slab),
+  // the quad resampler's the OUTPUT rate (101 multiply-adds per output).  Measured on B200
+  // (1024 captures x 16 blocks): mode 2 (0.184 outputs per input) 0.195 vs 0.245 ms; mode 3 (0.138)
+  // 0.674 vs 0.686 ms, which does not pay for the front end's extra plane stores (+0.07 ms).
+  if (p->resample && !p->stereo && cfg->variant == SDR_VARIANT_FAST &&
+      (long long)m.audio_upsamp * 100 >= (long long)m.audio_decim * 16 && build_resample_tc(p, rt_tiles))
     p->audio_kernel = sdr_pipeline::AK_RS_TC;
   std::vector<int8_t> tc_b;
   std::vector<int32_t> tc_h;

@@ -246,6 +246,8 @@ def test_tc_resampler_wide_batch_and_streaming(sdr, orc, mode):
         whole = p.process_host(iq)
         audio = {c: p.tap("audio_filt", c) for c in (0, 5, 127, 128, 129)}
         assert "k_audio_resample" in p.kernel_times()
+        # mode 2 runs the tensor-core resampler (the front end then also writes the fp16 planes);
+        # mode 3 stays on the quad kernel (pipeline.cu: measured, no gain there)
         p.keep_taps(False)
         p.reset()
         parts = [p.process_host(np.ascontiguousarray(iq[:, a:b])) for a, b in zip(cuts[:-1], cuts[1:])]
