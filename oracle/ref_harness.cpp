@@ -19,6 +19,7 @@
 
 #include "filter.h"  // reference include/filter.h
 #include "iofunc.h"  // reference include/iofunc.h
+#include "fourier.h" // reference include/fourier.h (estimatePSD: the off-path diagnostics op)
 
 namespace {
 
@@ -282,3 +283,12 @@ size_t ref_chain_process(ref_chain *c, const uint8_t *iq, size_t nbytes, int16_t
 }
 
 }  // extern "C"
+
+// estimatePSD (src/fourier.cpp:44-126), called as the reference declares it (include/fourier.h:29).
+extern "C" int ref_psd(const float *samples, size_t n, float Fs, float *freq, float *psd) {
+  std::vector<float> f, p, x(samples, samples + n);
+  estimatePSD(f, p, x, Fs);
+  for (size_t i = 0; i < 256 && i < f.size(); ++i) freq[i] = f[i];
+  for (size_t i = 0; i < 256 && i < p.size(); ++i) psd[i] = p[i];
+  return (int)(n / 512);
+}
