@@ -225,6 +225,59 @@ int sdr_multi_process_host(sdr_multi *m, const uint8_t *iq, size_t iq_stride_byt
                            size_t nbytes_per_channel, int16_t *pcm, size_t pcm_stride);
 
 /* ------------------------------------------------------------------------ */
+/* Either side of the receiver.                   */
+/* ------------------------------------------------------------------------ */
+/* estimatePSD(freq, psd_est, samples, Fs)   include/fourier.h:29, src/fourier.cpp:44-126:
+ * Bartlett estimate over 512-sample (include/dy4.h:27) Hann-windowed segments, in dB, averaged in
+ * dB as the reference does.  samples: [rows][stride] floats in host memory, n per row (>= 512);
+ * freq: 256 values (may be NULL); psd: [rows][256]. */
+int sdr_psd(int device, const float *samples, size_t rows, size_t stride, size_t n, float Fs,
+            float *freq, float *psd);
+/* The same on intermediate `stage` (SDR_TAP_*) of the last process call of a pipeline, for every
+ * capture, without leaving the device until the 256 values per capture come back (needs
+ * sdr_pipeline_keep_taps).  Fs is the stage's own rate (IF rate or audio rate). */
+int sdr_pipeline_psd(sdr_pipeline *p, int stage, float *freq, float *psd);
+
+/* De-emphasis (time constant tau, 75e-6 in the Americas, 50e-6 elsewhere) on the receiver's PCM, in
+ * place: the output stage the course spec left out (doc/3dy4-project-2022.pdf p.6).  One-pole
+ * y[n] = (1-b) x[n] + b y[n-1], b = exp(-1/(Fs tau)); state per capture and audio channel carried
+ * on the device.  pcm is [batch][pcm_stride] int16, n_frames frames of `channels` values. */
+typedef struct sdr_deemph sdr_deemph;
+int sdr_deemph_create(int device, int batch, int channels, float Fs, float tau, sdr_deemph **out);
+int sdr_deemph_destroy(sdr_deemph *d);
+int sdr_deemph_reset(sdr_deemph *d);
+int sdr_deemph_process_device(sdr_deemph *d, int16_t *d_pcm, size_t pcm_stride, size_t n_frames, void *stream);
+int sdr_deemph_process_host(sdr_deemph *d, int16_t *pcm, size_t pcm_stride, size_t n_frames);
+
+/* 44-byte RIFF/WAVE header (16-bit PCM) for the receiver's output (48000 / 44100 Hz, 1 | 2 channels). */
+int sdr_wav_header(uint8_t *out44, int sample_rate, int channels, uint64_t n_frames);
+
+/* Polyphase channeliser in FRONT of the receiver: `n_wide` wideband captures, unsigned 8-bit I/Q at
+ * n_channels x Fs, each become n_channels captures at Fs in device memory, in the format
+ * sdr_pipeline_process_device consumes (row w * n_channels + c = the band centred c * Fs above the
+ * wideband centre, wrapping: c > n_channels/2 lies below it).  Critically sampled analysis bank:
+ * prototype = impulseResponseLPF at the wideband rate (n_channels * taps_per_branch taps, cut-off 0.8
+ * of half the channel spacing), decimation n_channels, DFT across the branches; filter history is
+ * carried on the device between calls. */
+typedef struct sdr_channelizer sdr_channelizer;
+typedef struct {
+  int n_channels;      /* 2, 4, 8 or 16 */
+  int taps_per_branch; /* 2..64 */
+  int n_wide;          /* wideband captures per call */
+  int device;
+  float gain;          /* output scale before requantisation to 8 bits (0 = 1.0) */
+} sdr_channelizer_config;
+int sdr_channelizer_create(const sdr_channelizer_config *cfg, sdr_channelizer **out);
+int sdr_channelizer_destroy(sdr_channelizer *c);
+int sdr_channelizer_reset(sdr_channelizer *c);
+int sdr_channelizer_prototype(const sdr_channelizer *c, float *h, size_t cap, size_t *n);
+/* d_wide [n_wide][wide_stride] -> d_out [n_wide * n_channels][out_stride], nbytes_wide / n_channels bytes per row */
+int sdr_channelizer_process_device(sdr_channelizer *c, const uint8_t *d_wide, size_t wide_stride,
+                                   size_t nbytes_wide, uint8_t *d_out, size_t out_stride, void *stream);
+int sdr_channelizer_process_host(sdr_channelizer *c, const uint8_t *wide, size_t wide_stride,
+                                 size_t nbytes_wide, uint8_t *out, size_t out_stride);
+
+/* ------------------------------------------------------------------------ */
 /* RDS receiver chain (modes 0 and 2), attached to a batched pipeline.       */
 /* The reference has no C++ RDS path: these entry points replace the block    */
 /* loop of its Python model, model/fmRDS.py:222-276 (functions in             */

@@ -83,8 +83,8 @@ void orc_deemphasis(int16_t *pcm, size_t n_frames, int channels, float Fs, float
 
 /* Critically sampled M-channel analysis bank, direct form: channel c of a wideband capture sampled
  * at M*Fs is  y_c[n] = sum_t h[t] * x[n*M + (M-1) - t] * exp(-j 2 pi c (n*M + (M-1) - t) / M),
- * x = (u8 - 127.5)/127.5 (zero before the capture), h the M*T-tap prototype; output requantised to
- * unsigned 8-bit I/Q: clip(rint(127.5 + 127.5 * gain * y)).  out is [M][2*n_out]. */
+ * x = (u8 - 128)/128 as the receiver reads it (iofunc.cpp:133; zero before the capture), h the M*T-tap
+ * prototype; output back in the same format: clip(128 + rint(128 * gain * y)).  out is [M][2*n_out]. */
 void orc_channelize(const uint8_t *iq, size_t n_in, int M, const float *h, int ntaps, float gain,
                     uint8_t *out, size_t n_out) {
   for (int c = 0; c < M; ++c)
@@ -93,14 +93,14 @@ void orc_channelize(const uint8_t *iq, size_t n_in, int M, const float *h, int n
       for (int t = 0; t < ntaps; ++t) {
         const long long i = (long long)n * M + (M - 1) - t;
         if (i < 0 || (size_t)i >= n_in) continue;
-        const double xi = ((double)iq[2 * i] - 127.5) / 127.5, xq = ((double)iq[2 * i + 1] - 127.5) / 127.5;
+        const double xi = ((double)iq[2 * i] - 128.0) / 128.0, xq = ((double)iq[2 * i + 1] - 128.0) / 128.0;
         const long long ph = ((long long)c * (i % M)) % M;
         const double ang = -2.0 * ORC_PI * (double)ph / M;
         const double cr = cos(ang), ci = sin(ang);
         re += h[t] * (xi * cr - xq * ci);
         im += h[t] * (xi * ci + xq * cr);
       }
-      double vi = rint(127.5 + 127.5 * gain * re), vq = rint(127.5 + 127.5 * gain * im);
+      double vi = 128.0 + rint(128.0 * (double)gain * re), vq = 128.0 + rint(128.0 * (double)gain * im);
       vi = vi < 0 ? 0 : vi > 255 ? 255 : vi;
       vq = vq < 0 ? 0 : vq > 255 ? 255 : vq;
       out[(size_t)c * 2 * n_out + 2 * n] = (uint8_t)vi;

@@ -48,6 +48,11 @@ class MultiConfig(C.Structure):
     _fields_ = [("cfg", Config), ("n_devices", C.c_int), ("devices", C.POINTER(C.c_int))]
 
 
+class ChannelizerConfig(C.Structure):
+    _fields_ = [("n_channels", C.c_int), ("taps_per_branch", C.c_int), ("n_wide", C.c_int), ("device", C.c_int),
+                ("gain", C.c_float)]
+
+
 class RdsConfig(C.Structure):
     _fields_ = [("block_if", C.c_int), ("max_pending_blocks", C.c_int), ("keep_nco", C.c_int),
                 ("cdr_carry", C.c_int), ("pll_form", C.c_int)]
@@ -108,6 +113,20 @@ ABI = {
     "sdr_multi_pcm_count": (C.c_int, [_vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sdr_multi_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
     "sdr_multi_process_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_size_t]),
+    "sdr_psd": (C.c_int, [C.c_int, _vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, _vp, _vp]),
+    "sdr_pipeline_psd": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "sdr_deemph_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(_vp)]),
+    "sdr_deemph_destroy": (C.c_int, [_vp]),
+    "sdr_deemph_reset": (C.c_int, [_vp]),
+    "sdr_deemph_process_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp]),
+    "sdr_deemph_process_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t]),
+    "sdr_wav_header": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64]),
+    "sdr_channelizer_create": (C.c_int, [C.POINTER(ChannelizerConfig), C.POINTER(_vp)]),
+    "sdr_channelizer_destroy": (C.c_int, [_vp]),
+    "sdr_channelizer_reset": (C.c_int, [_vp]),
+    "sdr_channelizer_prototype": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "sdr_channelizer_process_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_size_t, _vp]),
+    "sdr_channelizer_process_host": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_size_t]),
     "sdr_rds_design": (C.c_int, [C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "sdr_rds_create": (C.c_int, [_vp, C.POINTER(RdsConfig), C.POINTER(_vp)]),
     "sdr_rds_destroy": (C.c_int, [_vp]),
@@ -332,6 +351,13 @@ class Pipeline:
             out[name.value.decode()] = (ms.value, cnt.value)
             i += 1
 
+    def psd(self, name: str):
+        """estimatePSD of intermediate `name` of the last call, every capture: (freq[256], psd[batch, 256])."""
+        freq = np.zeros(256, np.float32)
+        out = np.zeros((self.batch, 256), np.float32)
+        _check(lib().sdr_pipeline_psd(self._h, TAP_NAMES.index(name), freq.ctypes.data, out.ctypes.data))
+        return freq, out
+
     def tap(self, name: str, channel: int = 0) -> np.ndarray:
         stage = TAP_NAMES.index(name)
         n = C.c_size_t(0)
@@ -339,6 +365,118 @@ class Pipeline:
         out = np.zeros(n.value, np.float32)
         _check(lib().sdr_pipeline_tap(self._h, stage, channel, out.ctypes.data, out.size, C.byref(n)))
         return out
+
+
+# ---- either side of the receiver: PSD diagnostics, de-emphasis, WAV header, channeliser -----------
+def estimatePSD(samples, Fs: float, device: int = 0):
+    """estimatePSD of the reference (fourier.cpp:44-126) for one row or a [rows, n] array:
+    returns (freq[256], psd_dB[rows, 256])."""
+    x = np.ascontiguousarray(samples, np.float32)
+    one = x.ndim == 1
+    if one:
+        x = x[None, :]
+    freq = np.zeros(256, np.float32)
+    psd = np.zeros((x.shape[0], 256), np.float32)
+    _check(lib().sdr_psd(device, x.ctypes.data, x.shape[0], x.strides[0] // 4, x.shape[1], Fs,
+                         freq.ctypes.data, psd.ctypes.data))
+    return freq, (psd[0] if one else psd)
+
+
+def wav_header(sample_rate: int, channels: int, n_frames: int) -> bytes:
+    buf = (C.c_uint8 * 44)()
+    _check(lib().sdr_wav_header(buf, sample_rate, channels, n_frames))
+    return bytes(buf)
+
+
+class Deemphasis:
+    """One-pole de-emphasis on the receiver's PCM (int16 [batch, n_frames * channels]), in place."""
+
+    def __init__(self, batch: int, channels: int, Fs: float, tau: float = 75e-6, device: int = 0):
+        self.batch, self.channels = batch, channels
+        self._h = _vp()
+        _check(lib().sdr_deemph_create(device, batch, channels, Fs, tau, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sdr_deemph_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self):
+        _check(lib().sdr_deemph_reset(self._h))
+
+    def process_host(self, pcm: np.ndarray) -> np.ndarray:
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.batch and pcm.flags.c_contiguous
+        _check(lib().sdr_deemph_process_host(self._h, pcm.ctypes.data, pcm.strides[0] // 2,
+                                             pcm.shape[1] // self.channels))
+        return pcm
+
+    def process_device(self, d_pcm_ptr: int, pcm_stride: int, n_frames: int, stream: int = 0):
+        _check(lib().sdr_deemph_process_device(self._h, d_pcm_ptr, pcm_stride, n_frames, stream))
+
+
+class Channelizer:
+    """Polyphase analysis bank in front of the receiver: [n_wide, nbytes] wideband uint8 I/Q at
+    n_channels x Fs -> [n_wide * n_channels, nbytes / n_channels] uint8 I/Q at Fs."""
+
+    def __init__(self, n_channels: int, taps_per_branch: int = 16, n_wide: int = 1, device: int = 0, gain: float = 1.0):
+        self.M, self.W = n_channels, n_wide
+        cfg = ChannelizerConfig(n_channels, taps_per_branch, n_wide, device, gain)
+        self._h = _vp()
+        _check(lib().sdr_channelizer_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sdr_channelizer_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self):
+        _check(lib().sdr_channelizer_reset(self._h))
+
+    def prototype(self) -> np.ndarray:
+        n = C.c_size_t(0)
+        _check(lib().sdr_channelizer_prototype(self._h, None, 0, C.byref(n)))
+        h = np.zeros(n.value, np.float32)
+        _check(lib().sdr_channelizer_prototype(self._h, h.ctypes.data, h.size, C.byref(n)))
+        return h
+
+    def process_host(self, wide: np.ndarray) -> np.ndarray:
+        wide = np.ascontiguousarray(wide, np.uint8)
+        if wide.ndim == 1:
+            wide = wide[None, :]
+        assert wide.shape[0] == self.W
+        out = np.zeros((self.W * self.M, wide.shape[1] // self.M), np.uint8)
+        _check(lib().sdr_channelizer_process_host(self._h, wide.ctypes.data, wide.strides[0], wide.shape[1],
+                                                  out.ctypes.data, out.strides[0]))
+        return out
+
+    def process_device(self, d_wide_ptr: int, wide_stride: int, nbytes_wide: int, d_out_ptr: int, out_stride: int,
+                       stream: int = 0):
+        _check(lib().sdr_channelizer_process_device(self._h, d_wide_ptr, wide_stride, nbytes_wide, d_out_ptr,
+                                                    out_stride, stream))
 
 
 class MultiPipeline:

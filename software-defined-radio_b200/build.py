@@ -51,7 +51,7 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> str:
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(ROOT, "include", "sdr_b200.h"))
     hdrs.append(os.path.join(ROOT, "include", "dropin", "filter.h"))
-    cu = [os.path.join(CSRC, f) for f in ("pipeline.cu", "ops.cu", "rds.cu", "multi.cu")]
+    cu = [os.path.join(CSRC, f) for f in ("pipeline.cu", "ops.cu", "rds.cu", "multi.cu", "aux.cu")]
     design = os.path.join(CSRC, "design.cpp")
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)

@@ -1263,6 +1263,48 @@ extern "C" int sdr_pipeline_tap(sdr_pipeline *p, int stage, int channel, float *
   return SDR_OK;
 }
 
+namespace sdr {
+int psd_device(int device, const float *d_x, size_t rows, size_t x_stride, size_t n, float Fs, float *d_db,
+               float *d_psd, cudaStream_t s);
+void psd_freq_axis(float Fs, float *freq);
+}  // namespace sdr
+
+// estimatePSD (fourier.cpp:44-126) of intermediate `stage` for every capture of the last call.
+extern "C" int sdr_pipeline_psd(sdr_pipeline *p, int stage, float *freq, float *psd) {
+  if (!p || !psd) return fail(SDR_ERR_INVALID, "null argument");
+  if (!p->keep_taps) return fail(SDR_ERR_INVALID, "call sdr_pipeline_keep_taps(p, 1) before process");
+  SDR_CUDA(cudaSetDevice(p->cfg.device));
+  const float *rows = nullptr;
+  size_t stride = 0, n = 0;
+  float Fs = (float)p->m.if_Fs;
+  switch (stage) {   // device rows that still hold the whole last call (see sdr_pipeline_tap)
+    case SDR_TAP_I_FILT: rows = p->t_ifilt.p; stride = p->tap_if_stride; n = p->last_n_if; break;
+    case SDR_TAP_Q_FILT: rows = p->t_qfilt.p; stride = p->tap_if_stride; n = p->last_n_if; break;
+    case SDR_TAP_DEMOD: rows = p->demod.p + p->HD; stride = p->demod_stride; n = p->last_n_if; break;
+    case SDR_TAP_AUDIO_FILT: rows = p->t_audio.p; stride = p->tap_audio_stride; n = p->last_n_audio; Fs = (float)p->m.audio_Fs; break;
+    case SDR_TAP_STEREO_FINAL:
+      if (p->stereo) { rows = p->t_stfinal.p; stride = p->tap_audio_stride; n = p->last_n_audio; Fs = (float)p->m.audio_Fs; }
+      break;
+    case SDR_TAP_CARRIER_FILT: if (p->stereo) { rows = p->car.p; stride = p->car_stride; n = p->last_n_if; } break;
+    case SDR_TAP_STEREO_FILT: if (p->stereo) { rows = p->stf.p + p->HA; stride = p->stf_stride; n = p->last_n_if; } break;
+    case SDR_TAP_NCO: if (p->stereo) { rows = p->t_nco.p; stride = p->tap_if_stride; n = p->last_n_if; } break;
+    case SDR_TAP_MIXER: if (p->stereo) { rows = p->mix.p + p->HA; stride = p->stf_stride; n = p->last_n_if; } break;
+    case SDR_TAP_ALLPASS: if (p->stereo) { rows = p->t_allpass.p; stride = p->tap_if_stride; n = p->last_n_if; } break;
+    default: return fail(SDR_ERR_INVALID, "unknown tap stage");
+  }
+  if (!rows) return fail(SDR_ERR_INVALID, "stereo-only tap");
+  const size_t B = (size_t)p->cfg.batch, segs = n / 512;
+  if (!segs) return fail(SDR_ERR_INVALID, "the last call is shorter than one 512-sample PSD segment");
+  DevBuf<float> db, out;
+  int rc;
+  if ((rc = db.alloc(B * segs * 256)) || (rc = out.alloc(B * 256))) return rc;
+  SDR_CUDA(cudaDeviceSynchronize());
+  if ((rc = psd_device(p->cfg.device, rows, B, stride, n, Fs, db.p, out.p, nullptr))) return rc;
+  SDR_CUDA(cudaMemcpy(psd, out.p, B * 256 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (freq) psd_freq_axis(Fs, freq);
+  return SDR_OK;
+}
+
 extern "C" int sdr_pipeline_copy_state(sdr_pipeline *p, int dst, int src) {
   if (!p) return fail(SDR_ERR_INVALID, "null pipeline");
   if (dst < 0 || src < 0 || dst >= p->cfg.batch || src >= p->cfg.batch)

@@ -24,6 +24,10 @@
 //                                     smallest span that is whole in both block sizes.
 //            --rds-carry              with --rds: carry the clock-recovery state from block to block
 //                                     (sdr_rds_config.cdr_carry) instead of re-creating it per block
+//            --deemphasis US          apply the de-emphasis the course spec skipped (time constant in
+//                                     microseconds: 75 in the Americas, 50 elsewhere) to the PCM
+//            --wav FILE               also write the PCM to FILE as RIFF/WAVE (stdout is unchanged:
+//                                     pipe it to aplay, there is no ALSA in this build)
 //            --batch B [--devices N]  B independent captures at once, spread over N devices (default:
 //                                     all) by sdr_multi_*.  stdin then carries, per device call, B
 //                                     consecutive chunks of (--blocks x block_size) bytes, one per
@@ -62,7 +66,7 @@ int die(const char *what) {
 
 void usage(const char *argv0) {
   std::fprintf(stderr,
-               "Usage: %s\nor\nUsage: %s <mode> [<channels>] [--taps rf,audio,stereo] [--blocks N] [--device D] [--rds FILE [--rds-carry]] [--batch B [--devices N]]\n"
+               "Usage: %s\nor\nUsage: %s <mode> [<channels>] [--taps rf,audio,stereo] [--blocks N] [--device D] [--rds FILE [--rds-carry]] [--batch B [--devices N]] [--deemphasis US] [--wav FILE]\n"
                "\t\t <mode> is a value from 0 to 3, <channels> is 1 (mono) or 2 (stereo)\n",
                argv0, argv0);
 }
@@ -73,8 +77,9 @@ int main(int argc, char *argv[]) {
   int mode = 0, channels = 1, device = 0, blocks = 1, batch = 1, devices = 0;
   int rf_taps = 151, audio_taps = 101, stereo_taps = 151;
   std::vector<std::string> pos;
-  std::string rds_path;
+  std::string rds_path, wav_path;
   bool rds_carry = false;
+  double deemph_us = 0.0;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "--taps" && i + 1 < argc) {
@@ -86,6 +91,10 @@ int main(int argc, char *argv[]) {
       blocks = std::atoi(argv[++i]);
     } else if (a == "--device" && i + 1 < argc) {
       device = std::atoi(argv[++i]);
+    } else if (a == "--wav" && i + 1 < argc) {
+      wav_path = argv[++i];
+    } else if (a == "--deemphasis" && i + 1 < argc) {
+      deemph_us = std::atof(argv[++i]);
     } else if (a == "--batch" && i + 1 < argc) {
       batch = std::atoi(argv[++i]);
     } else if (a == "--devices" && i + 1 < argc) {
@@ -101,7 +110,8 @@ int main(int argc, char *argv[]) {
       pos.push_back(a);
     }
   }
-  if (pos.size() > 2 || blocks < 1 || batch < 1 || devices < 0 || (batch > 1 && !rds_path.empty())) {
+  if (pos.size() > 2 || blocks < 1 || batch < 1 || devices < 0 || (batch > 1 && !rds_path.empty()) || deemph_us < 0 ||
+      (batch > 1 && (!wav_path.empty() || deemph_us > 0))) {
     usage(argv[0]);
     return 1;
   }
@@ -191,6 +201,20 @@ int main(int argc, char *argv[]) {
   if (sdr_host_alloc(B * pcm_per_call * sizeof(int16_t), reinterpret_cast<void **>(&pcm)))
     return die("sdr_host_alloc");
 
+  sdr_deemph *deemph = nullptr;
+  if (deemph_us > 0 &&
+      sdr_deemph_create(device, 1, channels, (float)mi.audio_Fs, (float)(deemph_us * 1e-6), &deemph))
+    return die("sdr_deemph_create");
+  std::FILE *wav = nullptr;
+  if (!wav_path.empty()) {
+    wav = std::fopen(wav_path.c_str(), "wb");
+    uint8_t hdr[44];
+    if (!wav || sdr_wav_header(hdr, mi.audio_Fs, channels, 0) || std::fwrite(hdr, 1, 44, wav) != 44) {
+      std::perror(wav_path.c_str());
+      return 2;
+    }
+  }
+
   std::mutex mu;
   std::condition_variable cv;
   bool eof = false;
@@ -247,7 +271,12 @@ int main(int argc, char *argv[]) {
           break;
         }
       }
+      if (deemph && sdr_deemph_process_host(deemph, pcm, n_pcm, n_pcm / (size_t)channels)) {
+        rc = die("sdr_deemph_process_host");
+        break;
+      }
       std::fwrite(pcm, sizeof(int16_t), B * n_pcm, stdout);
+      if (wav) std::fwrite(pcm, sizeof(int16_t), n_pcm, wav);
       if (rds) {
         size_t n_bits = 0, n_blocks = 0;
         if (sdr_rds_read(rds, 0, nullptr, rds_bits.data(), rds_bits.size(), &n_bits, rds_counts.data(),
@@ -282,6 +311,14 @@ int main(int argc, char *argv[]) {
                total_out);
   for (auto &s : slots) sdr_host_free(s.data);
   sdr_host_free(pcm);
+  if (wav) {   // now that the length is known: the real header
+    uint8_t hdr[44];
+    sdr_wav_header(hdr, mi.audio_Fs, channels, total_out / (size_t)channels);
+    std::fseek(wav, 0, SEEK_SET);
+    std::fwrite(hdr, 1, 44, wav);
+    std::fclose(wav);
+  }
+  sdr_deemph_destroy(deemph);
   if (rds_out) std::fclose(rds_out);
   sdr_rds_destroy(rds);
   sdr_pipeline_destroy(pipe);

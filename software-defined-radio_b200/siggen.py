@@ -184,3 +184,30 @@ def make_batch(n_channels: int, mode: int, n_blocks: int, kind: str = "stereo",
         rot = 2 * ((c // distinct) * 977 % (src.size // 2))
         out[c] = np.roll(src, rot) if rot else src
     return out
+
+
+def make_wideband(n_channels: int, n_pairs_per_channel: int, tone_hz=None, fs_channel: float = 2.4e6,
+                  skip=()) -> tuple[np.ndarray, float]:
+    """One wideband capture (interleaved uint8 I/Q at n_channels * fs_channel) holding one mono FM
+    station per channel of an n_channels-band channeliser: station c sits c * fs_channel above the
+    centre (c >= n_channels/2: below it, the DFT's wrap) and carries a single tone of tone_hz[c]
+    (default 1000 + 400 c Hz) at 37.5 kHz deviation.  Returns (bytes, amplitude of one station)."""
+    M = n_channels
+    n = n_pairs_per_channel * M
+    fs = fs_channel * M
+    t = np.arange(n, dtype=np.float64) / fs
+    amp = 0.8 / M
+    x = np.zeros(n, np.complex128)
+    for c in range(M):
+        if c in skip:
+            continue
+        f_tone = (1000.0 + 400.0 * c) if tone_hz is None else tone_hz[c]
+        f_c = (c if c < M / 2 else c - M) * fs_channel
+        # phase of the carrier offset is exact per sample (f_c / fs is a multiple of 1/M)
+        dev = 37_500.0 / (2 * np.pi * f_tone) * (-np.cos(2 * np.pi * f_tone * t) + 1.0) * 2 * np.pi
+        k = (c if c < M / 2 else c - M)
+        x += amp * np.exp(1j * (dev + 2 * np.pi * ((k * np.arange(n)) % M) / M))
+    out = np.empty(2 * n, np.uint8)
+    out[0::2] = np.clip(np.rint(128 + 128 * x.real), 0, 255).astype(np.uint8)
+    out[1::2] = np.clip(np.rint(128 + 128 * x.imag), 0, 255).astype(np.uint8)
+    return out, amp
