@@ -374,10 +374,10 @@ def estimatePSD(samples, Fs: float, device: int = 0):
     x = np.ascontiguousarray(samples, np.float32)
     one = x.ndim == 1
     if one:
-        x = x[None, :]
+        x = x.reshape(1, -1)
     freq = np.zeros(256, np.float32)
     psd = np.zeros((x.shape[0], 256), np.float32)
-    _check(lib().sdr_psd(device, x.ctypes.data, x.shape[0], x.strides[0] // 4, x.shape[1], Fs,
+    _check(lib().sdr_psd(device, x.ctypes.data, x.shape[0], x.shape[1], x.shape[1], Fs,
                          freq.ctypes.data, psd.ctypes.data))
     return freq, (psd[0] if one else psd)
 
