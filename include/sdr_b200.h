@@ -302,7 +302,12 @@ typedef struct {
   int pll_form;           /* which form of the 114 kHz PLL kernel runs: SDR_RDS_PLL_AUTO picks by batch
                              size (a warp per capture up to 4096 captures, one lane per capture above);
                              both give the same result to 1e-9 (tests) */
+  int precision;          /* SDR_RDS_F64 (default: the model's arithmetic, parity <= 1e-9) or SDR_RDS_F32_FIR:
+                             the three FIR stages (channel / carrier band-pass, RRC) multiply and accumulate
+                             in single precision (RRC output within 1e-5 of the model, SURVEY 8c's bar) */
 } sdr_rds_config;
+#define SDR_RDS_F64 0
+#define SDR_RDS_F32_FIR 1
 #define SDR_RDS_PLL_AUTO 0
 #define SDR_RDS_PLL_LANE 1
 #define SDR_RDS_PLL_WARP 2

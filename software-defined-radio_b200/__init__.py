@@ -55,7 +55,7 @@ class ChannelizerConfig(C.Structure):
 
 class RdsConfig(C.Structure):
     _fields_ = [("block_if", C.c_int), ("max_pending_blocks", C.c_int), ("keep_nco", C.c_int),
-                ("cdr_carry", C.c_int), ("pll_form", C.c_int)]
+                ("cdr_carry", C.c_int), ("pll_form", C.c_int), ("precision", C.c_int)]
 
 
 class RdsInfo(C.Structure):
@@ -565,11 +565,11 @@ class Rds:
     process call of that pipeline, on the same stream."""
 
     def __init__(self, pipeline: Pipeline, block_if=0, max_pending_blocks=0, keep_nco=False,
-                 cdr_carry=False, pll_form="auto"):
+                 cdr_carry=False, pll_form="auto", f32_fir=False):
         self.pipeline = pipeline
         self._h = _vp()
         cfg = RdsConfig(block_if, max_pending_blocks, 1 if keep_nco else 0, 1 if cdr_carry else 0,
-                        {"auto": 0, "lane": 1, "warp": 2}[pll_form])
+                        {"auto": 0, "lane": 1, "warp": 2}[pll_form], 1 if f32_fir else 0)
         _check(lib().sdr_rds_create(pipeline._h, C.byref(cfg), C.byref(self._h)))
         self.info = RdsInfo()
         _check(lib().sdr_rds_info(self._h, C.byref(self.info)))

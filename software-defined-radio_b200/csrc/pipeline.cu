@@ -568,10 +568,10 @@ static bool build_resample_tc(sdr_pipeline *p, std::vector<uint8_t> &tiles) {
           const double v = std::ldexp((double)p->h_poly[(size_t)phase * TA + tap] * (1.0 + U), S);
           const __half hh = __float2half_rn((float)v);
           const __half hl = __float2half_rn((float)(v - (double)__half2float(hh)));
-          // [half][chunk kc][output o][8 halfs]
-          const size_t at = ((size_t)(k / 8) * RT_NB + o) * 8 + (k % 8);
+          // [chunk kc][row: hh of output o | hl of output o at 16 + o][8 halfs]
+          const size_t at = ((size_t)(k / 8) * RT_NC + o) * 8 + (k % 8);
           tile[at] = __half_as_ushort(hh);
-          tile[(size_t)(RT_SLAB / 8) * RT_NB * 8 + at] = __half_as_ushort(hl);
+          tile[at + (size_t)RT_NB * 8] = __half_as_ushort(hl);
         }
       }
     }

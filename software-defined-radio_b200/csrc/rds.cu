@@ -52,9 +52,9 @@ constexpr int RDS_HS = 104;  // resampler-output history prefix: the RRC reaches
 constexpr int RDS_DELAY = (RDS_T - 1) / 2;  // fmRDS.py:178 state_rds_allpass
 constexpr int RDS_CDR_START = 158;          // fmRDS.py:259 start_init
 
-template <int T>
+template <int T, typename E = double>
 struct DTaps {
-  double h[T];
+  E h[T];
 };
 
 // ---------------------------------------------------------------------------
@@ -77,14 +77,18 @@ struct RdsFirArgs {
   int outs_per_seg;
 };
 
-// INMODE 0: float input with a separate history; 1: double input, squared; 2: double input
-template <int T, int R, int NT, int INMODE>
+// INMODE 0: float input with a separate history; 1: double input, squared; 2: double input.
+// E = double is the model's arithmetic.  E = float (sdr_rds_config.precision = SDR_RDS_F32_FIR) keeps
+// rows and taps' values but multiplies and accumulates in single precision: the experiment the
+// survey's parity bar allows ("f32 GPU vs f64 model", RRC output <= 1e-5) -- see DESIGN.md 4b for
+// what it buys and what it costs.
+template <int T, int R, int NT, int INMODE, typename E = double>
 __global__ void __launch_bounds__(NT)
-k_rds_fir(const RdsFirArgs a, const __grid_constant__ DTaps<T> taps) {
+k_rds_fir(const RdsFirArgs a, const __grid_constant__ DTaps<T, E> taps) {
   constexpr int HALO = ((T - 1 + R - 1) / R) * R;
   constexpr int TILE = NT * R;
   constexpr int WIN = HALO + TILE;
-  __shared__ double xs[WIN + WIN / R + 1];
+  __shared__ E xs[WIN + WIN / R + 1];
   const int t = threadIdx.x;
   const int b = blockIdx.y;
   const int z = blockIdx.z;
@@ -108,18 +112,18 @@ k_rds_fir(const RdsFirArgs a, const __grid_constant__ DTaps<T> taps) {
           if (INMODE == 1) v = __dmul_rn(v, v);  // fmRDS.py:230
         }
       }
-      xs[q + q / R] = v;
+      xs[q + q / R] = (E)v;
     }
     __syncthreads();
-    double acc[R];
+    E acc[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = 0.0;
-    const double *w = xs + (t * R + HALO) + (t * R + HALO) / R;
+    for (int r = 0; r < R; ++r) acc[r] = (E)0;
+    const E *w = xs + (t * R + HALO) + (t * R + HALO) / R;
 #pragma unroll
     for (int c = R - 1; c >= -(T - 1); --c) {
       // window slot of sample (output 0 of this thread) + c, with the group padding
       const int off = c + (c >= 0 ? c / R : -((-c + R - 1) / R));
-      const double v = w[off];
+      const E v = w[off];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int k = r - c;
@@ -129,7 +133,7 @@ k_rds_fir(const RdsFirArgs a, const __grid_constant__ DTaps<T> taps) {
     const int o = o0 + t * R;
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      if (o + r < o_end) drow[o + r] = acc[r];
+      if (o + r < o_end) drow[o + r] = (double)acc[r];
   }
 }
 
@@ -923,6 +927,9 @@ struct sdr_rds {
   size_t chan_stride = 0, carr_stride = 0, theta_stride = 0, mix_stride = 0, rs_stride = 0, rrc_stride = 0, nco_stride = 0;
   DTaps<RDS_T> h_chan{}, h_carr{};
   DTaps<RDS_TP> h_rrc{};
+  DTaps<RDS_T, float> h_chan32{}, h_carr32{};   // the same coefficients rounded to float (precision = SDR_RDS_F32_FIR)
+  DTaps<RDS_TP, float> h_rrc32{};
+  int precision = 0;
   RBuf<double> cdr_state, quad, chan, carr, theta, mixI, mixQ, rsI, rsQ, rrcI, rrcQ, ncoI, ncoQ, pll;
   RBuf<float> hist32;
   RBuf<uint8_t> bits;
@@ -1019,7 +1026,8 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     dim3 grid(segs_for(n, TILE, B, 1, &ops), B, 1);
     a.outs_per_seg = ops;
     sdr_prof_begin(p, "k_rds_fir_channel", s);
-    k_rds_fir<RDS_T, R, NT, 0><<<grid, NT, 0, s>>>(a, r->h_chan);
+    if (r->precision) k_rds_fir<RDS_T, R, NT, 0, float><<<grid, NT, 0, s>>>(a, r->h_chan32);
+    else k_rds_fir<RDS_T, R, NT, 0><<<grid, NT, 0, s>>>(a, r->h_chan);
     if ((rc = sdr_check_launch(p, "k_rds_fir_channel"))) return rc;
   }
   {  // R2
@@ -1034,7 +1042,8 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     dim3 grid(segs_for(n, TILE, B, 1, &ops), B, 1);
     a.outs_per_seg = ops;
     sdr_prof_begin(p, "k_rds_fir_carrier", s);
-    k_rds_fir<RDS_T, R, NT, 1><<<grid, NT, 0, s>>>(a, r->h_carr);
+    if (r->precision) k_rds_fir<RDS_T, R, NT, 1, float><<<grid, NT, 0, s>>>(a, r->h_carr32);
+    else k_rds_fir<RDS_T, R, NT, 1><<<grid, NT, 0, s>>>(a, r->h_carr);
     if ((rc = sdr_check_launch(p, "k_rds_fir_carrier"))) return rc;
   }
   {  // R3a
@@ -1118,7 +1127,8 @@ static int rds_process(sdr_rds *r, size_t n_if, cudaStream_t s) {
     dim3 grid(segs_for(n_out, TILE, B, 2, &ops), B, 2);
     a.outs_per_seg = ops;
     sdr_prof_begin(p, "k_rds_fir_rrc", s);
-    k_rds_fir<RDS_TP, R, NT, 2><<<grid, NT, 0, s>>>(a, r->h_rrc);
+    if (r->precision) k_rds_fir<RDS_TP, R, NT, 2, float><<<grid, NT, 0, s>>>(a, r->h_rrc32);
+    else k_rds_fir<RDS_TP, R, NT, 2><<<grid, NT, 0, s>>>(a, r->h_rrc);
     if ((rc = sdr_check_launch(p, "k_rds_fir_rrc"))) return rc;
   }
   {  // R6
@@ -1305,6 +1315,8 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
   r->keep_nco = cfg && cfg->keep_nco;
   r->cdr_carry = cfg && cfg->cdr_carry;
   r->pll_form = cfg ? cfg->pll_form : 0;
+  r->precision = cfg ? cfg->precision : 0;
+  if (r->precision < 0 || r->precision > 1) { delete r; return fail(SDR_ERR_INVALID, "unknown sdr_rds_config.precision"); }
   if (r->pll_form < 0 || r->pll_form > 2) { delete r; return fail(SDR_ERR_INVALID, "unknown sdr_rds_config.pll_form"); }
   auto up = [](size_t v) { return (v + 3) / 4 * 4; };
   r->chan_stride = up(RDS_HC + r->cap_if);
@@ -1323,6 +1335,11 @@ extern "C" int sdr_rds_create(sdr_pipeline *p, const sdr_rds_config *cfg, sdr_rd
   std::memcpy(r->h_chan.h, hc.data(), sizeof(r->h_chan.h));
   std::memcpy(r->h_carr.h, hk.data(), sizeof(r->h_carr.h));
   std::memcpy(r->h_rrc.h, hq.data(), sizeof(r->h_rrc.h));
+  for (int i = 0; i < RDS_T; ++i) {
+    r->h_chan32.h[i] = (float)hc[i];
+    r->h_carr32.h[i] = (float)hk[i];
+  }
+  for (int i = 0; i < RDS_TP; ++i) r->h_rrc32.h[i] = (float)hq[i];
   // Quad table of the resampler: for a quad whose first output has phase p0, output i has
   // phase (p0 + i*D) mod U and its newest input lies floor((p0 + i*D)/U) samples after that of
   // output 0; row r of the entry is the sample r steps before the newest input of output 3.

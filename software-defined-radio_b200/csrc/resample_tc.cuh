@@ -16,7 +16,7 @@
 // Precision.  fm_demod and the taps are split into two halves, x = xh + xl and h' = hh + hl
 // (h' = h * (1+U) * 2^S: the reference's output gain, filter.cpp:213, and a power-of-two scale that
 // puts the taps in the fp16 range are folded in), each half an fp16 with an 11-bit significand:
-//     y * 2^S = sum xh*hh + sum xh*hl + sum xl*hh            (xl*hl ~ 2^-22 relative is dropped)
+//     y * 2^S = sum xh*hh + sum xh*hl + sum xl*hh + sum xl*hl
 // Every product is exact in the fp32 accumulator; the result differs from the reference's
 // sequential float sum by ~1e-6 relative (tests: audio >= 100 dB, PCM +-1 LSB).  The front end
 // writes the two planes itself (rf_tc.cuh), so no conversion pass runs here.
@@ -25,11 +25,14 @@
 // the slabs its blocks touch in time order.  Per slab step the workers copy the slab of both
 // planes (2 x 8 KB, canonical no-swizzle K-major core-matrix layout: chunk kc of row r at
 // kc*2048 + r*16) and the tap tiles of the <= 4 blocks active at that slab (concatenated along N)
-// into one of NST stages with 16-byte asynchronous copies; one elected thread issues, for the
-// blocks already running, ONE MMA of N = 16 x (#blocks) per K step and operand pair, and for a
-// block that starts at this slab its own N = 16 MMAs (the first one overwrites the accumulator).
-// A block's accumulator (16 of 128 tensor-memory columns, a ring of 8 slots) is read back by the
-// workers one step after its last slab: scale, int16 conversion, PCM store.
+// into one of NST stages with 16-byte asynchronous copies.  A small MMA costs a fixed 68 cycles
+// whatever N <= 128 is (tools/ubench_umma_smalln.cu), so MMAs are made as wide as the schedule
+// allows: a block's tap tile holds hh and hl side by side (32 accumulator columns: sum x*hh and
+// sum x*hl, added in the read-back) and the tiles of all blocks active at a slab sit next to each
+// other, so ONE MMA per K step and plane (N = 32 x #blocks) serves them all: xh*[hh|hl] and
+// xl*[hh|hl] (which also brings the xl*hl term).  Every MMA accumulates; the workers clear an
+// accumulator (32 of 256 tensor-memory columns, a ring of 8 slots) right after reading it back,
+// one step after the block's last slab: add the two halves, scale, int16 conversion, PCM store.
 #pragma once
 
 #include "rf_tc.cuh"
@@ -45,10 +48,12 @@ constexpr int RT_NST = 4;             // pipeline stages (x 2 resident CTAs per 
 constexpr int RT_WORKERS = 256;
 constexpr int RT_BLOCK = RT_WORKERS + 64;   // + the MMA issue warp + the proxy-fence warp
 constexpr int RT_X_BYTES = 2 * (RT_SLAB / 8) * RT_ROWS * 16;           // both planes of one slab: 16 KB
-constexpr int RT_BROWS = RT_NB * RT_NACT;                              // 64 tap-tile rows per stage
-constexpr int RT_B_BYTES = 2 * (RT_SLAB / 8) * RT_BROWS * 16;          // hh and hl tiles: 8 KB
+constexpr int RT_NC = 2 * RT_NB;      // accumulator columns per block: sum x*hh | sum x*hl
+constexpr int RT_BROWS = RT_NC * RT_NACT;                              // 128 tap-tile rows per stage
+constexpr int RT_B_BYTES = (RT_SLAB / 8) * RT_BROWS * 16;              // [hh | hl] tiles of the active blocks: 8 KB
+constexpr int RT_TMEM_COLS = RT_SLOTS * RT_NC;                         // 256
 constexpr int RT_STAGE = RT_X_BYTES + RT_B_BYTES;
-constexpr int RT_TILE_BYTES = 2 * (RT_SLAB / 8) * RT_NB * 16;          // one (block, slab) tile in global memory: 2 KB
+constexpr int RT_TILE_BYTES = (RT_SLAB / 8) * RT_NC * 16;              // one (block, slab) tile in global memory: 2 KB
 constexpr int RT_MAX_SP = 128;        // slabs per period, at most (mode 3: 100)
 constexpr int RT_MAX_BLK = 64;        // blocks per period, at most (mode 3: 28)
 constexpr size_t rt_smem(int nst) { return (size_t)nst * RT_STAGE + 1024; }
@@ -71,7 +76,7 @@ struct ResampleTcArgs {
   const uint16_t *xh, *xl;            // [B][pl_stride] fp16 planes, sample 0 at pl_off (history before it)
   size_t pl_stride;
   int pl_off;
-  const uint8_t *tiles;               // [sum_b nslab_b][2 (hh, hl)][4 chunks][16 outputs][8 halfs]
+  const uint8_t *tiles;               // [sum_b nslab_b][4 chunks][32 rows: hh of 16 outputs, hl of 16 outputs][8 halfs]
   int16_t *pcm;                       // [B][pcm_stride]
   size_t pcm_stride;
   float *audio_filt;                  // optional [B][tap_stride]
@@ -115,13 +120,25 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tc_smem_u32(&tmem_slot)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "n"(RT_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = tmem_slot;
+  // every MMA accumulates: start from cleared accumulators (each worker warp clears its lane
+  // quarter of half of the columns)
+  if (warp < RT_WORKERS / 32) {
+    const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * (RT_TMEM_COLS / 2);
+#pragma unroll
+    for (int c = 0; c < RT_TMEM_COLS / 2; c += 8)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(base + c), "r"(0u));
+    asm volatile("tcgen05.wait::st.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
   // (registers: every asm with a memory clobber would otherwise make the compiler re-read them from shared memory)
   const int NBLK = tab.NBLK, SP = tab.SP, P_out = tab.P_out;
 
@@ -209,44 +226,43 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
           constexpr uint32_t HI = (128u >> 4) | (1u << 14);
           constexpr uint32_t A_LBO = ((uint32_t)(RT_ROWS * 16) >> 4) << 16, B_LBO = ((uint32_t)(RT_BROWS * 16) >> 4) << 16;
           constexpr uint32_t A_KS = (2 * RT_ROWS * 16) >> 4, A_PLANE = ((RT_SLAB / 8) * RT_ROWS * 16) >> 4;
-          constexpr uint32_t B_KS = (2 * RT_BROWS * 16) >> 4, B_HALF = ((RT_SLAB / 8) * RT_BROWS * 16) >> 4;
+          constexpr uint32_t B_KS = (2 * RT_BROWS * 16) >> 4;
           const uint32_t xs_lo = ((smem_u32 + (uint32_t)stage * RT_STAGE) >> 4) | A_LBO;
           const uint32_t bs_lo = ((smem_u32 + (uint32_t)stage * RT_STAGE + RT_X_BYTES) >> 4) | B_LBO;
-          // group the active blocks: consecutive accumulator slots with the same "accumulate" flag
-          // (entry i's tap tile sits at rows 16 i of the stage, its accumulator in slot lb % 8)
+          // a block that starts here takes over an accumulator slot: its previous tenant must have
+          // been read back (and cleared)
+#pragma unroll
+          for (int i = 0; i < RT_NACT; ++i)
+            if (e[i].valid && e[i].js == 0 && e[i].lb >= RT_SLOTS) {
+              mbar_wait(&acc_empty[e[i].lb % RT_SLOTS], ((e[i].lb / RT_SLOTS) - 1) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;");
+            }
+          // one MMA per K step and plane for every run of consecutive accumulator slots (entry i's
+          // tile sits at rows 32 i of the stage, its accumulator in slot lb % 8: a run ends where the
+          // ring of slots wraps)
 #pragma unroll
           for (int i = 0; i < RT_NACT; ++i) {
             if (!e[i].valid) continue;
-            const bool fresh = e[i].js == 0;
             const int slot0 = e[i].lb % RT_SLOTS;
-            if (i > 0 && e[i - 1].valid && !fresh && e[i - 1].js != 0 && slot0 != 0) continue;   // merged into the group before
-            if (fresh && e[i].lb >= RT_SLOTS) {   // the slot's previous tenant has been read back
-              mbar_wait(&acc_empty[slot0], ((e[i].lb / RT_SLOTS) - 1) & 1);
-              asm volatile("tcgen05.fence::after_thread_sync;");
-            }
+            if (i > 0 && e[i - 1].valid && slot0 != 0) continue;   // part of the run that started earlier
             int cnt = 1;
-            if (!fresh) {
 #pragma unroll
-              for (int k = 1; k < RT_NACT; ++k)
-                if (i + k < RT_NACT && cnt == k && e[(i + k) & (RT_NACT - 1)].valid && e[(i + k) & (RT_NACT - 1)].js != 0 &&
-                    slot0 + k < RT_SLOTS)
-                  cnt = k + 1;
-            }
-            const uint32_t idesc = idesc16 | ((uint32_t)((RT_NB * cnt) >> 3) << 17);
-            const uint32_t d = tmem + slot0 * RT_NB;
-            const uint32_t b_lo = bs_lo + (uint32_t)(i * RT_NB);   // 16 rows of 16 bytes = 16 address units
+            for (int k = 1; k < RT_NACT; ++k)
+              if (i + k < RT_NACT && cnt == k && e[(i + k) & (RT_NACT - 1)].valid && slot0 + k < RT_SLOTS) cnt = k + 1;
+            const uint32_t idesc = idesc16 | ((uint32_t)((RT_NC * cnt) >> 3) << 17);
+            const uint32_t d = tmem + slot0 * RT_NC;
+            const uint32_t b_lo = bs_lo + (uint32_t)(i * RT_NC);   // 32 rows of 16 bytes = 32 address units
 #pragma unroll
-            for (int seg = 0; seg < 3; ++seg) {           // (xh, hh), (xh, hl), (xl, hh)
+            for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t a_lo = xs_lo + (seg == 2 ? A_PLANE : 0) + ks * A_KS;
-                const uint32_t bb_lo = b_lo + (seg == 1 ? B_HALF : 0) + ks * B_KS;
-                const uint32_t acc = (fresh && seg == 0 && ks == 0) ? 0u : 1u;
+              for (int plane = 0; plane < 2; ++plane) {      // xh, xl
+                const uint32_t a_lo = xs_lo + plane * A_PLANE + ks * A_KS;
+                const uint32_t bb_lo = b_lo + ks * B_KS;
                 asm volatile(
-                    "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+                    "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %4};\nmov.b64 db, {%2, %4};\n"
                     "setp.ne.b32 p, %4, 0;\n"
                     "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n" ::"r"(d),
-                    "r"(a_lo), "r"(bb_lo), "r"(idesc), "r"(acc), "r"(HI));
+                    "r"(a_lo), "r"(bb_lo), "r"(idesc), "r"(HI));
               }
             }
           }
@@ -317,14 +333,14 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
                          "l"(src + row_off[i])
                          : "memory");
           const uint32_t bdst = tc_smem_u32(xs) + RT_X_BYTES;
-          // tile chunk w = (half * 4 + kc) * 16 + o  ->  stage offset ((half * 4 + kc) * BROWS + 16 a + o) * 16;
+          // tile chunk w = kc * 32 + row  ->  stage offset (kc * BROWS + 32 a + row) * 16;
           // a thread copies chunk w = tid % 128 of entries a = tid / 128 and a + 2
-          const int w = tid & (RT_TILE_BYTES / 16 - 1), hk = w / RT_NB, o = w % RT_NB;
+          const int w = tid & (RT_TILE_BYTES / 16 - 1), wk = w / RT_NC, wr = w % RT_NC;
 #pragma unroll
           for (int a = 0; a < RT_NACT; ++a) {
             if ((a & 1) != (tid >> 7) || !e[a].valid) continue;
             const uint8_t *tsrc = g.tiles + (size_t)e[a].tile * RT_TILE_BYTES + (size_t)w * 16;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bdst + (hk * RT_BROWS + a * RT_NB + o) * 16),
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bdst + (wk * RT_BROWS + a * RT_NC + wr) * 16),
                          "l"(tsrc)
                          : "memory");
           }
@@ -353,11 +369,19 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
           const int lb = e[k].lb, slot = lb % RT_SLOTS;
           mbar_wait(&acc_full[slot], (lb / RT_SLOTS) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;");
-          uint32_t v[8];
+          uint32_t v[8], u[8];
+          const uint32_t tcol = tmem + tlane + slot * RT_NC + half * 8;
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                       : "r"(tmem + tlane + slot * RT_NB + half * 8));
+                       : "r"(tcol));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                       : "r"(tcol + RT_NB));
           asm volatile("tcgen05.wait::ld.sync.aligned;");
+          // clear both halves for the slot's next tenant (every MMA accumulates)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(tcol), "r"(0u));
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(tcol + RT_NB), "r"(0u));
+          asm volatile("tcgen05.wait::st.sync.aligned;");
           asm volatile("tcgen05.fence::before_thread_sync;");
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&acc_empty[slot])) : "memory");
           if (ocap < g.batch) {
@@ -369,7 +393,7 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
             int16_t s[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              y[i] = __fmul_rn(__uint_as_float(v[i]), g.out_scale);
+              y[i] = __fmul_rn(__fadd_rn(__uint_as_float(v[i]), __uint_as_float(u[i])), g.out_scale);
               s[i] = pcm16(y[i]);
             }
             if (nv == 8 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
@@ -416,7 +440,7 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(RT_TMEM_COLS));
 }
 
 }  // namespace sdr
