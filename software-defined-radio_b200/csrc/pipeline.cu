@@ -116,6 +116,7 @@ struct sdr_pipeline {
   RtTables rt_tab{};
   DevBuf<uint8_t> d_rt_tiles;
   DevBuf<uint16_t> xh, xl;
+  CUtensorMap map_h{}, map_l{};   // the planes as 2-D tensors [capture][time] for the resampler's TMA copies
   size_t pl_stride = 0;
   int pl_off = 0;
   float rt_out_scale = 0.0f;
@@ -500,6 +501,33 @@ static int alloc_tap_buffers(sdr_pipeline *p) {
   return SDR_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only).
+static int make_plane_map(CUtensorMap *map, const uint16_t *base, size_t stride_halfs, size_t rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return fail(SDR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)stride_halfs, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride_halfs * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)RT_SLAB, (cuuint32_t)RT_ROWS};   // 32 samples (64 B) x 128 captures
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t *>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SDR_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return SDR_OK;
+}
+
 // Period tables and tap tiles of the tensor-core resampler (resample_tc.cuh).  Returns false when
 // the mode's geometry does not fit the kernel (the quad resampler then stays in charge).
 static bool build_resample_tc(sdr_pipeline *p, std::vector<uint8_t> &tiles) {
@@ -530,7 +558,6 @@ static bool build_resample_tc(sdr_pipeline *p, std::vector<uint8_t> &tiles) {
   // the schedule: which blocks meet slab position q (at most RT_NACT; a block has long finished when
   // its accumulator slot comes round again: RT_SLOTS = 2 * RT_NACT)
   std::memset(t.sched, 0, sizeof t.sched);
-  std::memset(t.tile, 0, sizeof t.tile);
   std::memset(t.any_last, 0, sizeof t.any_last);
   for (int q = 0; q < t.SP; ++q) {
     int n = 0;
@@ -539,7 +566,6 @@ static bool build_resample_tc(sdr_pipeline *p, std::vector<uint8_t> &tiles) {
         const int qq = q - dp * t.SP;
         if (qq < t.qs[b] || qq > t.qe[b]) continue;
         if (n == RT_NACT || t.qe[b] - t.qs[b] > 255) return false;
-        t.tile[q][n] = (uint32_t)(t.tile0[b] + qq - t.qs[b]);
         if (qq == t.qe[b]) t.any_last[q] = 1;
         t.sched[q][n++] = (uint32_t)b | ((uint32_t)(qq - t.qs[b]) << 8) | ((uint32_t)dp << 16) |
                           ((uint32_t)(qq == t.qe[b]) << 17) | (1u << 18);
@@ -553,29 +579,42 @@ static bool build_resample_tc(sdr_pipeline *p, std::vector<uint8_t> &tiles) {
   while (S < 40 && std::ldexp(hmax, S + 1) < 8192.0) ++S;
   while (S > -40 && std::ldexp(hmax, S) >= 8192.0) --S;
   p->rt_out_scale = (float)std::ldexp(1.0, -S);
+  // tap tiles, stored per slab position q with the tiles of the blocks active there side by side:
+  // [chunk kc][32 rows per entry: hh of its 16 outputs, then hl][8 halfs]
   tiles.assign((size_t)n_tiles * RT_TILE_BYTES, 0);
-  for (int b = 0; b < t.NBLK; ++b) {
-    for (int js = 0; js <= t.qe[b] - t.qs[b]; ++js) {
-      uint16_t *tile = reinterpret_cast<uint16_t *>(tiles.data() + (size_t)(t.tile0[b] + js) * RT_TILE_BYTES);
+  std::memset(t.nact, 0, sizeof t.nact);
+  std::memset(t.bq_off, 0, sizeof t.bq_off);
+  int placed = 0;
+  for (int q = 0; q < t.SP; ++q) {
+    int n = 0;
+    while (n < RT_NACT && (t.sched[q][n] >> 18)) ++n;
+    t.nact[q] = (uint32_t)n;
+    t.bq_off[q] = (uint32_t)placed;
+    uint16_t *blk = reinterpret_cast<uint16_t *>(tiles.data() + (size_t)placed * RT_TILE_BYTES);
+    for (int i = 0; i < n; ++i) {
+      const uint32_t w = t.sched[q][i];
+      const int b = (int)(w & 0xff), js = (int)((w >> 8) & 0xff);
       for (int o = 0; o < RT_NB; ++o) {
         const int j = b * RT_NB + o;
         if (j >= t.P_out) continue;
         const long long m = (long long)j * D;
         const int phase = (int)(m % U), i0 = (int)(m / U);
         for (int k = 0; k < RT_SLAB; ++k) {
-          const int i = RT_SLAB * (t.qs[b] + js) + k, tap = i0 - i;
+          const int in = RT_SLAB * (t.qs[b] + js) + k, tap = i0 - in;
           if (tap < 0 || tap >= TA) continue;
           const double v = std::ldexp((double)p->h_poly[(size_t)phase * TA + tap] * (1.0 + U), S);
           const __half hh = __float2half_rn((float)v);
           const __half hl = __float2half_rn((float)(v - (double)__half2float(hh)));
-          // [chunk kc][row: hh of output o | hl of output o at 16 + o][8 halfs]
-          const size_t at = ((size_t)(k / 8) * RT_NC + o) * 8 + (k % 8);
-          tile[at] = __half_as_ushort(hh);
-          tile[at + (size_t)RT_NB * 8] = __half_as_ushort(hl);
+          const size_t row = (size_t)i * RT_NC + o;
+          const size_t at = ((size_t)(k / 8) * (size_t)(RT_NC * n) + row) * 8 + (k % 8);
+          blk[at] = __half_as_ushort(hh);
+          blk[at + (size_t)RT_NB * 8] = __half_as_ushort(hl);
         }
       }
     }
+    placed += n;
   }
+  if (placed != n_tiles) return false;
   p->pl_off = -t.qmin * RT_SLAB;
   p->pl_stride = (size_t)round_up((int)(p->pl_off + p->cap_if + RT_SLAB), 8);
   return true;
@@ -676,7 +715,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     cudaFuncSetAttribute(k_rf_demod_tc<10>, at, (int)TcCfg<10>::SMEM);
     cudaFuncSetAttribute(k_rf_demod_tc<5>, at, (int)TcCfg<5>::SMEM);
     cudaFuncSetAttribute(k_rf_demod_tc<3>, at, (int)TcCfg<3>::SMEM);
-    cudaFuncSetAttribute(k_audio_resample_tc<RT_NST, 2, true>, at, (int)rt_smem(RT_NST));
+    cudaFuncSetAttribute(k_audio_resample_tc<RT_NST, 2>, at, (int)rt_smem(RT_NST));
     cudaFuncSetAttribute(k_audio_resample_v5<true, 2>, at, big);
     cudaFuncSetAttribute(k_audio_resample_v5<false, 2>, at, big);
     cudaFuncSetAttribute(k_audio_resample_v4<true, 101, 5, true>, at, big);
@@ -831,6 +870,8 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
     TRY(p->d_rt_tiles.alloc(rt_tiles.size()));
     TRY(p->xh.alloc(B * p->pl_stride));
     TRY(p->xl.alloc(B * p->pl_stride));
+    TRY(make_plane_map(&p->map_h, p->xh.p, p->pl_stride, B));
+    TRY(make_plane_map(&p->map_l, p->xl.p, p->pl_stride, B));
     rc = cudaMemcpy(p->d_rt_tiles.p, rt_tiles.data(), rt_tiles.size(), cudaMemcpyHostToDevice) == cudaSuccess
              ? SDR_OK
              : SDR_ERR_CUDA;
@@ -1076,9 +1117,6 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
     prof_begin(p, "k_audio_resample", s);
     if (rs_tc) {
       ResampleTcArgs t{};
-      t.xh = p->xh.p;
-      t.xl = p->xl.p;
-      t.pl_stride = p->pl_stride;
       t.pl_off = p->pl_off;
       t.tiles = p->d_rt_tiles.p;
       t.pcm = d_pcm;
@@ -1091,7 +1129,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
       const int row_tiles = (B + RT_ROWS - 1) / RT_ROWS;
       const int total_blocks = t.n_periods * p->rt_tab.NBLK;
       t.ctas_per_tile = std::max(1, std::min(total_blocks, (2 * p->n_sm) / row_tiles));
-      k_audio_resample_tc<RT_NST, 2, true><<<row_tiles * t.ctas_per_tile, RT_BLOCK, rt_smem(RT_NST), s>>>(t, p->rt_tab);
+      k_audio_resample_tc<RT_NST, 2><<<row_tiles * t.ctas_per_tile, RT_BLOCK, rt_smem(RT_NST), s>>>(t, p->rt_tab, p->map_h, p->map_l);
     } else if (p->audio_kernel == sdr_pipeline::AK_RS_QUAD) {
       ResampleQuadArgs q{aa, p->d_h_quad.p, p->m.audio_upsamp, p->m.audio_decim, p->TA, p->quad_kb, (int)n_if};
       dim3 grid(((int)n_audio + RQ_J - 1) / RQ_J, (B + 63) / 64);
