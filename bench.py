@@ -263,6 +263,8 @@ def pick_variant(sdr, args, mode, audio_channels):
         return sdr.VARIANT_FAST, "fast"
     if args.variant == "mixed":
         return sdr.VARIANT_MIXED, "mixed"
+    if args.variant == "exact_scalar":   # A/B: the FMUL + FADD form of the exact FIR kernels (same bits)
+        return sdr.VARIANT_EXACT | sdr.VARIANT_SCALAR_FIR, "exact"
     return sdr.VARIANT_EXACT, "exact"
 
 
@@ -524,10 +526,11 @@ def other_config_list(args, world):
                  dict(base, mode=2, audio_channels=1, variant="exact")),
                 ("stereo_mode0_1024", "configs[2]: stereo, 1024 captures (the PLL's 32 warps cannot fill the GPU)",
                  dict(base, mode=0, audio_channels=2, variant="exact"))]
-    lst += [("stereo_mode0_fill", "configs[2] shaped to fill the GPU: 16384 captures x 4 blocks, bit-exact",
-             dict(base, mode=0, audio_channels=2, variant="exact", batch=16384, blocks=4)),
+    lst += [("stereo_mode0_fill", "configs[2] shaped to fill the GPU: 32768 captures x 2 blocks (two PLL warps per "
+                                  "scheduler), bit-exact",
+             dict(base, mode=0, audio_channels=2, variant="exact", batch=32768, blocks=2)),
             ("stereo_mode0_fill_mixed", "same shape, SDR_VARIANT_MIXED (PLL chain exact, other filters contracted, PCM +-1 LSB)",
-             dict(base, mode=0, audio_channels=2, variant="mixed", batch=16384, blocks=4)),
+             dict(base, mode=0, audio_channels=2, variant="mixed", batch=32768, blocks=2)),
             ("mixed_8192", f"configs[3]: 8192 captures (half mono fast, half stereo exact) over {world} GPU(s), "
                            f"{8192 // world} per GPU, two pipeline handles on two streams",
              dict(base, mode=0, audio_channels=1, mixed=True, streams=2, batch=8192 // world, blocks=4))]
@@ -699,7 +702,7 @@ def main():
                     help="half of the handles mono, half stereo (BASELINE configs[3]); needs --streams >= 2")
     ap.add_argument("--rds", action="store_true",
                     help="also run the RDS chain (modes 0/2) behind every step; not the default workload")
-    ap.add_argument("--variant", default="fast", choices=["fast", "exact", "mixed"],
+    ap.add_argument("--variant", default="fast", choices=["fast", "exact", "mixed", "exact_scalar"],
                     help="fast: tensor-core RF front end (mono, +-1 LSB PCM); exact: bit-identical CUDA-core path; "
                          "mixed: exact in front of the PLL, contracted multiply-adds elsewhere (+-1 LSB PCM)")
     args = ap.parse_args()

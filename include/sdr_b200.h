@@ -56,6 +56,11 @@ extern "C" {
  * resampling filters) contract each multiply-add into one FMA.  fm_demod, carrier_filt and the
  * NCO are bit-identical, the other float intermediates agree to >= 100 dB and PCM to +-1 LSB. */
 #define SDR_VARIANT_MIXED 2
+/* Flag, OR-ed into a variant: run the exact 151-tap FIR kernels (RF front end, stereo band-pass
+ * pair) in their scalar form (FMUL + FADD per tap) instead of the packed one (FMUL2 + FFMA2 on
+ * register pairs).  Same bits either way; kept so that the two forms can be checked against each
+ * other and timed side by side. */
+#define SDR_VARIANT_SCALAR_FIR 0x100
 
 /* Intermediate signals that sdr_pipeline_tap can return (same numbering as the
  * oracle, oracle/fm_oracle.h).  Names follow src/project.cpp's variables. */

@@ -24,6 +24,7 @@ TAP_NAMES = ["i_filt", "q_filt", "demod", "allpass", "stereo_filt", "carrier_fil
 VARIANT_EXACT = 0
 VARIANT_FAST = 1
 VARIANT_MIXED = 2
+VARIANT_SCALAR_FIR = 0x100   # flag: scalar form of the exact FIR kernels (same bits; for cross-checks)
 
 
 class SdrError(RuntimeError):

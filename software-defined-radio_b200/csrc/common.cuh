@@ -25,6 +25,34 @@ __device__ __forceinline__ float xmac(float acc, float h, float x) {
   return __fadd_rn(acc, __fmul_rn(h, x));
 }
 
+// Two lanes of the same two-rounding multiply-add in one instruction pair (sm_100a FMUL2 + FFMA2):
+// the product is rounded by mul.rn.f32x2, the sum by an fma whose multiplier is a RUN-TIME 1.0
+// (p*1 is exact, so the fma rounds p + acc once).  ptxas contracts an explicit mul.rn.f32x2 /
+// add.rn.f32x2 pair into one FFMA2 (seen with CUDA 12.9, -fmad=false or not), which would drop the
+// product's rounding; it cannot contract through a multiplier it does not know.  Each lane is
+// bit-identical to xmac; the pair takes two issue slots instead of four
+// (tools/ubench_f32x2_issue.cu).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) {
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t xmac2(f32x2_t acc, f32x2_t h, f32x2_t x, f32x2_t one) {
+  f32x2_t p;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(h), "l"(x));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc) : "l"(p), "l"(one), "l"(acc));
+  return acc;
+}
+// contracted pair (FAST / MIXED only)
+__device__ __forceinline__ f32x2_t fma2(f32x2_t acc, f32x2_t h, f32x2_t x) {
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc) : "l"(h), "l"(x), "l"(acc));
+  return acc;
+}
+
 // (u8 - 128) as an exact float without an integer->float conversion: the byte is
 // placed in the low mantissa bits of 2^23 and the bias is subtracted.
 __device__ __forceinline__ float u8_centered(uint32_t byte) {

@@ -206,6 +206,66 @@ __device__ __forceinline__ void fir_groups2(const float *__restrict__ w,
   }
 }
 
+// Packed form of fir_groups2 (both filters exact): accumulator pair (A_r, B_r), tap pair
+// (hA[n], hB[n]) from the constant bank, the input sample broadcast to both lanes; one
+// FMUL2 + FFMA2 per tap and output where the scalar form issues four instructions.
+template <int N>
+struct TapPairs {
+  float2 h[N];
+};
+template <int T, int D, int R>
+__device__ __forceinline__ void fir_groups2_packed(const float *__restrict__ w,
+                                                   const TapPairs<taps_groups(T, D, R)> &taps,
+                                                   f32x2_t (&acc)[R], f32x2_t one) {
+  constexpr int G = R * D;
+  constexpr int STRIDE = G + fir_pad(G);
+  constexpr int NG = fir_groups_count(T, D, R);
+  static_assert(G % 4 == 0, "group must keep float4 alignment");
+  float xb[R][D];
+  {
+    constexpr int NCH = (D * (R - 1)) / 4 + 1;
+    float own[NCH * 4];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const float4 v = *reinterpret_cast<const float4 *>(w + 4 * c);
+      own[4 * c] = v.x; own[4 * c + 1] = v.y; own[4 * c + 2] = v.z; own[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int b = 1; b < R; ++b)
+#pragma unroll
+      for (int j = 0; j < D; ++j) xb[b][j] = own[D * b - j];
+  }
+#pragma unroll 1
+  for (int p = 0; p < NG / R; ++p) {
+    const float *base = w - p * STRIDE;
+    const float2 *hp = taps.h + p * G;
+    float xv[G + 4];
+#pragma unroll
+    for (int c = 0; c < G / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4 *>(base - STRIDE + 4 * c);
+      xv[4 * c] = v.x; xv[4 * c + 1] = v.y; xv[4 * c + 2] = v.z; xv[4 * c + 3] = v.w;
+    }
+    {
+      const float4 v = *reinterpret_cast<const float4 *>(base);
+      xv[G] = v.x; xv[G + 1] = v.y; xv[G + 2] = v.z; xv[G + 3] = v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) xb[(R - c) % R][j] = xv[G - D * c - j];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const f32x2_t h2 = pack2(hp[D * c + j].x, hp[D * c + j].y);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float x = xb[(r - c + R) % R][j];
+          acc[r] = xmac2(acc[r], h2, pack2(x, x), one);
+        }
+      }
+    }
+  }
+}
+
 // Geometry of one padded shared-memory row holding tile samples [-HALO, TILE_IN).
 template <int D, int R, int NT, int HALO>
 struct RowGeom {
@@ -252,6 +312,7 @@ struct RfArgs {
   size_t pl_stride;
   int pl_off;
   int write_f32;           // 0: the planes replace the float row (nobody else reads fm_demod)
+  float one;               // 1.0f, known only at run time (xmac2's multiplier; see common.cuh)
 };
 
 template <int T, int D>
@@ -383,6 +444,182 @@ k_rf_demod(const RfArgs a, const __grid_constant__ TapArray<RfCfg<T, D, R, NT, A
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {  // exact power-of-two scaling: (u8-128)/128
+      ai[r] = xmul(ai[r], 0.0078125f);
+      aq[r] = xmul(aq[r], 0.0078125f);
+    }
+    edge_i[t + 1] = ai[R - 1];
+    edge_q[t + 1] = aq[R - 1];
+    __syncthreads();
+    float pi = edge_i[t], pq = edge_q[t];
+    const int o = o0 + t * R;
+    float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (o + r < o_end) {
+        drow[o + r] = fm_demod_one(ai[r], aq[r], pi, pq);
+        if (a.i_filt) {
+          a.i_filt[(size_t)b * a.tap_stride + o + r] = ai[r];
+          a.q_filt[(size_t)b * a.tap_stride + o + r] = aq[r];
+        }
+        if (o + r == a.n_if - 1) {
+          a.prev_out[2 * b] = ai[r];
+          a.prev_out[2 * b + 1] = aq[r];
+        }
+      }
+      pi = ai[r];
+      pq = aq[r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1, packed form (the exact variant's default for the 151-tap filter).  I and Q of a sample
+// sit side by side in shared memory and in one 64-bit register pair; each tap is applied to both
+// with xmac2 (FMUL2 + FFMA2, the tap a broadcast uniform-register operand), so the
+// separately rounded multiply-adds of an output's I and Q take 302 issue slots instead of 604
+// and the tap loads are shared by the two components.  Per lane the arithmetic is xmac's:
+// bit-identical to k_rf_demod (tests run both against the oracle).  Four outputs per thread: the
+// window walk at two per thread ran the shared-memory data pipe at 93 % of its wavefront peak
+// (each staged pair is re-read by ~8 threads); at four it is 74 %, level with the FP32 pipe.
+// ---------------------------------------------------------------------------
+template <int D, int R, int NT, int HALO>
+struct RowGeomIQ {   // positions in I/Q PAIRS (8 bytes); one LDS.128 = 2 pairs
+  static constexpr int G = R * D;
+  static_assert(G % 2 == 0 && HALO % 2 == 0, "a 16-byte unit must not straddle two threads' groups");
+  static constexpr int PAD = ((G / 2) % 2 == 1) ? 0 : 2;   // per-thread stride in 16-byte units is odd
+  static constexpr int HALO_G = (HALO + G - 1) / G;
+  static constexpr int ORIGIN = HALO_G * (G + PAD);
+  static constexpr int PAIRS = round_up(ORIGIN + NT * (G + PAD) + 4, 2);
+  __device__ static __forceinline__ int pos(int a) {
+    const int ap = a + HALO_G * G;
+    return ap + PAD * (ap / G);
+  }
+  static constexpr int off(int e) { return e + PAD * floordiv(e, G); }   // relative to a thread's own group
+  __device__ static __forceinline__ int thread_base(int t) { return ORIGIN + t * (G + PAD); }
+};
+
+template <int T, int D, int R, int NT>
+struct RfIqCfg {
+  static constexpr int HALO = round_up(T - 1 + D, 8);
+  static constexpr int TILE_OUT = NT * R;
+  static constexpr int TILE_IN = TILE_OUT * D;
+  using Geom = RowGeomIQ<D, R, NT, HALO>;
+  static constexpr size_t SMEM = (size_t)Geom::PAIRS * sizeof(float2);
+};
+
+template <int T, int D, int R, int NT>
+__global__ void __launch_bounds__(NT)
+k_rf_demod_iq(const RfArgs a, const __grid_constant__ TapArray<taps_window(T)> taps) {
+  using Cfg = RfIqCfg<T, D, R, NT>;
+  using Geom = typename Cfg::Geom;
+  constexpr int HALO = Cfg::HALO;
+  extern __shared__ __align__(16) float2 xiq[];
+  __shared__ float edge_i[NT + 1], edge_q[NT + 1];
+
+  const int t = threadIdx.x;
+  const int b = blockIdx.y;
+  const int o_begin = blockIdx.x * a.outs_per_seg;
+  const int o_end = min(o_begin + a.outs_per_seg, a.n_if);
+  if (o_begin >= o_end) return;
+  const uint8_t *row = a.iq + (size_t)b * a.iq_stride;
+  const uint8_t *hrow = a.hist + (size_t)b * 2 * a.rf_hist_len;
+  const bool row_aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  const f32x2_t one = pack2(a.one, a.one);
+
+  // A tile's raw bytes (16-byte chunks of 8 I/Q pairs, NPRE per thread) are loaded into registers one
+  // tile ahead: the loads of tile k+1 are in flight while tile k is computed, so only a segment's
+  // first tile waits for HBM (without this 40 % of the stall samples sat on the first use of the
+  // loaded word, profiles/r2).
+  constexpr int NCHUNK = (HALO + Cfg::TILE_IN) / 8;
+  constexpr int NPRE = (NCHUNK + NT - 1) / NT;
+  uint4 pre[NPRE];
+  auto chunk_in_row = [&](long long i) { return row_aligned && i >= 0 && i + 8 <= a.n_rf; };
+  auto fetch = [&](int o0) {
+    const long long s0 = (long long)o0 * D - HALO;
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int q = t + k * NT;
+      const long long i = s0 + 8ll * q;
+      if (q < NCHUNK && chunk_in_row(i)) pre[k] = __ldg(reinterpret_cast<const uint4 *>(row + 2 * i));
+    }
+  };
+  fetch(o_begin);
+
+  for (int o0 = o_begin; o0 < o_end; o0 += Cfg::TILE_OUT) {
+    __syncthreads();
+    if (t == 0 && o0 != o_begin) {
+      edge_i[0] = edge_i[NT];
+      edge_q[0] = edge_q[NT];
+    }
+    // ---- stage [o0*D - HALO, o0*D + TILE_IN) as centred float pairs, in the input's own order ----
+    const long long s0 = (long long)o0 * D - HALO;
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int q = t + k * NT;
+      if (q >= NCHUNK) break;
+      const long long i = s0 + 8ll * q;
+      float fi[8], fq[8];
+      if (chunk_in_row(i)) {
+        const uint32_t wds[4] = {pre[k].x, pre[k].y, pre[k].z, pre[k].w};
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          fi[2 * m] = u8_centered(wds[m] & 0xffu);
+          fq[2 * m] = u8_centered((wds[m] >> 8) & 0xffu);
+          fi[2 * m + 1] = u8_centered((wds[m] >> 16) & 0xffu);
+          fq[2 * m + 1] = u8_centered(wds[m] >> 24);
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 8; ++m) rf_fetch_pair<T, D>(a, row, hrow, i + m, fi[m], fq[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < 8; m += 2)
+        *reinterpret_cast<float4 *>(xiq + Geom::pos(8 * q + m - HALO)) = make_float4(fi[m], fq[m], fi[m + 1], fq[m + 1]);
+    }
+    if (o0 + Cfg::TILE_OUT < o_end) fetch(o0 + Cfg::TILE_OUT);
+    __syncthreads();
+    // ---- I,Q of the output that precedes this segment (fmDemod's prev_i/prev_q) ----
+    if (o0 == o_begin && t < 2) {
+      float v;
+      if (o_begin == 0) {
+        v = a.prev_in[2 * b + t];
+      } else {
+        const float *src = reinterpret_cast<const float *>(xiq) + t;
+        float acc = 0.0f;  // output o0-1: newest sample is tile sample -D
+#pragma unroll 1
+        for (int n = 0; n < T; ++n) acc = xmac(acc, taps.h[n], src[2 * Geom::pos(-D - n)]);
+        v = xmul(acc, 0.0078125f);
+      }
+      (t == 0 ? edge_i : edge_q)[0] = v;
+    }
+    // ---- R outputs per thread, I and Q in the two lanes of a pair ----
+    f32x2_t acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0ull;
+    {
+      const float2 *w = xiq + Geom::thread_base(t);   // the thread's first output's newest sample (e = 0)
+      constexpr int NEWEST = (R - 1) * D;
+      constexpr int C_HI = (HALO + NEWEST) / 2;
+      constexpr int C_LO = (HALO - (T - 1)) / 2;
+#pragma unroll
+      for (int c = C_HI; c >= C_LO; --c) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(w + Geom::off(2 * c - HALO));
+#pragma unroll
+        for (int j = 1; j >= 0; --j) {
+          const int e = 2 * c + j - HALO;
+          const f32x2_t x = j ? v.y : v.x;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int n = r * D - e;
+            if (n >= 0 && n < T) acc[r] = xmac2(acc[r], pack2(taps.h[n], taps.h[n]), x, one);
+          }
+        }
+      }
+    }
+    float ai[R], aq[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // exact power-of-two scaling: (u8-128)/128
+      unpack2(acc[r], ai[r], aq[r]);
       ai[r] = xmul(ai[r], 0.0078125f);
       aq[r] = xmul(aq[r], 0.0078125f);
     }
@@ -1092,6 +1329,7 @@ struct BpfArgs {
   size_t car_stride;
   int n_if;
   int outs_per_seg;
+  float one;   // 1.0f at run time (xmac2)
 };
 
 template <int T, int R, int NT, bool FMA_STEREO = false>
@@ -1126,6 +1364,44 @@ k_bpf_dual(const BpfArgs a, const __grid_constant__ TapArray<taps_groups(T, 1, R
       if (o + r < o_end) {
         a.stf[(size_t)b * a.stf_stride + a.hist_off + o + r] = as[r];
         a.car[(size_t)b * a.car_stride + o + r] = ap[r];
+      }
+    }
+  }
+}
+
+// Packed form (EXACT variant): see fir_groups2_packed.  Same staging, same bits.
+template <int T, int R, int NT>
+__global__ void __launch_bounds__(NT)
+k_bpf_dual_packed(const BpfArgs a, const __grid_constant__ TapPairs<taps_groups(T, 1, R)> h2) {
+  constexpr int HALO = round_up(taps_groups(T, 1, R) + R, 4);
+  constexpr int TILE = NT * R;
+  using Geom = RowGeom<1, R, NT, HALO>;
+  __shared__ __align__(16) float xs[round_up(Geom::FLOATS, 4)];
+  const int t = threadIdx.x;
+  const int b = blockIdx.y;
+  const int o_begin = blockIdx.x * a.outs_per_seg;
+  const int o_end = min(o_begin + a.outs_per_seg, a.n_if);
+  const float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off;
+  const f32x2_t one = pack2(a.one, a.one);
+  for (int o0 = o_begin; o0 < o_end; o0 += TILE) {
+    __syncthreads();
+    for (int q = t; q < HALO + TILE; q += NT) {
+      const int i = o0 - HALO + q;
+      xs[Geom::pos(q - HALO)] = (i < a.n_if && i >= -a.demod_off) ? drow[i] : 0.0f;
+    }
+    __syncthreads();
+    f32x2_t acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0ull;
+    fir_groups2_packed<T, 1, R>(xs + Geom::thread_base(t), h2, acc, one);
+    const int o = o0 + t * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (o + r < o_end) {
+        float vs, vp;
+        unpack2(acc[r], vs, vp);
+        a.stf[(size_t)b * a.stf_stride + a.hist_off + o + r] = vs;
+        a.car[(size_t)b * a.car_stride + o + r] = vp;
       }
     }
   }

@@ -122,6 +122,7 @@ struct sdr_pipeline {
   float rt_out_scale = 0.0f;
   int rs_pitch = 0, rs_rows_cap = 0;   // tile geometry of the chosen resampler
   size_t rs_smem = 0;
+  bool scalar_fir = false;             // SDR_VARIANT_SCALAR_FIR: the scalar form of the exact 151-tap FIR kernels
   bool fma_aux = false;                // contract the multiply-adds that do not feed the PLL (FAST, MIXED)
   int n_sm = 148;
   size_t cap_if, cap_audio;  // per-capture capacities of one call
@@ -247,6 +248,21 @@ static int launch_rf(sdr_pipeline *p, RfArgs a, cudaStream_t s) {
   return check_launch(p, "k_rf_demod");
 }
 
+template <int T, int D, int R, int NT>
+static int launch_rf_iq(sdr_pipeline *p, RfArgs a, cudaStream_t s) {
+  using Cfg = RfIqCfg<T, D, R, NT>;
+  auto kern = k_rf_demod_iq<T, D, R, NT>;
+  static std::once_flag once[16];
+  std::call_once(once[p->cfg.device & 15], [&] {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  });
+  int segs = pick_segments(a.n_if, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
+  dim3 grid(segs, p->cfg.batch);
+  prof_begin(p, "k_rf_demod", s);
+  kern<<<grid, NT, Cfg::SMEM, s>>>(a, make_taps<taps_window(T)>(p->h_rf));
+  return check_launch(p, "k_rf_demod");
+}
+
 static bool rf_fast_available(int T, int D) {
   return (T == 151 || T == 13) && (D == 10 || D == 5 || D == 3);
 }
@@ -290,6 +306,12 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
   }
   if (p->rf_fast) {
     // tile shapes from the sweep in DESIGN.md section 4 (two outputs per thread, one merged I/Q loop)
+    if (!p->scalar_fir) {   // packed two-rounding multiply-adds (I and Q in one register pair)
+      // tile shape: sweep on B200: R = 2 / 4 / 6 / 8 -> 2.14 / 1.99 / 2.33 / 3.20 ms
+      if (T == 151 && D == 10) return launch_rf_iq<151, 10, 4, 128>(p, a, s);
+      if (T == 151 && D == 5) return launch_rf_iq<151, 5, 4, 128>(p, a, s);
+      if (T == 151 && D == 3) return launch_rf_iq<151, 3, 4, 128>(p, a, s);
+    }
     if (T == 151 && D == 10) return launch_rf<151, 10, 2, 128, true>(p, a, s);
     if (T == 151 && D == 5) return launch_rf<151, 5, 4, 128, true>(p, a, s);
     if (T == 151 && D == 3) return launch_rf<151, 3, 4, 128, true>(p, a, s);
@@ -352,6 +374,16 @@ static int launch_bpf(sdr_pipeline *p, BpfArgs a, cudaStream_t s) {
   int segs = pick_segments(a.n_if, NT * R, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
   prof_begin(p, "k_bpf_dual", s);
+  if (!p->fma_aux && !p->scalar_fir) {   // EXACT: both filters in the lanes of one register pair
+    constexpr int N = taps_groups(T, 1, R);
+    TapPairs<N> h2;
+    std::memset(&h2, 0, sizeof h2);   // zero padding: see fir_groups
+    for (size_t i = 0; i < p->h_stereo.size() && i < (size_t)N; ++i) h2.h[i].x = p->h_stereo[i];
+    for (size_t i = 0; i < p->h_pilot.size() && i < (size_t)N; ++i) h2.h[i].y = p->h_pilot[i];
+    a.one = 1.0f;
+    k_bpf_dual_packed<T, R, NT><<<grid, NT, 0, s>>>(a, h2);
+    return check_launch(p, "k_bpf_dual");
+  }
   // MIXED: the 22-54 kHz band only reaches the mixer, so its multiply-adds may be contracted; the
   // pilot band feeds the PLL and keeps the reference's two roundings
   auto kern = p->fma_aux ? k_bpf_dual<T, R, NT, true> : k_bpf_dual<T, R, NT, false>;
@@ -620,9 +652,13 @@ static bool build_resample_tc(sdr_pipeline *p, std::vector<uint8_t> &tiles) {
   return true;
 }
 
-extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
-  if (!cfg || !out) return fail(SDR_ERR_INVALID, "null argument");
+extern "C" int sdr_pipeline_create(const sdr_config *cfg_in, sdr_pipeline **out) {
+  if (!cfg_in || !out) return fail(SDR_ERR_INVALID, "null argument");
   *out = nullptr;
+  sdr_config cfg_base = *cfg_in;
+  const bool scalar_fir = (cfg_base.variant & SDR_VARIANT_SCALAR_FIR) != 0;
+  cfg_base.variant &= ~SDR_VARIANT_SCALAR_FIR;
+  const sdr_config *cfg = &cfg_base;
   if (cfg->mode < 0 || cfg->mode > 3) return fail(SDR_ERR_INVALID, "mode must be 0..3 (project.cpp:396)");
   if (cfg->channels < 1 || cfg->channels > 2)
     return fail(SDR_ERR_INVALID, "channels must be 1 or 2 (project.cpp:405)");
@@ -662,6 +698,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg, sdr_pipeline **out) {
   p->if_per_granule = p->base_if_per_granule = mi.granule_bytes / 2 / m.rf_decim;
   p->pcm_per_granule = p->base_pcm_per_granule = mi.pcm_per_granule;
   p->fma_aux = cfg->variant != SDR_VARIANT_EXACT;
+  p->scalar_fir = scalar_fir;
   cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
   uint64_t cap_bytes = cfg->max_bytes_per_channel ? cfg->max_bytes_per_channel : (uint64_t)m.block_bytes;
   cap_bytes = (cap_bytes + mi.granule_bytes - 1) / mi.granule_bytes * mi.granule_bytes;
@@ -1033,6 +1070,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   ra.tap_stride = p->tap_if_stride;
   ra.n_rf = n_rf;
   ra.n_if = (int)n_if;
+  ra.one = 1.0f;
   const bool rs_tc = p->audio_kernel == sdr_pipeline::AK_RS_TC;
   ra.write_f32 = 1;
   if (rs_tc) {   // the front end hands fm_demod to the tensor-core resampler as two fp16 planes
