@@ -813,12 +813,11 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg_in, sdr_pipeline **out)
   }
 
   std::vector<uint8_t> rt_tiles;
-  // The tensor-core resampler's cost follows the INPUT rate (one pipeline step per 32-sample slab),
-  // the quad resampler's the OUTPUT rate (101 multiply-adds per output).  Measured on B200
-  // (1024 captures x 16 blocks): mode 2 (0.184 outputs per input) 0.195 vs 0.245 ms; mode 3 (0.138)
-  // 0.674 vs 0.686 ms, which does not pay for the front end's extra plane stores (+0.07 ms).
-  if (p->resample && !p->stereo && cfg->variant == SDR_VARIANT_FAST &&
-      (long long)m.audio_upsamp * 100 >= (long long)m.audio_decim * 16 && build_resample_tc(p, rt_tiles))
+  // Tensor-core resampler for both custom-rate modes.  Its cost follows the INPUT rate (one pipeline
+  // step per 32-sample slab), the quad resampler's the OUTPUT rate (101 multiply-adds per output).
+  // Measured on B200, 1024 captures x 16 blocks: mode 2 0.120 vs 0.245 ms; mode 3 0.377 vs 0.684 ms
+  // (the front end's two plane stores instead of one float store cost it 0.03 ms there).
+  if (p->resample && !p->stereo && cfg->variant == SDR_VARIANT_FAST && build_resample_tc(p, rt_tiles))
     p->audio_kernel = sdr_pipeline::AK_RS_TC;
   std::vector<int8_t> tc_b;
   std::vector<int32_t> tc_h;
