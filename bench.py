@@ -645,6 +645,8 @@ def run_ours(args):
                 pass
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                        "traffic_gbs": (traffic / (dom_ms * 1e-3) / 1e9) if traffic else None,
+                        "traffic_frac_of_peak": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if traffic else None,
                         "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
                         "kernel_share_of_step": kt[dom][0] / args.steps / step_kernel_ms,

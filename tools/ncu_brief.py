@@ -5,6 +5,7 @@ rep = sys.argv[1]; nl = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]
+units = dict(zip(hdr, rows[1]))
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_issued.avg.pct_of_peak_sustained_active", "sm__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -15,7 +16,7 @@ for r in rows[2:]:
     d = dict(zip(hdr, r))
     print("==", d.get("Kernel Name", "")[:80])
     for k in KEYS:
-        if k in d: print(f"  {k} = {d[k]}")
+        if k in d: print(f"  {k} = {d[k]} {units.get(k, '')}")
     st = []
     for k in hdr:
         if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio"):
