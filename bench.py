@@ -504,6 +504,38 @@ def bind_to_gpu_numa_node(index: int):
     return before  # the caller restores it before the CPU-baseline leg forks its workers
 
 
+def time_channelizer(torch, sdr, peak, M=16, T=8, W=64, blocks=16, steps=5, warmup=3):
+    """W wideband captures (M x 2.4 MS/s, uint8 I/Q) -> W*M receiver inputs in HBM
+    (mode-0 captures of `blocks` reference blocks each).  Device-timed with CUDA events; algorithmic
+    bytes: 2 read + 2 written per wideband I/Q pair."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nbytes_ch = blocks * 102400
+    nbytes_wide = nbytes_ch * M
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    d_wide = torch.randint(0, 256, (W, nbytes_wide), dtype=torch.uint8, device=dev, generator=g)
+    d_out = torch.empty((W * M, nbytes_ch), dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    with sdr.Channelizer(M, T, n_wide=W, device=dev.index, gain=1.0) as ch:
+        for _ in range(warmup):
+            ch.process_device(d_wide.data_ptr(), nbytes_wide, nbytes_wide, d_out.data_ptr(), nbytes_ch, s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ch.process_device(d_wide.data_ptr(), nbytes_wide, nbytes_wide, d_out.data_ptr(), nbytes_ch, s)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    pairs = W * nbytes_wide // 2
+    gbs = pairs * 4 / (ms * 1e-3) / 1e9
+    return {"what": f"SURVEY 8f3 channeliser: {W} wideband captures ({M} x 2.4 MS/s) -> {W * M} receiver inputs "
+                    f"({blocks} reference blocks each) in HBM, {T} taps per branch",
+            "value": pairs / (ms * 1e-3) / 1e6, "unit": "wideband input I/Q MS/s (device-timed)", "ms_per_step": ms,
+            "steps": steps, "warmup": warmup, "algorithmic_bytes_per_pair": 4, "achieved_gbs": gbs,
+            "frac_of_hbm_peak": gbs / peak, "gpu_launches": 2 * steps}
+
+
 def with_args(args, **kw):
     d = dict(vars(args))
     d.update(kw)
@@ -610,6 +642,12 @@ def run_ours(args):
                 o["rds"] = r["rds"]
             others[name] = o
 
+    if not args.no_others and world == 1:
+        try:
+            others["channelizer_16"] = time_channelizer(torch, sdr, peak)
+        except Exception as e:
+            others["channelizer_16"] = {"error": str(e)[:300]}
+
     e2e = None
     if not (args.rds or args.mixed or args.streams > 1):
         os.sched_setaffinity(0, affinity_before)
@@ -704,6 +742,7 @@ def main():
                     help="half of the handles mono, half stereo (BASELINE configs[3]); needs --streams >= 2")
     ap.add_argument("--rds", action="store_true",
                     help="also run the RDS chain (modes 0/2) behind every step; not the default workload")
+    ap.add_argument("--only-channelizer", action="store_true", help="time the channeliser alone and exit")
     ap.add_argument("--variant", default="fast", choices=["fast", "exact", "mixed", "exact_scalar"],
                     help="fast: tensor-core RF front end (mono, +-1 LSB PCM); exact: bit-identical CUDA-core path; "
                          "mixed: exact in front of the PLL, contracted multiply-adds elsewhere (+-1 LSB PCM)")
@@ -711,7 +750,11 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.mixed and args.streams < 2:
         args.streams = 2
-    if args.impl == "reference":
+    if args.only_channelizer:
+        import torch
+        import sdr_b200 as sdr
+        print(json.dumps(time_channelizer(torch, sdr, measured_peak()[0])))
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

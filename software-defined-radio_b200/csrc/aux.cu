@@ -272,6 +272,174 @@ __global__ void __launch_bounds__(CH_NT) k_channelize(const ChanArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Channeliser, throughput form (the one the C ABI launches; k_channelize above stays as the plain
+// statement of the sums, used when the tile would not fit shared memory).
+// The bank is M independent T-tap FIRs, one per branch r, each over its OWN phase of the input
+// (pairs n M + M-1-r), followed by an M-point DFT across the branches of one output instant.
+//  phase 1  thread = (branch r = t % M, run of R = 16 consecutive instants): a sample is loaded
+//           once per thread and tap chunk and used for up to 4 taps x 16 instants from registers;
+//           (re, im) accumulators are register pairs, one FFMA2 per tap and instant.
+//  transpose through shared memory V[r][instant] (padded and skewed: conflict-free both ways)
+//  phase 2  thread = instant: reads its M branch sums, u_k = v_{M-1-k}, in-register radix-2 FFT,
+//           requantises (clamp, magic-number rounding = rint) and writes one uchar2 per channel row;
+//           consecutive lanes are consecutive instants, so every row gets 64 contiguous bytes per warp.
+// Staging converts each byte pair to float2 once per CTA (16-byte global loads, 8 pairs each).
+// ---------------------------------------------------------------------------------------------
+constexpr int CH2_NT = 256, CH2_R = 16;
+
+template <int M>
+struct Ch2Geom {
+  static constexpr int G = CH2_NT / M;              // instant groups per tile
+  static constexpr int NI = G * CH2_R;              // instants per tile
+  static constexpr int VPAD = M == 16 ? 0 : M;      // V: a group's R instants are followed by VPAD slots so that the
+                                                    // 16/M groups of a half-warp hit different banks
+  static constexpr int VROW = G * (CH2_R + VPAD) + 1;   // V row pitch (float2): odd -> lanes r hit distinct banks
+  __host__ __device__ static int vcol(int i) { return (i / CH2_R) * (CH2_R + VPAD) + i % CH2_R; }
+  __host__ __device__ static int x_pairs(int Tp) { return (NI + Tp - 1) * M; }
+  // staged pair p (0 = first pair of the tile's window) -> float2 slot; one group's M pairs of an instant are
+  // contiguous, and every R*M pairs the slot index skips M so that the groups of a warp hit different banks
+  __host__ __device__ static int xpos(int p) { return p + (p / (CH2_R * M)) * M; }
+  __host__ __device__ static size_t smem_bytes(int Tp) {
+    return (size_t)(xpos(x_pairs(Tp)) + M + 8) * sizeof(float2) + (size_t)M * VROW * sizeof(float2) + (size_t)Tp * M * sizeof(float);
+  }
+};
+
+// in-register DFT: y[c] = sum_k u[k] exp(-2 pi i c k / M), radix-2 decimation in time
+template <int M>
+__device__ __forceinline__ void ch_dft(float2 (&u)[M]) {
+  if constexpr (M == 2) {
+    const float2 a = u[0], b = u[1];
+    u[0] = make_float2(a.x + b.x, a.y + b.y);
+    u[1] = make_float2(a.x - b.x, a.y - b.y);
+  } else {
+    float2 e[M / 2], o[M / 2];
+#pragma unroll
+    for (int k = 0; k < M / 2; ++k) { e[k] = u[2 * k]; o[k] = u[2 * k + 1]; }
+    ch_dft<M / 2>(e);
+    ch_dft<M / 2>(o);
+    // exp(-2 pi i k / M), k < M/2, for M up to 16
+    constexpr float C16[8] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                              0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+    constexpr float S16[8] = {0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
+                              -1.0f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
+#pragma unroll
+    for (int k = 0; k < M / 2; ++k) {
+      const float c = C16[k * (16 / M)], sn = S16[k * (16 / M)];
+      const float tr = o[k].x * c - o[k].y * sn, ti = o[k].x * sn + o[k].y * c;
+      u[k] = make_float2(e[k].x + tr, e[k].y + ti);
+      u[k + M / 2] = make_float2(e[k].x - tr, e[k].y - ti);
+    }
+  }
+}
+template <>
+__device__ __forceinline__ void ch_dft<1>(float2 (&)[1]) {}
+
+template <int M>
+__global__ void __launch_bounds__(CH2_NT) k_channelize2(const ChanArgs a, int Tp) {
+  using Geo = Ch2Geom<M>;
+  constexpr int R = CH2_R, NI = Geo::NI;
+  extern __shared__ __align__(16) float2 ch_sm[];
+  float2 *xs = ch_sm;
+  float2 *V = xs + Geo::xpos(Geo::x_pairs(Tp)) + M + 8;
+  float *hs = reinterpret_cast<float *>(V + (size_t)M * Geo::VROW);
+  const int w = blockIdx.y, n0 = blockIdx.x * NI, t = threadIdx.x;
+  const int T = a.T, HW = M * T;
+  const uint8_t *row = a.wide + (size_t)w * a.wide_stride;
+  const uint8_t *hrow = a.hist + (size_t)w * 2 * HW;
+  // taps, scaled by the output gain (the 1/128 of the input conversion and the 128 of the
+  // requantisation cancel), zero padded to Tp
+  for (int i = t; i < Tp * M; i += CH2_NT) hs[i] = i < HW ? a.h[i] * a.gain : 0.0f;
+  // ---- stage pairs [(n0 - (Tp-1)) M, (n0 + NI) M) as (byte - 128) float2 ----
+  const long long base = ((long long)n0 - (Tp - 1)) * M;
+  const int n_pairs = Geo::x_pairs(Tp);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  const int off = (int)(((base % 8) + 8) % 8);   // chunks of 8 pairs start on 16-byte boundaries of the row
+  for (int j = 8 * t - off; j < n_pairs; j += 8 * CH2_NT) {
+    const long long i = base + j;
+    float f[16];
+    if (aligned && i >= 0 && i + 8 <= a.n_in) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + 2 * i));
+      const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        f[4 * k] = u8_centered(wd[k] & 0xffu);
+        f[4 * k + 1] = u8_centered((wd[k] >> 8) & 0xffu);
+        f[4 * k + 2] = u8_centered((wd[k] >> 16) & 0xffu);
+        f[4 * k + 3] = u8_centered(wd[k] >> 24);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long long ii = i + k;
+        uint32_t bi = 128, bq = 128;   // outside the history / past the end: only zero taps or unused outputs see it
+        if (ii < 0) {
+          const long long hk = HW + ii;
+          if (hk >= 0) { bi = hrow[2 * hk]; bq = hrow[2 * hk + 1]; }
+        } else if (ii < a.n_in) {
+          bi = row[2 * ii];
+          bq = row[2 * ii + 1];
+        }
+        f[2 * k] = u8_centered(bi);
+        f[2 * k + 1] = u8_centered(bq);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (j + k >= 0 && j + k < n_pairs) xs[Geo::xpos(j + k)] = make_float2(f[2 * k], f[2 * k + 1]);
+  }
+  __syncthreads();
+  // ---- phase 1: branch r, instants g*R .. g*R+R-1 of the tile ----
+  {
+    const int r = t % M, g = t / M;
+    f32x2_t acc[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = 0ull;
+    // sample of instant (tile) i for this branch: staged pair (i + Tp-1) M + M-1-r
+    const int col0 = (g * R + Tp - 1) * M + (M - 1 - r);
+    for (int q0 = 0; q0 < Tp; q0 += 4) {
+      // window: instants g*R - q0 - 3 .. g*R + R-1 - q0  ->  wv[0 .. R+2]
+      f32x2_t wv[R + 3];
+#pragma unroll
+      for (int k = 0; k < R + 3; ++k)
+        wv[k] = *reinterpret_cast<const f32x2_t *>(xs + Geo::xpos(col0 + (k - 3 - q0) * M));
+#pragma unroll
+      for (int dq = 0; dq < 4; ++dq) {
+        const float hq = hs[(q0 + dq) * M + r];
+        const f32x2_t h2 = pack2(hq, hq);
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] = fma2(acc[j], h2, wv[j + 3 - dq]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      *reinterpret_cast<f32x2_t *>(V + (size_t)r * Geo::VROW + Geo::vcol(g * R + j)) = acc[j];
+  }
+  __syncthreads();
+  // ---- phase 2: one instant per thread and pass ----
+#pragma unroll 1
+  for (int e = 0; e < NI / CH2_NT; ++e) {
+    const int i = t + e * CH2_NT;
+    const int n = n0 + i;
+    if (n >= a.n_out) break;
+    const int col = Geo::vcol(i);
+    float2 u[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) u[k] = V[(size_t)(M - 1 - k) * Geo::VROW + col];
+    ch_dft<M>(u);
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+      // u8 = 128 + rint(v), clipped: clamp in float, add 1.5 * 2^23 (the sum's low byte is the
+      // two's-complement integer), flip the top bit of the byte for the +128
+      const float vr = fminf(fmaxf(u[c].x, -128.0f), 127.0f) + 12582912.0f;
+      const float vi = fminf(fmaxf(u[c].y, -128.0f), 127.0f) + 12582912.0f;
+      const uint32_t qi = (__float_as_uint(vr) & 0xffu) ^ 0x80u, qq = (__float_as_uint(vi) & 0xffu) ^ 0x80u;
+      uint8_t *dst = a.out + ((size_t)w * M + c) * a.out_stride + 2 * (size_t)n;
+      *reinterpret_cast<uchar2 *>(dst) = make_uchar2((unsigned char)qi, (unsigned char)qq);
+    }
+  }
+}
+
 __global__ void k_chan_carry(const uint8_t *wide, size_t wide_stride, uint8_t *hist, int HW, long long n_in) {
   extern __shared__ uint8_t stage[];
   const int w = blockIdx.x;
@@ -461,13 +629,35 @@ extern "C" int sdr_channelizer_process_device(sdr_channelizer *c, const uint8_t 
   a.n_out = (int)(a.n_in / M);
   a.T = T;
   a.gain = c->cfg.gain;
-  dim3 grid((a.n_out + CH_NT - 1) / CH_NT, c->cfg.n_wide);
-  const size_t smem = (size_t)(CH_NT + T) * M * sizeof(float2);
+  const int Tp = (T + 3) / 4 * 4;
+  auto launch2 = [&](auto geom, auto kern) -> bool {   // throughput form, when its tile fits shared memory
+    using Geo = decltype(geom);
+    const size_t smem2 = Geo::smem_bytes(Tp);
+    if (smem2 > 200 * 1024) return false;
+    static std::once_flag once[16];
+    std::call_once(once[c->cfg.device & 15], [&] {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    dim3 grid2((a.n_out + Geo::NI - 1) / Geo::NI, c->cfg.n_wide);
+    kern<<<grid2, CH2_NT, smem2, s>>>(a, Tp);
+    return true;
+  };
+  bool done = false;
   switch (M) {
-    case 2: k_channelize<2><<<grid, CH_NT, smem, s>>>(a); break;
-    case 4: k_channelize<4><<<grid, CH_NT, smem, s>>>(a); break;
-    case 8: k_channelize<8><<<grid, CH_NT, smem, s>>>(a); break;
-    default: k_channelize<16><<<grid, CH_NT, smem, s>>>(a); break;
+    case 2: done = launch2(Ch2Geom<2>{}, k_channelize2<2>); break;
+    case 4: done = launch2(Ch2Geom<4>{}, k_channelize2<4>); break;
+    case 8: done = launch2(Ch2Geom<8>{}, k_channelize2<8>); break;
+    default: done = launch2(Ch2Geom<16>{}, k_channelize2<16>); break;
+  }
+  if (!done) {
+    dim3 grid((a.n_out + CH_NT - 1) / CH_NT, c->cfg.n_wide);
+    const size_t smem = (size_t)(CH_NT + T) * M * sizeof(float2);
+    switch (M) {
+      case 2: k_channelize<2><<<grid, CH_NT, smem, s>>>(a); break;
+      case 4: k_channelize<4><<<grid, CH_NT, smem, s>>>(a); break;
+      case 8: k_channelize<8><<<grid, CH_NT, smem, s>>>(a); break;
+      default: k_channelize<16><<<grid, CH_NT, smem, s>>>(a); break;
+    }
   }
   SDR_CUDA(cudaGetLastError());
   k_chan_carry<<<c->cfg.n_wide, 128, 2 * (size_t)M * T, s>>>(d_wide, wide_stride, c->d_hist, M * T, a.n_in);
