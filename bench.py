@@ -321,7 +321,8 @@ def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, wor
             if nbytes % 192000:
                 raise SystemExit("--rds needs --blocks such that a capture is a multiple of 192000 B "
                                  "(mode 0: 15, 30, ...; mode 2: 12, 24, ...)")
-            rds = sdr.Rds(p, block_if=9600, max_pending_blocks=(steps + warmup) * (nbytes // 192000))
+            rds = sdr.Rds(p, block_if=9600, max_pending_blocks=(steps + warmup) * (nbytes // 192000),
+                          f32_fir=bool(getattr(args, "rds_f32", False)))
         n_pcm = p.pcm_count(nbytes)
         d_pcm = torch.zeros((per, n_pcm), dtype=torch.int16, device=dev)
         # alternating priorities: when two groups have throughput kernels ready, one goes first,
@@ -568,7 +569,10 @@ def other_config_list(args, world):
              dict(base, mode=0, audio_channels=1, mixed=True, streams=2, batch=8192 // world, blocks=4))]
     if world == 1:
         lst += [("stereo_rds_mode0", "configs[4]: stereo + RDS chain (BPF, squaring PLL, RRC, clock recovery), 1024 captures x 15 blocks",
-                 dict(base, mode=0, audio_channels=2, variant="exact", rds=True, blocks=15))]
+                 dict(base, mode=0, audio_channels=2, variant="exact", rds=True, blocks=15)),
+                ("stereo_rds_fill", "configs[4] shaped to fill the GPU: 8192 captures x 15 blocks (the stereo PLL's 27 ms are "
+                                    "flat up to 16 k captures; the RDS chain's FP64 filters scale with the batch)",
+                 dict(base, mode=0, audio_channels=2, variant="exact", rds=True, blocks=15, batch=8192))]
     return lst
 
 
@@ -740,6 +744,8 @@ def main():
                     help="pipeline handles per GPU, each with batch/streams captures on its own CUDA stream")
     ap.add_argument("--mixed", action="store_true",
                     help="half of the handles mono, half stereo (BASELINE configs[3]); needs --streams >= 2")
+    ap.add_argument("--rds-f32", action="store_true",
+                    help="with --rds: the RDS chain's three FIR stages in single precision (experiment; DESIGN.md section 6)")
     ap.add_argument("--rds", action="store_true",
                     help="also run the RDS chain (modes 0/2) behind every step; not the default workload")
     ap.add_argument("--only-channelizer", action="store_true", help="time the channeliser alone and exit")
