@@ -56,11 +56,16 @@ def build(force: bool = False, verbose_ptxas: bool = False) -> str:
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose_ptxas else []
+    jobs = []
     for src in cu:
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
         if force or _newer(obj, [src] + hdrs):
-            _run([NVCC, *NVCC_FLAGS, *extra, "-c", src, "-o", obj])
+            jobs.append([NVCC, *NVCC_FLAGS, *extra, "-c", src, "-o", obj])
         objs.append(obj)
+    if jobs:   # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(_run, jobs))
     dobj = os.path.join(HERE, "build", "design.o")
     if force or _newer(dobj, [design] + hdrs):
         _run([CXX, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-c", design, "-o", dobj])

@@ -105,6 +105,31 @@ def test_channelizer_matches_direct_form_oracle(sdr, M, T):
         assert float(np.mean(d != 0)) < 0.01, float(np.mean(d != 0))
 
 
+@pytest.mark.parametrize("M,T,n_inst", [(16, 5, 300), (16, 8, 3), (8, 7, 513), (4, 3, 2049), (2, 64, 40)])
+def test_channelizer_ragged_shapes(sdr, M, T, n_inst):
+    """Edges of the throughput kernel's tiling: tap counts that are not a multiple of its 4-tap chunk,
+    fewer output instants than taps, one instant past a tile (256 / 512 / 1024 / 2048 instants per tile
+    for M = 16 / 8 / 4 / 2), the longest branch filter, and a capture cut into three uneven calls."""
+    rng = np.random.default_rng(100 * M + T)
+    wide = rng.integers(0, 256, size=(3, 2 * M * n_inst)).astype(np.uint8)
+    wide[1] = 128                                             # silence
+    wide[2, ::2] = 255                                        # clipped I
+    with sdr.Channelizer(M, T, n_wide=3, gain=0.9) as ch:
+        h = ch.prototype()
+        got = ch.process_host(wide)
+        ch.reset()
+        a, b = 2 * M * (n_inst // 3), 2 * M * (n_inst // 3 + max(1, n_inst // 2))
+        cuts = [c for c in (0, a, min(b, wide.shape[1]), wide.shape[1])]
+        parts = [ch.process_host(np.ascontiguousarray(wide[:, cuts[k]:cuts[k + 1]]))
+                 for k in range(3) if cuts[k + 1] > cuts[k]]
+    assert np.array_equal(np.concatenate(parts, axis=1), got), "history carried across uneven calls"
+    for w in range(3):
+        want = auxlib.channelize(wide[w], M, h, 0.9)
+        d = np.abs(got[w * M:(w + 1) * M].astype(np.int32) - want.astype(np.int32))
+        assert int(d.max()) <= 1, (w, int(d.max()))
+    assert np.all(got[M:2 * M] == 128), "silence in, silence out"
+
+
 def test_wideband_capture_to_pcm_on_the_device(sdr):
     """eight stations in one 19.2 MS/s capture, channelised in device memory and handed
     to the batched receiver without crossing PCIe again; every channel's PCM carries its own tone."""
