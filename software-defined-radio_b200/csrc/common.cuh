@@ -82,6 +82,16 @@ __device__ __forceinline__ float fm_demod_one(float i, float q, float pi, float 
   return xdiv(num, den);
 }
 
+// Programmatic dependent launch (the mono fast path's three kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): pdl_trigger lets the NEXT kernel of the stream be
+// scheduled as soon as every CTA of this one has started -- its CTAs take the SM slots this kernel's
+// CTAs free as they finish and run their prologue (barriers, tensor memory, tap tiles) under this
+// kernel's tail --; pdl_wait blocks until the PREVIOUS kernel has completed and its writes are visible,
+// and must precede the first access to anything that kernel produced.  Both are no-ops in a kernel
+// launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- host-side error plumbing -------------------------------------------
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);

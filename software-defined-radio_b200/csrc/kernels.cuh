@@ -1547,6 +1547,8 @@ static __global__ void k_carry(const CarryArgs c) {
   extern __shared__ unsigned char stage[];
   const int b = blockIdx.x;
   const int t = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (c.work_counter && b == 0 && t == 0) *c.work_counter = 0;
   // 1. float tails.  Source and destination ranges may overlap when the call was
   //    shorter than the history, so go through shared memory.

@@ -232,6 +232,25 @@ static TapArray<N> make_taps(const std::vector<float> &h) {
   return t;
 }
 
+// Launch with programmatic stream serialisation (see pdl_trigger / pdl_wait in common.cuh): the kernel may
+// be scheduled before its predecessor in the stream has finished and waits for it itself.  Only
+// kernels that call pdl_wait() before touching their predecessor's output may be launched this way.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // ---- K1 dispatch -------------------------------------------------------------
 template <int T, int D, int R, int NT, bool MERGE, int ALGO = 0>
 static int launch_rf(sdr_pipeline *p, RfArgs a, cudaStream_t s) {
@@ -299,9 +318,9 @@ static int run_rf(sdr_pipeline *p, const RfArgs &a, cudaStream_t s) {
       return fail(SDR_ERR_CUDA, "cudaMemsetAsync");
     p->tc_counter_armed = false;
     prof_begin(p, "k_rf_demod_tc", s);
-    if (D == 10) k_rf_demod_tc<10><<<grid, TC_BLOCK, TcCfg<10>::SMEM, s>>>(g);
-    else if (D == 5) k_rf_demod_tc<5><<<grid, TC_BLOCK, TcCfg<5>::SMEM, s>>>(g);
-    else k_rf_demod_tc<3><<<grid, TC_BLOCK, TcCfg<3>::SMEM, s>>>(g);
+    if (D == 10) launch_pdl(k_rf_demod_tc<10>, grid, dim3(TC_BLOCK), TcCfg<10>::SMEM, s, g);
+    else if (D == 5) launch_pdl(k_rf_demod_tc<5>, grid, dim3(TC_BLOCK), TcCfg<5>::SMEM, s, g);
+    else launch_pdl(k_rf_demod_tc<3>, grid, dim3(TC_BLOCK), TcCfg<3>::SMEM, s, g);
     return check_launch(p, "k_rf_demod_tc");
   }
   if (p->rf_fast) {
@@ -1166,7 +1185,8 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
       const int row_tiles = (B + RT_ROWS - 1) / RT_ROWS;
       const int total_blocks = t.n_periods * p->rt_tab.NBLK;
       t.ctas_per_tile = std::max(1, std::min(total_blocks, (2 * p->n_sm) / row_tiles));
-      k_audio_resample_tc<RT_NST, 2><<<row_tiles * t.ctas_per_tile, RT_BLOCK, rt_smem(RT_NST), s>>>(t, p->rt_tab, p->map_h, p->map_l);
+      launch_pdl(k_audio_resample_tc<RT_NST, 2>, dim3(row_tiles * t.ctas_per_tile), dim3(RT_BLOCK), rt_smem(RT_NST), s,
+                 t, p->rt_tab, p->map_h, p->map_l);
     } else if (p->audio_kernel == sdr_pipeline::AK_RS_QUAD) {
       ResampleQuadArgs q{aa, p->d_h_quad.p, p->m.audio_upsamp, p->m.audio_decim, p->TA, p->quad_kb, (int)n_if};
       dim3 grid(((int)n_audio + RQ_J - 1) / RQ_J, (B + 63) / 64);
@@ -1266,7 +1286,7 @@ extern "C" int sdr_pipeline_process_device(sdr_pipeline *p, const uint8_t *d_iq,
   size_t sh = std::max<size_t>((size_t)std::max({p->HD, p->HA + 1, p->pl_off / 2}) * sizeof(float), (size_t)2 * p->HR);
   ca.work_counter = p->tc_next_item.p;   // nullptr unless the fast variant allocated it
   prof_begin(p, "k_carry", s);
-  k_carry<<<B, 128, sh, s>>>(ca);
+  launch_pdl(k_carry, dim3(B), dim3(128), sh, s, ca);
   if ((rc = check_launch(p, "k_carry"))) return rc;
   p->tc_counter_armed = true;
   p->last_n_if = n_if;

@@ -139,6 +139,8 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
+  pdl_trigger();
+  pdl_wait();   // the planes come from the front end's kernel; nothing above read them
   const int NBLK = tab.NBLK, SP = tab.SP, P_out = tab.P_out;
 
   // ---- this CTA's range of global blocks gb = p * NBLK + b of its capture tile ----

@@ -255,6 +255,10 @@ k_rf_demod_tc(const RfTcArgs g) {
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
+  // everything above read constants only; the input history, the carried I/Q and the work counter
+  // come from the previous call's k_carry
+  pdl_trigger();
+  pdl_wait();
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                          ((uint32_t)(TC_ROWS >> 4) << 24);
