@@ -95,6 +95,15 @@ struct ResampleTcArgs {
   int ctas_per_tile;                  // CTAs sharing one 128-capture tile (they split its blocks)
 };
 
+#ifdef SDR_RT_TRACE
+// Debug build only: cycles one CTA's roles spend in each wait (printed by CTA 7).
+#define RT_T0() const long long rt_t0__ = clock64()
+#define RT_ACC(v) (v) += clock64() - rt_t0__
+#else
+#define RT_T0() do { } while (0)
+#define RT_ACC(v) do { } while (0)
+#endif
+
 // The period tables travel as a kernel parameter (constant bank): the per-step schedule lookups are
 // constant-cache reads.  NST pipeline stages, MINB resident CTAs per SM.
 template <int NST, int MINB>
@@ -105,8 +114,24 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
   const uint32_t smem_u32 = (tc_smem_u32(rt_smem_raw) + 1023u) & ~1023u;   // swizzled tiles want their natural alignment
   __shared__ __align__(8) uint64_t full[NST], empty[NST], acc_full[RT_SLOTS], acc_empty[RT_SLOTS];
   __shared__ uint32_t tmem_slot;
+  // One step's work for the issuer, planned by the producer thread (which runs NST steps ahead and
+  // spends most of its time waiting): the issuer's own instruction stream was the kernel's critical path
+  // -- ~1950 cycles per slab step in one thread, of which ~850 decoded the schedule (debug build
+  // SDR_RT_TRACE) -- so it now only reads this record, waits, and issues.
+  struct __align__(16) Cmd {
+    uint32_t n_run;            // MMA runs (1 or 2): consecutive accumulator slots served by one MMA per K step and plane
+    uint32_t b_lbo;            // B descriptor's leading-dimension offset (32 * nact rows * 16 B) >> 4
+    uint32_t d[2], b_off[2], idesc[2];   // per run: accumulator address offset, B start (address units), instruction descriptor
+    uint32_t wait_slot[RT_NACT], wait_par[RT_NACT];   // per schedule entry: its slot; parity | 2 when the block starts here and must wait for the slot's previous tenant
+    uint32_t done_slot[RT_NACT];                      // per schedule entry: slot | 8 when the block ends here
+  };
+  __shared__ Cmd cmds[NST];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef SDR_RT_TRACE
+  long long tr_prod_empty = 0, tr_iss_full = 0, tr_iss_acc = 0, tr_rb_full = 0;
+  const long long tr_begin = clock64();
+#endif
 
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -190,72 +215,100 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
 
     if (warp == RT_WORKERS / 32 + 1) {
       // ---- producer: asynchronous-proxy copies into the stage the MMAs of NST steps ago have read ----
-      if (lane == 0) {
-        int q = q_first;
-        for (int st = 0; st < n_steps; ++st) {
+      {
+        // the whole warp plans (lane i < 4 decodes schedule entry i; votes give the runs), lane 0 copies
+        const uint32_t idesc16 = (1u << 4) | ((uint32_t)(RT_ROWS >> 4) << 24);   // f16 x f16 -> f32, M = 128
+        int p = p_first, q = q_first;
+        for (int st = 0; st < n_steps; ++st, advance(p, q)) {
           const int stage = st % NST;
-          if (st >= NST) mbar_wait(&empty[stage], ((st / NST) - 1) & 1);
-          const uint32_t dst = smem_u32 + (uint32_t)stage * RT_STAGE, bar = tc_smem_u32(&full[stage]);
-          const uint32_t nb = tab.nact[q] * RT_TILE_BYTES;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)RT_X_BYTES + nb) : "memory");
-          const int x0 = g.pl_off + (T0 + st) * RT_SLAB;
-          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-                       "l"(&map_h), "r"(x0), "r"(c0), "r"(bar)
-                       : "memory");
-          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst + RT_X_BYTES / 2),
-                       "l"(&map_l), "r"(x0), "r"(c0), "r"(bar)
-                       : "memory");
-          if (nb)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + RT_X_BYTES),
-                         "l"(g.tiles + (size_t)tab.bq_off[q] * RT_TILE_BYTES), "r"(nb), "r"(bar)
+          if (st >= NST && lane == 0) { RT_T0(); mbar_wait(&empty[stage], ((st / NST) - 1) & 1); RT_ACC(tr_prod_empty); }
+          __syncwarp();
+          // ---- plan the issuer's step (the previous tenant of this record was consumed NST steps ago) ----
+          {
+            Cmd &c = cmds[stage];
+            const uint32_t w = lane < RT_NACT ? tab.sched[q][lane] : 0u;
+            const int bb = (int)(w & 0xff);
+            const int pp = p + (int)((w >> 16) & 1);
+            const int gb = pp * NBLK + bb;
+            const bool valid = (w >> 18) && gb >= gb0 && gb < gb1;
+            const int lb = gb - gb0, slot = lb & (RT_SLOTS - 1);
+            const bool first = ((w >> 8) & 0xff) == 0, last = (w >> 17) & 1;
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid) & ((1u << RT_NACT) - 1);
+            // a run of consecutive accumulator slots starts at the first valid entry and where the ring wraps
+            const bool start = valid && (lane == 0 || !((vmask >> (lane - 1)) & 1) || slot == 0);
+            const uint32_t smask = __ballot_sync(0xffffffffu, start) & ((1u << RT_NACT) - 1);
+            if (lane < RT_NACT) {
+              c.wait_slot[lane] = (uint32_t)slot;
+              c.wait_par[lane] = (valid && first && lb >= RT_SLOTS) ? (uint32_t)((((lb / RT_SLOTS) - 1) & 1) | 2u) : 0u;   // bit 1: wait
+              c.done_slot[lane] = (valid && last) ? (uint32_t)slot | 8u : 0u;                                                 // bit 3: commit
+              if (start) {
+                const uint32_t above = ~((2u << lane) - 1);                       // entries after this one
+                const uint32_t stop = ((smask | ~vmask) & above) | (1u << RT_NACT);   // next start, first gap, or the end
+                const int cnt = (__ffs(stop) - 1) - lane;
+                const int r = __popc(smask & ((1u << lane) - 1));
+                c.d[r] = (uint32_t)(slot * RT_NC);
+                c.b_off[r] = (uint32_t)(lane * RT_NC);          // entry i's tile: 32 rows of 16 bytes = 32 address units
+                c.idesc[r] = idesc16 | ((uint32_t)((RT_NC * cnt) >> 3) << 17);
+              }
+            }
+            if (lane == 0) {
+              c.n_run = (uint32_t)__popc(smask);
+              c.b_lbo = tab.nact[q] * RT_NC;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t dst = smem_u32 + (uint32_t)stage * RT_STAGE, bar = tc_smem_u32(&full[stage]);
+            const uint32_t nb = tab.nact[q] * RT_TILE_BYTES;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)RT_X_BYTES + nb) : "memory");
+            const int x0 = g.pl_off + (T0 + st) * RT_SLAB;
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                         "l"(&map_h), "r"(x0), "r"(c0), "r"(bar)
                          : "memory");
-          if (++q == SP) q = 0;
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst + RT_X_BYTES / 2),
+                         "l"(&map_l), "r"(x0), "r"(c0), "r"(bar)
+                         : "memory");
+            if (nb)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + RT_X_BYTES),
+                           "l"(g.tiles + (size_t)tab.bq_off[q] * RT_TILE_BYTES), "r"(nb), "r"(bar)
+                           : "memory");
+          }
         }
       }
       __syncwarp();
     } else if (warp == RT_WORKERS / 32) {
-      // ---- issuer ----
+      // ---- issuer: executes the records the producer planned ----
       if (lane == 0) {
-        const uint32_t idesc16 = (1u << 4) | ((uint32_t)(RT_ROWS >> 4) << 24);   // f16 x f16 -> f32, M = 128
         // Matrix descriptors, K-major.  A (a plane's slab: 128 rows of 64 bytes, 64-byte swizzle as the
         // tensor copy wrote it): 8-row groups 512 B apart, layout type 4; a K step of 16 halfs is 32 bytes
         // further into the swizzle atom.  B (tap tiles, no swizzle, 16-byte core-matrix rows): 8-row groups
         // 128 B apart, chunks of K (32 * nact rows) * 16 B apart.  Version 1 in both.
         constexpr uint32_t A_HI = (512u >> 4) | (1u << 14) | (4u << 29), B_HI = (128u >> 4) | (1u << 14);
-        int p = p_first, q = q_first;
-        for (int st = 0; st < n_steps; ++st, advance(p, q)) {
+        for (int st = 0; st < n_steps; ++st) {
           const int stage = st % NST;
-          Ent e[RT_NACT];
-          active(p, q, e);
-          const uint32_t nact = tab.nact[q];
-          mbar_wait(&full[stage], (st / NST) & 1);
+          { RT_T0(); mbar_wait(&full[stage], (st / NST) & 1); RT_ACC(tr_iss_full); }
           asm volatile("tcgen05.fence::after_thread_sync;");
+          const Cmd &c = cmds[stage];   // read in place (shared memory): no dynamically indexed local copy
           const uint32_t xs_lo = ((smem_u32 + (uint32_t)stage * RT_STAGE) >> 4) & 0x3fff;
-          const uint32_t b_lbo = nact * RT_NC;                          // (32 nact rows * 16 B) >> 4
-          const uint32_t bs_lo = (((smem_u32 + (uint32_t)stage * RT_STAGE + RT_X_BYTES) >> 4) & 0x3fff) | (b_lbo << 16);
           // a block that starts here takes over an accumulator slot: its previous tenant must have
           // been read back (and cleared)
+          const uint32_t n_run = c.n_run, b_lbo = c.b_lbo;
+          const uint4 wp = *reinterpret_cast<const uint4 *>(c.wait_par), ws4 = *reinterpret_cast<const uint4 *>(c.wait_slot);
+          const uint4 dn = *reinterpret_cast<const uint4 *>(c.done_slot);
+          const uint32_t wpar[RT_NACT] = {wp.x, wp.y, wp.z, wp.w}, wslot[RT_NACT] = {ws4.x, ws4.y, ws4.z, ws4.w};
+          const uint32_t done[RT_NACT] = {dn.x, dn.y, dn.z, dn.w};
 #pragma unroll
           for (int i = 0; i < RT_NACT; ++i)
-            if (e[i].valid && e[i].first && e[i].lb >= RT_SLOTS) {
-              mbar_wait(&acc_empty[e[i].lb % RT_SLOTS], ((e[i].lb / RT_SLOTS) - 1) & 1);
+            if (wpar[i] & 2u) {
+              { RT_T0(); mbar_wait(&acc_empty[wslot[i]], wpar[i] & 1u); RT_ACC(tr_iss_acc); }
               asm volatile("tcgen05.fence::after_thread_sync;");
             }
-          // one MMA per K step and plane for every run of consecutive accumulator slots (entry i's
-          // tile sits at rows 32 i of the stage, its accumulator in slot lb % 8: a run ends where the
-          // ring of slots wraps)
-#pragma unroll
-          for (int i = 0; i < RT_NACT; ++i) {
-            if (!e[i].valid) continue;
-            const int slot0 = e[i].lb % RT_SLOTS;
-            if (i > 0 && e[i - 1].valid && slot0 != 0) continue;   // part of the run that started earlier
-            int cnt = 1;
-#pragma unroll
-            for (int k = 1; k < RT_NACT; ++k)
-              if (i + k < RT_NACT && cnt == k && e[(i + k) & (RT_NACT - 1)].valid && slot0 + k < RT_SLOTS) cnt = k + 1;
-            const uint32_t idesc = idesc16 | ((uint32_t)((RT_NC * cnt) >> 3) << 17);
-            const uint32_t d = tmem + slot0 * RT_NC;
-            const uint32_t b_lo = bs_lo + (uint32_t)(i * RT_NC);   // 32 rows of 16 bytes = 32 address units
+#ifdef SDR_RT_TRACE
+          const long long tr_m = clock64();
+#endif
+          const uint32_t bs_lo = (((smem_u32 + (uint32_t)stage * RT_STAGE + RT_X_BYTES) >> 4) & 0x3fff) | (b_lbo << 16);
+          for (uint32_t r = 0; r < n_run; ++r) {
+            const uint32_t d = tmem + c.d[r], b_lo = bs_lo + c.b_off[r], idesc = c.idesc[r];
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -270,10 +323,17 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
               }
             }
           }
+#ifdef SDR_RT_TRACE
+          const long long tr_c = clock64();
+          tr_rb_full += tr_c - tr_m;   // (issuer: MMA issue)
+#endif
           tc_commit(&empty[stage]);            // the stage may be refilled once these MMAs have read it
 #pragma unroll
-          for (int k = 0; k < RT_NACT; ++k)
-            if (e[k].valid && e[k].last) tc_commit(&acc_full[e[k].lb % RT_SLOTS]);
+          for (int i = 0; i < RT_NACT; ++i)
+            if (done[i] & 8u) tc_commit(&acc_full[done[i] & 7u]);
+#ifdef SDR_RT_TRACE
+          tr_prod_empty += clock64() - tr_c;   // (issuer: commits)
+#endif
         }
       }
       __syncwarp();
@@ -291,7 +351,7 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
         for (int k = 0; k < RT_NACT; ++k) {
           if (!e[k].valid || !e[k].last) continue;
           const int lb = e[k].lb, slot = lb % RT_SLOTS;
-          mbar_wait(&acc_full[slot], (lb / RT_SLOTS) & 1);
+          { RT_T0(); mbar_wait(&acc_full[slot], (lb / RT_SLOTS) & 1); RT_ACC(tr_rb_full); }
           asm volatile("tcgen05.fence::after_thread_sync;");
           uint32_t v[8], u[8];
           const uint32_t tcol = tmem + tlane + slot * RT_NC + half * 8;
@@ -345,6 +405,11 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
       }
     }
   }
+#ifdef SDR_RT_TRACE
+  if (blockIdx.x == 7 && lane == 0 && (warp == 0 || warp >= RT_WORKERS / 32))
+    printf("rt trace cta 7 warp %d: total %lld  producer waits empty %lld  issuer waits full %lld, acc_empty %lld  read-back waits acc_full %lld\n",
+           warp, clock64() - tr_begin, tr_prod_empty, tr_iss_full, tr_iss_acc, tr_rb_full);
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(RT_TMEM_COLS));
