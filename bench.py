@@ -321,7 +321,7 @@ def time_config(torch, sdr, args, mode, audio_channels, steps, warmup, dist, wor
             if nbytes % 192000:
                 raise SystemExit("--rds needs --blocks such that a capture is a multiple of 192000 B "
                                  "(mode 0: 15, 30, ...; mode 2: 12, 24, ...)")
-            rds = sdr.Rds(p, block_if=9600, max_pending_blocks=(steps + warmup) * (nbytes // 192000),
+            rds = sdr.Rds(p, block_if=9600, max_pending_blocks=(2 * steps + warmup) * (nbytes // 192000),   # timed pass + per-kernel pass
                           f32_fir=bool(getattr(args, "rds_f32", False)))
         n_pcm = p.pcm_count(nbytes)
         d_pcm = torch.zeros((per, n_pcm), dtype=torch.int16, device=dev)
