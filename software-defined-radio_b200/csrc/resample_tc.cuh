@@ -277,8 +277,10 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
       }
       __syncwarp();
     } else if (warp == RT_WORKERS / 32) {
-      // ---- issuer: executes the records the producer planned ----
-      if (lane == 0) {
+      // ---- issuer: executes the records the producer planned.  The whole warp walks the steps in
+      // lockstep and ONE ELECTED lane issues: under a plain `if (lane == 0)` ptxas wraps every
+      // tcgen05 instruction in an ELECT / BRA.U.ANY loop over "possibly different" operand values ----
+      {
         // Matrix descriptors, K-major.  A (a plane's slab: 128 rows of 64 bytes, 64-byte swizzle as the
         // tensor copy wrote it): 8-row groups 512 B apart, layout type 4; a K step of 16 halfs is 32 bytes
         // further into the swizzle atom.  B (tap tiles, no swizzle, 16-byte core-matrix rows): 8-row groups
@@ -307,6 +309,7 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
           const long long tr_m = clock64();
 #endif
           const uint32_t bs_lo = (((smem_u32 + (uint32_t)stage * RT_STAGE + RT_X_BYTES) >> 4) & 0x3fff) | (b_lbo << 16);
+          if (tc_elect_one()) {
           for (uint32_t r = 0; r < n_run; ++r) {
             const uint32_t d = tmem + c.d[r], b_lo = bs_lo + c.b_off[r], idesc = c.idesc[r];
 #pragma unroll
@@ -334,6 +337,8 @@ k_audio_resample_tc(const ResampleTcArgs g, const __grid_constant__ RtTables tab
 #ifdef SDR_RT_TRACE
           tr_prod_empty += clock64() - tr_c;   // (issuer: commits)
 #endif
+          }
+          __syncwarp();
         }
       }
       __syncwarp();

@@ -118,6 +118,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
   }
 }
+// True in exactly one lane of a converged warp (elect.sync).
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t p;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
       tc_smem_u32(bar)) : "memory");
