@@ -834,7 +834,7 @@ extern "C" int sdr_pipeline_create(const sdr_config *cfg_in, sdr_pipeline **out)
   std::vector<uint8_t> rt_tiles;
   // Tensor-core resampler for both custom-rate modes.  Its cost follows the INPUT rate (one pipeline
   // step per 32-sample slab), the quad resampler's the OUTPUT rate (101 multiply-adds per output).
-  // Measured on B200, 1024 captures x 16 blocks: mode 2 0.120 vs 0.245 ms; mode 3 0.377 vs 0.684 ms
+  // Measured on B200, 1024 captures x 16 blocks: mode 2 0.109 vs 0.245 ms; mode 3 0.350 vs 0.684 ms
   // (the front end's two plane stores instead of one float store cost it 0.03 ms there).
   if (p->resample && !p->stereo && cfg->variant == SDR_VARIANT_FAST && build_resample_tc(p, rt_tiles))
     p->audio_kernel = sdr_pipeline::AK_RS_TC;
