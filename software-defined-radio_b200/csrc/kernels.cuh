@@ -498,6 +498,32 @@ struct RowGeomIQ {   // positions in I/Q PAIRS (8 bytes); one LDS.128 = 2 pairs
   __device__ static __forceinline__ int thread_base(int t) { return ORIGIN + t * (G + PAD); }
 };
 
+// Window walk on PAIRS: R consecutive outputs of a decimate-by-D, T-tap FIR applied to both lanes of
+// a staged float2 stream (I and Q of the front end; mono-path and stereo-path input of the stereo audio
+// filter), newest sample first so that every accumulator sees its taps in ascending order.  `w` points
+// at the pair of the thread's first output's newest sample inside a RowGeomIQ row.
+template <int T, int D, int R, int HALO, typename Geom>
+__device__ __forceinline__ void fir_window_pairs(const float2 *__restrict__ w, const TapArray<taps_window(T)> &taps,
+                                                 f32x2_t (&acc)[R], f32x2_t one) {
+  constexpr int NEWEST = (R - 1) * D;
+  constexpr int C_HI = (HALO + NEWEST) / 2;
+  constexpr int C_LO = (HALO - (T - 1)) / 2;
+#pragma unroll
+  for (int c = C_HI; c >= C_LO; --c) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(w + Geom::off(2 * c - HALO));
+#pragma unroll
+    for (int j = 1; j >= 0; --j) {
+      const int e = 2 * c + j - HALO;
+      const f32x2_t x = j ? v.y : v.x;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int n = r * D - e;
+        if (n >= 0 && n < T) acc[r] = xmac2(acc[r], pack2(taps.h[n], taps.h[n]), x, one);
+      }
+    }
+  }
+}
+
 template <int T, int D, int R, int NT>
 struct RfIqCfg {
   static constexpr int HALO = round_up(T - 1 + D, 8);
@@ -596,26 +622,7 @@ k_rf_demod_iq(const RfArgs a, const __grid_constant__ TapArray<taps_window(T)> t
     f32x2_t acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0ull;
-    {
-      const float2 *w = xiq + Geom::thread_base(t);   // the thread's first output's newest sample (e = 0)
-      constexpr int NEWEST = (R - 1) * D;
-      constexpr int C_HI = (HALO + NEWEST) / 2;
-      constexpr int C_LO = (HALO - (T - 1)) / 2;
-#pragma unroll
-      for (int c = C_HI; c >= C_LO; --c) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(w + Geom::off(2 * c - HALO));
-#pragma unroll
-        for (int j = 1; j >= 0; --j) {
-          const int e = 2 * c + j - HALO;
-          const f32x2_t x = j ? v.y : v.x;
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int n = r * D - e;
-            if (n >= 0 && n < T) acc[r] = xmac2(acc[r], pack2(taps.h[n], taps.h[n]), x, one);
-          }
-        }
-      }
-    }
+    fir_window_pairs<T, D, R, HALO, Geom>(xiq + Geom::thread_base(t), taps, acc, one);
     float ai[R], aq[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {  // exact power-of-two scaling: (u8-128)/128
@@ -809,6 +816,67 @@ k_audio_fir(const AudioArgs a, const __grid_constant__ TapArray<taps_window(T)> 
           a.pcm[(size_t)b * a.pcm_stride + o + r] = pcm16(am[r]);
         }
         if (a.audio_filt) a.audio_filt[(size_t)b * a.tap_stride + o + r] = am[r];
+      }
+    }
+  }
+}
+
+// Stereo audio stage, packed form (EXACT variant): the mono-path and the stereo-path inputs of an
+// instant sit side by side in shared memory and share every tap, exactly like I and Q in the front
+// end: one FMUL2 + FFMA2 per tap and output for the two filters (project.cpp:219 and :257).
+template <int T, int D, int R, int NT>
+struct AudioPairCfg {
+  static constexpr int HALO = round_up(T - 1, 8);
+  static constexpr int TILE_OUT = NT * R;
+  static constexpr int TILE_IN = TILE_OUT * D;
+  using Geom = RowGeomIQ<D, R, NT, HALO>;
+  static constexpr size_t SMEM = (size_t)Geom::PAIRS * sizeof(float2);
+};
+
+template <int T, int D, int R, int NT>
+__global__ void __launch_bounds__(NT)
+k_audio_fir_pair(const AudioArgs a, const __grid_constant__ TapArray<taps_window(T)> taps, float one_rt) {
+  using Cfg = AudioPairCfg<T, D, R, NT>;
+  using Geom = typename Cfg::Geom;
+  constexpr int HALO = Cfg::HALO;
+  extern __shared__ __align__(16) float2 xms[];   // (mono-path input, stereo-path input = mixer output)
+  const int t = threadIdx.x;
+  const int b = blockIdx.y;
+  const int o_begin = blockIdx.x * a.outs_per_seg;
+  const int o_end = min(o_begin + a.outs_per_seg, a.n_out);
+  const float *drow = a.demod + (size_t)b * a.demod_stride + a.demod_off - a.delay;
+  const float *srow = a.stf + (size_t)b * a.stf_stride + a.hist_off;
+  const float *nrow = a.nco + (size_t)b * a.nco_stride + a.hist_off;
+  const long long n_in = (long long)a.n_out * D;
+  const f32x2_t one = pack2(one_rt, one_rt);
+
+  for (int o0 = o_begin; o0 < o_end; o0 += Cfg::TILE_OUT) {
+    __syncthreads();
+    const long long s0 = (long long)o0 * D - HALO;
+    for (int q = t; q < HALO + Cfg::TILE_IN; q += NT) {
+      const long long i = s0 + q;
+      // the history prefixes make negative indices valid down to -(T-1); HALO is rounded up past that
+      // for alignment and those first slots are never read by the filter
+      const bool ok = i < n_in && q >= HALO - (T - 1);
+      xms[Geom::pos(q - HALO)] = ok ? make_float2(drow[i], xmul(xmul(srow[i], nrow[i]), 2.0f)) : make_float2(0.0f, 0.0f);
+    }
+    __syncthreads();
+    f32x2_t acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0ull;
+    fir_window_pairs<T, D, R, HALO, Geom>(xms + Geom::thread_base(t), taps, acc, one);
+    const int o = o0 + t * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (o + r < o_end) {
+        float am, as;
+        unpack2(acc[r], am, as);
+        const float L = xadd(as, am), Rr = xsub(am, as);
+        int16_t *p = a.pcm + (size_t)b * a.pcm_stride + 2 * (size_t)(o + r);
+        p[0] = pcm16(L);
+        p[1] = pcm16(Rr);
+        if (a.stereo_final) a.stereo_final[(size_t)b * a.tap_stride + o + r] = as;
+        if (a.audio_filt) a.audio_filt[(size_t)b * a.tap_stride + o + r] = am;
       }
     }
   }

@@ -370,6 +370,18 @@ static int launch_audio(sdr_pipeline *p, AudioArgs a, cudaStream_t s) {
   int segs = pick_segments(a.n_out, Cfg::TILE_OUT, p->cfg.batch, &a.outs_per_seg);
   dim3 grid(segs, p->cfg.batch);
   prof_begin(p, "k_audio_fir", s);
+  if constexpr (STEREO && T == 101) {
+    if (!p->fma_aux && !p->scalar_fir) {   // EXACT stereo: the two filters in the lanes of one register pair
+      using PCfg = AudioPairCfg<T, D, R, NT>;
+      auto pk = k_audio_fir_pair<T, D, R, NT>;
+      static std::once_flag once2[16];
+      std::call_once(once2[p->cfg.device & 15], [&] {
+        cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCfg::SMEM);
+      });
+      pk<<<grid, NT, PCfg::SMEM, s>>>(a, make_taps<taps_window(T)>(p->h_audio), 1.0f);
+      return check_launch(p, "k_audio_fir");
+    }
+  }
   kern<<<grid, NT, SMEM, s>>>(a, make_taps<taps_window(T)>(p->h_audio));
   return check_launch(p, "k_audio_fir");
 }
