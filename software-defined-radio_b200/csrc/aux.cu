@@ -17,6 +17,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/sdr_b200.h"
@@ -299,9 +300,19 @@ struct Ch2Geom {
   __host__ __device__ static int x_pairs(int Tp) { return (NI + Tp - 1) * M; }
   // staged pair p (0 = first pair of the tile's window) -> float2 slot; one group's M pairs of an instant are
   // contiguous, and every R*M pairs the slot index skips M so that the groups of a warp hit different banks
-  __host__ __device__ static int xpos(int p) { return p + (p / (CH2_R * M)) * M; }
+  // ... and inside every chunk of 8 pairs the position is XOR-ed with bits of the chunk number: the
+  // staging stores put consecutive LANES on consecutive CHUNKS (64 bytes apart: a 16-way bank conflict
+  // without the swizzle, 483 M shared-memory wavefronts against 106 M ideal in profiles/r2/r3q); readers take
+  // whole chunks, for which the swizzle is a permutation
+  __host__ __device__ static int xpos(int p) {
+    const int ps = p ^ ((p >> 4) & 7);
+    return ps + (ps / (CH2_R * M)) * M;
+  }
+  // the transposed branch sums V reuse the staged input's memory (phase 1 has read all of it by then)
   __host__ __device__ static size_t smem_bytes(int Tp) {
-    return (size_t)(xpos(x_pairs(Tp)) + M + 8) * sizeof(float2) + (size_t)M * VROW * sizeof(float2) + (size_t)Tp * M * sizeof(float);
+    const int last = x_pairs(Tp) + 7;   // the swizzle moves a pair by less than 8 positions
+    const size_t xs_b = (size_t)(last + (last / (CH2_R * M)) * M + 8) * sizeof(float2), v_b = (size_t)M * VROW * sizeof(float2);
+    return (xs_b > v_b ? xs_b : v_b) + (size_t)((Tp * M + 3) / 4 * 4) * sizeof(float);
   }
 };
 
@@ -336,13 +347,13 @@ template <>
 __device__ __forceinline__ void ch_dft<1>(float2 (&)[1]) {}
 
 template <int M>
-__global__ void __launch_bounds__(CH2_NT) k_channelize2(const ChanArgs a, int Tp) {
+__global__ void __launch_bounds__(CH2_NT, 4) k_channelize2(const ChanArgs a, int Tp) {
   using Geo = Ch2Geom<M>;
   constexpr int R = CH2_R, NI = Geo::NI;
   extern __shared__ __align__(16) float2 ch_sm[];
-  float2 *xs = ch_sm;
-  float2 *V = xs + Geo::xpos(Geo::x_pairs(Tp)) + M + 8;
-  float *hs = reinterpret_cast<float *>(V + (size_t)M * Geo::VROW);
+  float *hs = reinterpret_cast<float *>(ch_sm);                    // taps
+  float2 *xs = ch_sm + (Tp * M + 3) / 4 * 2;                        // staged input ...
+  float2 *V = xs;                                                   // ... and, after phase 1, the branch sums
   const int w = blockIdx.y, n0 = blockIdx.x * NI, t = threadIdx.x;
   const int T = a.T, HW = M * T;
   const uint8_t *row = a.wide + (size_t)w * a.wide_stride;
@@ -397,20 +408,28 @@ __global__ void __launch_bounds__(CH2_NT) k_channelize2(const ChanArgs a, int Tp
     for (int j = 0; j < R; ++j) acc[j] = 0ull;
     // sample of instant (tile) i for this branch: staged pair (i + Tp-1) M + M-1-r
     const int col0 = (g * R + Tp - 1) * M + (M - 1 - r);
-    for (int q0 = 0; q0 < Tp; q0 += 4) {
-      // window: instants g*R - q0 - 3 .. g*R + R-1 - q0  ->  wv[0 .. R+2]
-      f32x2_t wv[R + 3];
+    // taps in chunks of CH (8 when the padded tap count allows, else 4): the window of R + CH - 1 samples is
+    // loaded once per chunk
+    auto chunks = [&](auto ch_tag) {
+      constexpr int CH = decltype(ch_tag)::value;
+      for (int q0 = 0; q0 < Tp; q0 += CH) {
+        // window: instants g*R - q0 - (CH-1) .. g*R + R-1 - q0  ->  wv[0 .. R+CH-2]
+        f32x2_t wv[R + CH - 1];
 #pragma unroll
-      for (int k = 0; k < R + 3; ++k)
-        wv[k] = *reinterpret_cast<const f32x2_t *>(xs + Geo::xpos(col0 + (k - 3 - q0) * M));
+        for (int k = 0; k < R + CH - 1; ++k)
+          wv[k] = *reinterpret_cast<const f32x2_t *>(xs + Geo::xpos(col0 + (k - (CH - 1) - q0) * M));
 #pragma unroll
-      for (int dq = 0; dq < 4; ++dq) {
-        const float hq = hs[(q0 + dq) * M + r];
-        const f32x2_t h2 = pack2(hq, hq);
+        for (int dq = 0; dq < CH; ++dq) {
+          const float hq = hs[(q0 + dq) * M + r];
+          const f32x2_t h2 = pack2(hq, hq);
 #pragma unroll
-        for (int j = 0; j < R; ++j) acc[j] = fma2(acc[j], h2, wv[j + 3 - dq]);
+          for (int j = 0; j < R; ++j) acc[j] = fma2(acc[j], h2, wv[j + (CH - 1) - dq]);
+        }
       }
-    }
+    };
+    if (Tp % 8 == 0) chunks(std::integral_constant<int, 8>{});
+    else chunks(std::integral_constant<int, 4>{});
+    __syncthreads();   // every thread has read its samples: the staged input's memory becomes V
 #pragma unroll
     for (int j = 0; j < R; ++j)
       *reinterpret_cast<f32x2_t *>(V + (size_t)r * Geo::VROW + Geo::vcol(g * R + j)) = acc[j];
