@@ -268,8 +268,7 @@ def test_tc_resampler_wide_batch_and_streaming(sdr, orc, mode):
         whole = p.process_host(iq)
         audio = {c: p.tap("audio_filt", c) for c in (0, 5, 127, 128, 129)}
         assert "k_audio_resample" in p.kernel_times()
-        # mode 2 runs the tensor-core resampler (the front end then also writes the fp16 planes);
-        # mode 3 stays on the quad kernel (pipeline.cu: measured, no gain there)
+        # both custom-rate modes run the tensor-core resampler (the front end then writes the fp16 planes)
         p.keep_taps(False)
         p.reset()
         parts = [p.process_host(np.ascontiguousarray(iq[:, a:b])) for a, b in zip(cuts[:-1], cuts[1:])]
@@ -279,3 +278,39 @@ def test_tc_resampler_wide_batch_and_streaming(sdr, orc, mode):
         assert snr_db(got, want["audio_filt"]) >= 100.0, (c, snr_db(got, want["audio_filt"]))
         d = np.abs(whole[c].astype(np.int32) - want_pcm.astype(np.int32))
         assert int(d.max()) <= 1, f"capture {c}: PCM differs by {int(d.max())} LSB"
+
+
+@pytest.mark.parametrize("mode", [2, 0])
+def test_many_short_device_calls_back_to_back(sdr, orc, mode):
+    """The fast mono path's kernels are launched with programmatic dependence (each may be scheduled
+    before its predecessor finishes and waits for it itself).  Dozens of granule-sized calls enqueued back
+    to back on one stream, nothing but the launches in between -- every kernel is a few microseconds, so
+    the overlap windows are as large as they get relative to the work -- must give the bits of one call."""
+    import torch
+    B = 257
+    gran = sdr.mode_info(mode, 1).granule_bytes
+    per = gran * (1 if mode == 2 else 16)
+    bb = siggen.MODES[mode]["block_bytes"]
+    calls = (6 if mode == 2 else 1) * bb // per          # whole reference blocks (the oracle's unit): 42 / 64 calls
+    n = per * calls
+    src = siggen.make_batch(6, mode, n // bb, "stereo")[:, :n]
+    iq = np.ascontiguousarray(np.tile(src, (B // 6 + 1, 1))[:B])
+    for c in range(B):
+        iq[c] = np.roll(iq[c], 2 * 17 * c)
+    d_iq = torch.from_numpy(iq).cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    with sdr.Pipeline(mode=mode, channels=1, batch=B, variant=sdr.VARIANT_FAST, max_bytes_per_channel=n) as p:
+        n_pcm = p.pcm_count(n)
+        one = torch.zeros((B, n_pcm), dtype=torch.int16, device="cuda")
+        p.process_device(d_iq.data_ptr(), d_iq.stride(0), n, one.data_ptr(), one.stride(0), s)
+        torch.cuda.synchronize()
+        p.reset()
+        many = torch.zeros_like(one)
+        k = p.pcm_count(per)
+        for i in range(calls):
+            p.process_device(d_iq.data_ptr() + i * per, d_iq.stride(0), per, many.data_ptr() + 2 * i * k, many.stride(0), s)
+        torch.cuda.synchronize()
+    assert torch.equal(one, many)
+    want, _ = orc.run_chain(iq[B - 1], mode, 1, keep_taps=False)
+    d = np.abs(one[B - 1].cpu().numpy().astype(np.int32) - want[:n_pcm].astype(np.int32))
+    assert int(d.max()) <= 1
