@@ -31,7 +31,11 @@
 //    all threads: 48 LDGSTS.128 per step at ~32 cycles each on the SM's load/store unit were the
 //    kernel's whole run time, profiles/r2 -- and generic-proxy writes need a proxy fence before the
 //    tensor core may read them; the asynchronous-proxy copies need neither.)
-//  * issuer (one thread): a small MMA costs a fixed 68 cycles whatever N <= 128 is
+//    The same warp PLANS each step for the issuer (lane i decodes schedule entry i, two votes give the
+//    runs of adjacent accumulator slots) and leaves an 80-byte record next to the stage: the issuer's
+//    own instruction stream is the kernel's critical path, the producer mostly waits.
+//  * issuer (one warp in lockstep, tcgen05 instructions under elect.sync so that ptxas emits them
+//    without its ELECT / BRA.U.ANY serialisation loops): a small MMA costs a fixed 68 cycles whatever N <= 128 is
 //    (tools/ubench_umma_smalln.cu), so MMAs are made as wide as the schedule allows: a block's
 //    tile holds hh and hl side by side (32 accumulator columns: sum x*hh and sum x*hl, added in the
 //    read-back), the active blocks' tiles are adjacent, and ONE MMA per K step and plane
