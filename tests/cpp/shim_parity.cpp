@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <random>
+#include <stdexcept>
 #include <vector>
 
 #include "dropin/filter.h"
@@ -79,6 +80,18 @@ int main() {
       expect_same("convolveBlockResampleFIR", y, wy);
       expect_same("resampler state", st, ost);
     }
+  }
+  {
+    // a state vector the C ABI cannot honour (it assumes h.size() - 1 floats) is refused, not overrun
+    std::vector<float> x = randv(64), y, bad_state(7, 0.0f);
+    bool threw = false;
+    try {
+      convolveBlockFIR(y, x, pilot, bad_state);
+    } catch (const std::invalid_argument &) {
+      threw = true;
+    }
+    std::printf("%-34s %s\n", "state of the wrong size refused", threw ? "ok" : "NOT REFUSED");
+    if (!threw) ++failures;
   }
   std::printf("%s\n", failures ? "FAILED" : "ALL OK");
   return failures ? 1 : 0;

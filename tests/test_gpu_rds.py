@@ -342,3 +342,16 @@ def test_rds_f32_fir_experiment(sdr, orc):
     with open(os.path.join(out, "rds_f32_experiment.json"), "w") as f:
         json.dump(record, f, indent=1)
     print("RDS f32-FIR experiment:", json.dumps(record))
+
+
+def test_detaching_the_rds_chain_restores_the_pipeline_granule(sdr):
+    """Attaching an RDS follower makes a call cover whole RDS blocks (the granule grows to 192000 B);
+    destroying it must give the pipeline its own granule back: a 100-byte call works again."""
+    with sdr.Pipeline(mode=0, channels=1, batch=2, max_bytes_per_channel=192000) as p:
+        base = p.info.granule_bytes
+        with sdr.Rds(p, block_if=9600) as r:
+            assert r.info.block_bytes == 192000
+            with pytest.raises(sdr.SdrError):
+                p.process_host(np.full((2, base * 3), 128, np.uint8))      # not a whole RDS block
+        pcm = p.process_host(np.full((2, base * 3), 128, np.uint8))         # fine again after the detach
+        assert pcm.shape == (2, p.pcm_count(base * 3))
