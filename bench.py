@@ -541,13 +541,31 @@ def time_channelizer(torch, sdr, peak, M=16, T=8, W=64, blocks=16, steps=5, warm
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
+    # parity on the bench's own input, outside the timed region: a fresh bank (empty history) over the first
+    # 2 MiB of wideband row 0 against the double-precision CPU oracle (oracle/aux_oracle.c; test infrastructure)
+    parity = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import auxlib
+        n_chk = 2 * M * 65536
+        wide0 = d_wide[0, :n_chk].cpu().numpy()
+        with sdr.Channelizer(M, T, n_wide=1, device=dev.index, gain=1.0) as ch:
+            h = ch.prototype()
+            got = ch.process_host(wide0[None, :])
+        want = auxlib.channelize(wide0, M, h, 1.0)
+        dd = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        parity = {"parity_checked": bool(int(dd.max()) <= 1), "max_abs_lsb": int(dd.max()),
+                  "mismatch_frac": float(np.mean(dd != 0)), "values": int(dd.size),
+                  "bar": "<= 1 LSB of the 8-bit output vs the double-precision oracle (single vs double at rounding boundaries)"}
+    except Exception as e:   # the check must not take the measurement down
+        parity = {"parity_checked": False, "error": str(e)[:200]}
     pairs = W * nbytes_wide // 2
     gbs = pairs * 4 / (ms * 1e-3) / 1e9
     return {"what": f"SURVEY 8f3 channeliser: {W} wideband captures ({M} x 2.4 MS/s) -> {W * M} receiver inputs "
                     f"({blocks} reference blocks each) in HBM, {T} taps per branch",
             "value": pairs / (ms * 1e-3) / 1e6, "unit": "wideband input I/Q MS/s (device-timed)", "ms_per_step": ms,
             "steps": steps, "warmup": warmup, "algorithmic_bytes_per_pair": 4, "achieved_gbs": gbs,
-            "frac_of_hbm_peak": gbs / peak, "gpu_launches": 2 * steps}
+            "frac_of_hbm_peak": gbs / peak, "gpu_launches": 2 * steps, "parity": parity}
 
 
 def with_args(args, **kw):

@@ -11,7 +11,7 @@ for k, v in (d.get("other_configs") or {}).items():
     if "error" in v:
         print(" ", k, "ERROR", v["error"]); continue
     if "achieved_gbs" in v:
-        print(f"  {k:26s} {v['value']/1e3:8.1f} GS/s {v['ms_per_step']:8.3f} ms  {v['achieved_gbs']:.0f} GB/s = {v['frac_of_hbm_peak']:.3f} of HBM peak"); continue
+        print(f"  {k:26s} {v['value']/1e3:8.1f} GS/s {v['ms_per_step']:8.3f} ms  {v['achieved_gbs']:.0f} GB/s = {v['frac_of_hbm_peak']:.3f} of HBM peak  parity {(v.get('parity') or {}).get('parity_checked')}/{(v.get('parity') or {}).get('max_abs_lsb')}"); continue
     c = v.get("fp32_pipe_ceiling", {})
     print(f"  {k:26s} {v['value']/1e3:8.1f} GS/s {v['ms_per_step']:8.3f} ms  hbm {v['whole_step_frac']:.4f}  {v['variant']:11s} parity {v['parity']['parity_checked']}/{v['parity']['max_abs_lsb']}"
           + (f"  fp32-ceiling frac {c['frac_of_ceiling']:.3f}" if c else ""))
